@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE ONLY — generates ``tests/golden/*.npz`` by running the UNMODIFIED
+reference (``/root/reference``) on CPU in the build container.
+
+    python -m oracle.make_golden            # regenerates every fixture
+
+The reference ships no golden vectors, so these fixtures are what pins
+both the oracle restatement (``oracle/psld_oracle.py``) and the CUDA path.  Inputs are
+reproducible from seeds alone (``oracle/weights.py``), so fixtures hold outputs only
+(plus the small inputs, for convenience).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import NoiseBank, load_reference, reference_time_grid  # noqa: E402
+from oracle.weights import fill_state_dict, noise_bank, prior  # noqa: E402
+from psld_b200.config import celeba64_config, cifar10_config, mid_config, tiny_config  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def ref_net(R, cfg, seed=0):
+    net = R.NCSNpp(cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = fill_state_dict(shapes, seed)
+    net.load_state_dict(sd)
+    return net, sd
+
+
+# ---------------------------------------------------------------- scalar known answers
+def golden_scalars(R):
+    rows = []
+    combos = [(4.01, 0.01, 8.0, 8.0, "lower"), (4.02, 0.02, 8.0, 8.0, "lower"),
+              (4.005, 0.005, 8.0, 8.0, "lower"), (4.0, 0.0, 8.0, 8.0, "lower"),
+              (4.02, 0.02, 0.5, 12.0, "lower"), (4.01, 0.01, 8.0, 8.0, "upper")]
+    for nu, ga, b0, b1, mode in combos:
+        cfg = tiny_config()
+        cfg.model.sde.update(nu=nu, gamma=ga, beta_min=b0, beta_max=b1, decomp_mode=mode)
+        sde = R.PSLD(cfg)
+        S = R.get_module("samplers", "sscs_sde")(cfg, sde, None)
+        for t, dt in [(0.0, 1e-3), (0.25, 2e-3), (0.5, 1e-2), (0.9, 5e-4), (0.998, 1e-3)]:
+            tt = torch.tensor([t], dtype=torch.float64)
+            h = torch.tensor(dt / 2, dtype=torch.float64)
+            # mean 2x2 from unit vectors
+            e = torch.zeros(1, 2, 1, 1, dtype=torch.float64)
+            ex = e.clone(); ex[0, 0] = 1.0
+            em = e.clone(); em[0, 1] = 1.0
+            mx = S._mean(ex, tt, h).flatten()      # (a_xx, a_mx)
+            mm = S._mean(em, tt, h).flatten()      # (a_xm, a_mm)
+            var = S._var(tt, h)
+            c = sde.get_coeff(var)
+            tau = torch.tensor([1.0 - t], dtype=torch.float64)
+            cov = sde._cov(0, sde.mm_0, tau)
+            ic = sde.get_inv_coeff(cov)
+            rows.append([nu, ga, b0, b1, 0.0 if mode == "lower" else 1.0, t, dt,
+                         mx[0].item(), mm[0].item(), mx[1].item(), mm[1].item(),
+                         *[float(v) for v in var], *[float(v) for v in c],
+                         *[float(v) for v in cov], *[float(v) for v in ic],
+                         float(sde.beta_t(tau)), sde.m_inv, sde.m, sde.mm_0])
+    cols = ("nu gamma beta0 beta1 upper t dt a_xx a_xm a_mx a_mm hxx hxm hmm c11 c12 c21 c22 "
+            "XX XM MM i11 i12 i21 i22 beta_tau m_inv m mm_0").split()
+    _save("scalars.npz", table=np.asarray(rows, dtype=np.float64), columns=np.asarray(cols))
+
+
+# ---------------------------------------------------------------- upfirdn2d
+def golden_upfirdn(R):
+    r = np.random.default_rng(7)
+    x = torch.from_numpy(r.standard_normal((2, 5, 8, 8)).astype(np.float32))
+    k = np.outer([1, 3, 3, 1], [1, 3, 3, 1]).astype(np.float32)
+    k /= k.sum()
+    kt = torch.from_numpy(k)
+    out = {"x": x.numpy(), "k": k}
+    for name, (kk, up, down, p0, p1) in {
+        "down": (kt, 1, 2, 1, 1), "up": (kt * 4, 2, 1, 2, 1), "pad": (kt, 1, 1, 2, 2),
+        "generic": (kt, 2, 3, 3, 0), "crop": (kt, 1, 1, -1, 2),
+    }.items():
+        y = R.upfirdn2d_native(x, kk, up, up, down, down, p0, p1, p0, p1)
+        out["y_" + name] = y.numpy()
+        out["arg_" + name] = np.asarray([up, down, p0, p1, 4.0 if name == "up" else 1.0])
+    _save("upfirdn.npz", **out)
+
+
+# ---------------------------------------------------------------- network forwards
+def golden_forward(R, cfg, fname, B, seed=0):
+    net, _ = ref_net(R, cfg, seed)
+    r = np.random.default_rng([11, seed])
+    H = cfg.data.image_size
+    x = torch.from_numpy((r.standard_normal((B, 6, H, H)) * 1.5).astype(np.float32))
+    t = torch.from_numpy(np.asarray([0.731, 0.0123, 1.0, 1e-3][:B], dtype=np.float32))
+    with torch.no_grad():
+        y = net(x, t)
+    _save(fname, x=x.numpy(), t=t.numpy(), y=y.numpy(), seed=np.asarray(seed))
+
+
+def golden_modules(R):
+    """Single-module outputs (ResnetBlockBigGANpp plain/down/up/cat, AttnBlockpp,
+    pyramid Downsample) on seeded inputs, taken with forward hooks from the tiny net."""
+    cfg = tiny_config()
+    net, _ = ref_net(R, cfg, 0)
+    want = {}
+    lp = R.layerspp
+    seen = set()
+    for i, m in enumerate(net.all_modules):
+        if isinstance(m, (lp.ResnetBlockBigGANpp, lp.AttnBlockpp, lp.Downsample)):
+            kind = (type(m).__name__, getattr(m, "up", 0), getattr(m, "down", 0),
+                    getattr(m, "in_ch", 0) != getattr(m, "out_ch", 0))
+            if kind not in seen:         # one instance of every distinct kind
+                seen.add(kind)
+                want[i] = m
+    rec = {}
+
+    def mk(i):
+        def hook(mod, inp, out):
+            rec[f"in_{i}"] = inp[0].detach().numpy().copy()
+            rec[f"out_{i}"] = out.detach().numpy().copy()
+        return hook
+
+    hs = [m.register_forward_hook(mk(i)) for i, m in want.items()]
+    r = np.random.default_rng(5)
+    x = torch.from_numpy(r.standard_normal((1, 6, 32, 32)).astype(np.float32))
+    t = torch.tensor([0.3])
+    with torch.no_grad():
+        net(x, t)
+    for h in hs:
+        h.remove()
+    rec["x"] = x.numpy(); rec["t"] = t.numpy()
+    rec["kinds"] = np.asarray([f"{i}:{type(m).__name__}:{int(getattr(m, 'up', False))}{int(getattr(m, 'down', False))}"
+                               for i, m in want.items()])
+    _save("modules_tiny.npz", **rec)
+
+
+# ---------------------------------------------------------------- samplers
+def golden_sampler(R, cfg, fname, B, seed_w=0, seed_p=1, seed_n=2, keep=2, score="net"):
+    sde = R.PSLD(cfg)
+    H = cfg.data.image_size
+    name = cfg.evaluation.sampler.name
+    if score == "net":
+        net, _ = ref_net(R, cfg, seed_w)
+    else:
+        net = fake_score
+    ts, n = reference_time_grid(cfg)
+    per = 2 if name == "sscs_sde" else 1
+    nb = noise_bank(per * n, (B, 6, H, H), seed_n)
+    u0 = prior((B, 3, H, H), float(np.sqrt(sde.m)), seed_p)
+    S = R.get_module("samplers", name)(cfg, sde, net)
+    stats, states = [], {}
+    probe = sorted(set([0, 1, n // 2, n - 1]))
+    orig = S.predictor_update_fn
+    ctr = {"i": 0}
+
+    def wrapped(u, t, dt):
+        r = orig(u, t, dt)
+        un = r[0] if isinstance(r, tuple) else r
+        i = ctr["i"]; ctr["i"] += 1
+        stats.append([un.sum().item(), un.abs().sum().item(), un.abs().max().item(),
+                      (un.double() ** 2).sum().item()])
+        if i in probe:
+            states[f"state_{i}"] = un[:keep].double().numpy().copy()
+        return r
+
+    S.predictor_update_fn = wrapped
+    with NoiseBank(nb):
+        out = S.sample(u0.clone(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    _save(fname, final=out.double().numpy(), stats=np.asarray(stats), ts=ts.numpy(),
+          n=np.asarray(n), seeds=np.asarray([seed_w, seed_p, seed_n]), B=np.asarray(B),
+          probe=np.asarray(probe), **states)
+
+
+def fake_score(u, t):
+    """Deterministic smooth stand-in score network (tests the sampler algebra alone)."""
+    return (torch.tanh(u * 0.3) * 0.7 + 0.1 * torch.sin(torch.roll(u, 1, 1))) * t.view(-1, 1, 1, 1)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    R = load_reference()
+    golden_scalars(R)
+    golden_upfirdn(R)
+    golden_modules(R)
+    golden_forward(R, tiny_config(), "forward_tiny.npz", B=4)
+    golden_forward(R, mid_config(), "forward_mid.npz", B=2)
+    c = cifar10_config(); c.model.score_fn.init_scale = 1.0
+    golden_forward(R, c, "forward_cifar10.npz", B=1)
+    c = celeba64_config(); c.model.score_fn.init_scale = 1.0
+    golden_forward(R, c, "forward_celeba64.npz", B=1)
+    # BASELINE.json configs[0]: tiny net, EM, 100 steps, 8 samples
+    golden_sampler(R, tiny_config(), "sampler_tiny_em100.npz", B=8)
+    golden_sampler(R, tiny_config(sampler="sscs_sde"), "sampler_tiny_sscs100.npz", B=8)
+    # sampler algebra alone (fake score), incl. varying beta, quadratic stride, score_m mode
+    for tag, kw, sd in [
+        ("sscs_fake_uniform", dict(sampler="sscs_sde", n_discrete_steps=50), {}),
+        ("em_fake_uniform", dict(sampler="em_sde", n_discrete_steps=50), {}),
+        ("sscs_fake_quad", dict(sampler="sscs_sde", n_discrete_steps=40, stride_type="quadratic"),
+         dict(nu=4.02, gamma=0.02, beta_min=0.5, beta_max=12.0)),
+        ("em_fake_quad", dict(sampler="em_sde", n_discrete_steps=40, stride_type="quadratic"),
+         dict(nu=4.02, gamma=0.02, beta_min=0.5, beta_max=12.0)),
+        ("sscs_fake_nodenoise", dict(sampler="sscs_sde", n_discrete_steps=30, denoise=False), {}),
+    ]:
+        cfg = tiny_config(**kw)
+        cfg.model.sde.update(sd)
+        cfg.data.image_size = 8
+        golden_sampler(R, cfg, f"sampler_{tag}.npz", B=3, keep=3, score="fake")
+
+
+if __name__ == "__main__":
+    main()
