@@ -1,0 +1,262 @@
+/*
+ * psld_b200.h — C ABI of libpsld_b200.so: hand-written sm_100a CUDA kernels for the
+ * reverse-time sampling hot path of PSLD (mandt-lab/PSLD).
+ *
+ * Boundary being replaced (reference file:line, relative to the reference repo):
+ *   - the only native boundary the reference has is a pybind11 torch extension that is
+ *     JIT-compiled at import: `Tensor upfirdn2d(const Tensor& input, const Tensor& kernel,
+ *     int up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)`
+ *     (main/models/score_fn/song_sde/op/upfirdn2d.cpp:12-23, kernel in
+ *     op/upfirdn2d_kernel.cu:107-369)  ->  psld_upfirdn2d / PSLD_OP_FIR below;
+ *   - everything else on the path is PyTorch-eager code that this library replaces
+ *     kernel by kernel; each entry point cites the reference lines it computes.
+ *
+ * Conventions: plain `extern "C"`, no torch/C++ types in signatures.
+ * Every function returns 0 on success or a negative PSLD_E* code and never throws;
+ * psld_last_error() returns a thread-local message for the last failure.  All data
+ * pointers are DEVICE pointers owned by the caller unless a parameter says "host".
+ * Every launch goes to the explicit `stream` (a cudaStream_t passed as void*).  The
+ * library allocates no device memory; scratch buffers are passed in by the caller.
+ */
+#ifndef PSLD_B200_H_
+#define PSLD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSLD_B200_VERSION 100
+
+/* error codes */
+#define PSLD_OK 0
+#define PSLD_EINVAL (-1)      /* bad argument / unsupported shape             */
+#define PSLD_ECUDA (-2)       /* CUDA runtime / driver error                  */
+#define PSLD_EUNSUPPORTED (-3)/* op not eligible for the requested engine     */
+#define PSLD_ENUMERIC (-4)    /* NaN in the 2x2 factorisation (psld.py:171)   */
+
+/* element types */
+#define PSLD_F32 0
+#define PSLD_BF16 1
+#define PSLD_F64 2
+
+/* tensor layouts */
+#define PSLD_NHWC 0
+#define PSLD_NCHW 1
+
+typedef void* psld_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define PSLD_API __attribute__((visibility("default")))
+#else
+#define PSLD_API
+#endif
+
+PSLD_API int psld_version(void);
+PSLD_API const char* psld_last_error(void);
+/* sm count / compute capability of the current device */
+PSLD_API int psld_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * 1. Fused phase-space update (SSCS / Euler-Maruyama / denoise)
+ *
+ * State u = [x; m], NCHW [B, 2C, H, W]; one "pair" = (x[b,j], m[b,j]), j in [0, C*H*W).
+ * Coefficients are identical for every batch element and are
+ * computed once on the host in float64 (psld_b200/schedule.py).
+ * ---------------------------------------------------------------------------------- */
+
+/* u' = A u + L z   — SSCSSampler.analytical_dynamics (main/samplers/sde.py:294-312):
+ * A from _mean (sde.py:236-263), L = get_coeff(_var) (sde.py:265-292, psld.py:154-186) */
+typedef struct {
+  double a_xx, a_xm, a_mx, a_mm; /* x' = a_xx x + a_xm m ;  m' = a_mx x + a_mm m      */
+  double c11, c12, c21, c22;     /* x' += c11 zx + c12 zm ; m' += c21 zx + c22 zm     */
+} psld_half_step;
+
+/* score = -L^{-T} eps with L^{-T} rounded to fp32 (main/models/sde/psld.py:230-260);
+ * SSCS:  x += k_x (s_x + x) ; m += k_m (s_m + m_inv m)     (sde.py:314-329)
+ * EM  :  u += fbar dt + g sqrt(dt) z,  fbar = -f + g^2 score (psld.py:330-364, sde.py:16-26)
+ * mode: 0 = score_xm (eps has 2C channels), 1 = score_m (eps has C channels, s_x = 0),
+ *       2 = score_x  (eps has C channels, s_m = 0)                                     */
+typedef struct {
+  float li11, li12, li21, li22;  /* L^{-T} entries, already rounded to fp32             */
+  int32_t mode;
+  int32_t _pad;
+  double k_x;      /* SSCS: dt*gamma*beta(tau)          EM: unused                      */
+  double k_m;      /* SSCS: dt*M*nu*beta(tau)           EM: unused                      */
+  double m_inv;
+  /* EM / denoise (reverse_sde): */
+  double half_beta, gamma, nu;   /* f_x = hb (m_inv m - gamma x); f_m = hb (-nu m - x) */
+  double g2_x, g2_m;             /* g_x^2, g_m^2                                        */
+  double dt;                     /* EM: dt ; denoise: eps                               */
+  double gs_x, gs_m;             /* g_x sqrt(dt), g_m sqrt(dt)  (0 for denoise)         */
+} psld_score_step;
+
+/* stage bits for psld_sscs_update */
+#define PSLD_STAGE_HALF_A 1 /* u <- A_a u + L_a z_a            (first half of a step) */
+#define PSLD_STAGE_SCORE 2  /* Euler score step with eps                              */
+#define PSLD_STAGE_HALF_B 4 /* second half of the step                                */
+#define PSLD_STAGE_HALF_C 8 /* first half of the NEXT step, fused into the same pass  */
+
+typedef struct {
+  psld_half_step half_a, half_b, half_c;
+  psld_score_step score;
+} psld_sscs_coeffs;
+
+/*
+ * One pass over HBM applying the selected stages in order A -> SCORE -> B -> C.
+ *   u_in / u_out : state, `state_dtype` PSLD_F64 (reference-faithful) or PSLD_F32; may alias.
+ *   net_in       : optional fp32 copy of u_out (the next score_fn input, sde.py:320), or NULL.
+ *   eps          : fp32 NCHW network output [B, 2C or C, H, W]; required with STAGE_SCORE.
+ *   z_a/z_b/z_c  : pre-drawn fp32 N(0,1) noise [B,2C,H,W] per stage (parity mode).  When a
+ *                  needed pointer is NULL the kernel draws from Philox4x32-10 keyed by
+ *                  (seed, stream id = stage slot of `step`, pair index)  (throughput mode).
+ *   B, chw       : batch and C*H*W (pairs per sample); chw % 4 == 0.
+ * Algorithmic HBM bytes per pair (fp32 state): 8 (u in) + 8 (u out) + 8 (eps) + 8 per
+ * pre-drawn noise tensor [+ 8 net_in]; Philox mode drops the noise reads.
+ */
+PSLD_API int psld_sscs_update(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                     const float* eps, const float* z_a, const float* z_b, const float* z_c,
+                     const psld_sscs_coeffs* coeffs /* host */, int stages,
+                     uint64_t seed, uint64_t step, int64_t B, int64_t chw,
+                     psld_stream_t stream);
+
+/* EulerMaruyamaSampler.predictor_update_fn (sde.py:16-26) and both samplers'
+ * denoising_fn (sde.py:28-36, 338-348; pass z = NULL and use_philox = 0, gs_* = 0). */
+PSLD_API int psld_em_update(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                   const float* eps, const float* z, int use_philox,
+                   const psld_score_step* coeffs /* host */, uint64_t seed, uint64_t step,
+                   int64_t B, int64_t chw, psld_stream_t stream);
+
+/* PSLD.prior_sampling (psld.py:366-370) on device: x ~ N(0,1), m ~ N(0, M); fp32 NCHW. */
+PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
+                      psld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 2. NCSN++ score network ops.  Activations are NHWC inside the network, element type
+ *    PSLD_F32 (reference-faithful path) or PSLD_BF16 (tensor-core path).
+ *    A network forward is a "program": a flat array of psld_op records built once by the
+ *    host (psld_b200/ncsnpp.py) and replayed by psld_program_run.
+ * ---------------------------------------------------------------------------------- */
+#define PSLD_OP_LAYOUT 1 /* NCHW f32 <-> NHWC T                                        */
+#define PSLD_OP_TEMB 2   /* Fourier/positional embedding + MLP + all Dense_0 projections */
+#define PSLD_OP_GN 3     /* GroupNorm (+SiLU) over a virtual channel-concat of 2 inputs  */
+#define PSLD_OP_FIR 4    /* upfirdn2d                                                   */
+#define PSLD_OP_CONV 5   /* conv3x3 / conv1x1 / NIN / strided conv as implicit GEMM     */
+#define PSLD_OP_ATTN 6   /* softmax(q k^T / sqrt(C)) v                                  */
+
+#define PSLD_ENGINE_SIMT 0 /* fp32 FFMA implicit GEMM (any shape)                       */
+#define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0)  */
+
+#define PSLD_OP_NI 28
+#define PSLD_OP_NF 24
+#define PSLD_OP_NP 8
+
+/* Generic op record.  Slot meaning per kind is documented next to each PSLD_*_ index
+ * enum below; unused slots must be zero.                                              */
+typedef struct {
+  int32_t kind;
+  int32_t engine;
+  int32_t i[PSLD_OP_NI];
+  float f[PSLD_OP_NF];
+  const void* in[PSLD_OP_NP];
+  void* out[PSLD_OP_NP];
+  void* aux; /* library-owned per-op host state (TMA descriptors); set by psld_op_prepare */
+} psld_op;
+
+/* --- PSLD_OP_LAYOUT: in[0] -> out[0].  i: N, C, HW, dir (0: NCHW f32 -> NHWC T, 1: NHWC T
+ *     -> NCHW f32), dtype (T) */
+enum { PSLD_LAYOUT_N = 0, PSLD_LAYOUT_C, PSLD_LAYOUT_HW, PSLD_LAYOUT_DIR, PSLD_LAYOUT_DTYPE };
+
+/* --- PSLD_OP_TEMB (ncsnpp.py:292-311, layerspp.py:32-41,262-263, layers.py:500-514):
+ *   in[0] = time [nt] f32 (forward time tau, or log(tau) when i[LOGGED]=1)
+ *   in[1] = Fourier W [nf] ; in[2],in[3] = Linear0 W [4nf, E], b ; in[4],in[5] = Linear1 W,b
+ *   in[6],in[7] = concatenated Dense_0 W [totalC, 4nf], b [totalC]
+ *   out[0] = proj [nt, totalC] f32 (Dense_0(SiLU(temb)) of every resblock)
+ *   out[1] = scratch f32 [nt, E + 8nf]
+ *   i: NT, NF, EMB (0 fourier, 1 positional), TOTALC, LOGGED                           */
+enum { PSLD_TEMB_NT = 0, PSLD_TEMB_NF, PSLD_TEMB_EMB, PSLD_TEMB_TOTALC, PSLD_TEMB_LOGGED };
+
+/* --- PSLD_OP_GN (nn.GroupNorm(min(C/4,32), C, eps=1e-6) [+ SiLU]; layerspp.py:219,231,67):
+ *   in[0] = x1 [N,HW,C1], in[1] = x2 [N,HW,C2] or NULL (virtual torch.cat([x1,x2],1),
+ *   ncsnpp.py:374), in[2] = gamma [C], in[3] = beta [C];  out[0] = y [N,HW,C1+C2],
+ *   out[1] = scratch, >= N*NCHUNK*G*2 doubles
+ *   i: N, HW, C1, C2, G, SILU, IN_DTYPE, OUT_DTYPE, NCHUNK ; f[0] = eps                 */
+enum { PSLD_GN_N = 0, PSLD_GN_HW, PSLD_GN_C1, PSLD_GN_C2, PSLD_GN_G, PSLD_GN_SILU,
+       PSLD_GN_IN_DTYPE, PSLD_GN_OUT_DTYPE, PSLD_GN_NCHUNK };
+
+/* --- PSLD_OP_FIR (upfirdn2d, op/upfirdn2d.py:159-200; callers up_or_down_sampling.py:195-257):
+ *   in[0] = x [N,H,W,C] ; out[0] = y [N,OH,OW,C]
+ *   i: N, H, W, C, UP, DOWN, PAD0, PAD1, KH (== KW <= 4), DTYPE ; f[0..KH*KW) = taps (unflipped) */
+enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR_DOWN,
+       PSLD_FIR_PAD0, PSLD_FIR_PAD1, PSLD_FIR_KH, PSLD_FIR_DTYPE };
+
+/* --- PSLD_OP_CONV: y = scale * (conv(cat(x1,x2), W) + bias + temb[n,:] + residual)
+ *   (ddpm_conv3x3/conv1x1 layers.py:85-109; NIN layers.py:531-540; F.conv2d(stride=2)
+ *   up_or_down_sampling.py:178; epilogue terms layerspp.py:262-274,88-91, ncsnpp.py:353-356)
+ *   in[0] = x1, in[1] = x2 or NULL, in[2] = residual [N,OH,OW,Cout] or NULL,
+ *   in[3] = temb proj (f32) or NULL, in[4] = weight, in[5] = bias f32 [Cout] or NULL
+ *   out[0] = y
+ *   weight layout: SIMT engine f32 [K, Cout] ; TC engine bf16 [Cout, K], K = (ky*KW+kx)*Cin + c
+ *   i: N, H, W, C1, C2, COUT, KS (1|3), STRIDE, PAD, OH, OW, IN_LAYOUT, OUT_LAYOUT,
+ *      IN_DTYPE, OUT_DTYPE, RES_DTYPE, TEMB_OFF, TEMB_BSTRIDE ; f[0] = scale            */
+enum { PSLD_CONV_N = 0, PSLD_CONV_H, PSLD_CONV_W, PSLD_CONV_C1, PSLD_CONV_C2, PSLD_CONV_COUT,
+       PSLD_CONV_KS, PSLD_CONV_STRIDE, PSLD_CONV_PAD, PSLD_CONV_OH, PSLD_CONV_OW,
+       PSLD_CONV_IN_LAYOUT, PSLD_CONV_OUT_LAYOUT, PSLD_CONV_IN_DTYPE, PSLD_CONV_OUT_DTYPE,
+       PSLD_CONV_RES_DTYPE, PSLD_CONV_TEMB_OFF, PSLD_CONV_TEMB_BSTRIDE };
+
+/* --- PSLD_OP_ATTN (AttnBlockpp core, layerspp.py:82-86): single head over HW tokens.
+ *   in[0] = qkv [N, HW, 3C] (q | k | v along the last axis) ; out[0] = o [N, HW, C]
+ *   i: N, HW, C, DTYPE ; f[0] = softmax scale (C^-0.5)                                  */
+enum { PSLD_ATTN_N = 0, PSLD_ATTN_HW, PSLD_ATTN_C, PSLD_ATTN_DTYPE };
+
+/* Validate an op and build its per-op host state (TMA descriptors for PSLD_ENGINE_TC).
+ * Returns PSLD_EUNSUPPORTED when the shape is not eligible for op->engine. */
+PSLD_API int psld_op_prepare(psld_op* op);
+PSLD_API int psld_op_release(psld_op* op);
+/* Launch one op / a whole program on `stream`. */
+PSLD_API int psld_op_run(const psld_op* op, psld_stream_t stream);
+PSLD_API int psld_program_run(const psld_op* ops, int n_ops, psld_stream_t stream);
+/* Number of kernel launches psld_program_run issues for this program (bench accounting). */
+PSLD_API int psld_program_launches(const psld_op* ops, int n_ops);
+
+/* Standalone drop-in for the reference's native op (op/upfirdn2d.cpp:12-23): NCHW fp32
+ * input [N*C, H, W] planes, taps [kh, kw] on the HOST, same argument meaning. */
+PSLD_API int psld_upfirdn2d(const float* input, float* output, const float* taps_host, int kh, int kw,
+                   int64_t planes, int in_h, int in_w, int up_x, int up_y, int down_x,
+                   int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                   psld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Native sampling loop: runs all n predictor steps (+ denoise) without returning to
+ *    the host interpreter.  SSCSSampler.sample / EulerMaruyamaSampler.sample
+ *    (main/samplers/sde.py:38-58, 350-370).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t sampler;      /* 0 = sscs_sde, 1 = em_sde                                     */
+  int32_t n_steps;      /* predictor steps n                                            */
+  int32_t denoise;      /* 1: final denoising step (one more network call)              */
+  int32_t state_dtype;  /* PSLD_F64 | PSLD_F32                                          */
+  int32_t fuse_halves;  /* SSCS: fuse half B of step i with half A of step i+1          */
+  int32_t temb_op;      /* index of the PSLD_OP_TEMB op in the program                  */
+  int64_t B, chw;
+  uint64_t seed;
+  void* state;          /* [B,2C,H,W] state_dtype, in: prior, out: samples              */
+  float* net_in;        /* [B,2C,H,W] fp32 : program input buffer                       */
+  const float* eps;     /* program output buffer (fp32 NCHW)                            */
+  const float* time_table; /* device f32 [n_steps+1]: log(tau) (fourier) or tau per call */
+  const float* noise;   /* pre-drawn fp32 noise [draws, B,2C,H,W] in reference draw order,
+                           or NULL for in-kernel Philox                                 */
+  const psld_sscs_coeffs* sscs; /* host [n_steps]  (sampler 0)                          */
+  const psld_score_step* em;    /* host [n_steps]  (sampler 1)                          */
+  const psld_score_step* den;   /* host, denoise step coefficients                      */
+  void* record;         /* optional: state after every step [n_steps, B,2C,H,W] or NULL */
+} psld_sampler_desc;
+
+PSLD_API int psld_sampler_run(const psld_op* ops, int n_ops, const psld_sampler_desc* d,
+                     psld_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLD_B200_H_ */

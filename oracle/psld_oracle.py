@@ -191,6 +191,16 @@ def reverse_drift(sde: PSLDScalars, score_fn, u: torch.Tensor, t: float):
     return fbar, (gx, gm)
 
 
+def _denoise(sde, score_fn, u, eps):
+    """``denoising_fn`` as called from ``sample`` (sde.py:52-57,364-369): the reference builds
+    ``t = torch.tensor(T - eps)`` and ``dt = torch.tensor(eps)`` as **float32** tensors, so the
+    denoise step runs at t = fl32(T - eps) with step fl32(eps)."""
+    t_den = float(np.float32(sde.T - eps))
+    dt_den = float(np.float32(eps))
+    fbar, _ = reverse_drift(sde, score_fn, u, t_den)
+    return u + fbar * dt_den
+
+
 def em_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, record=None):
     """``EulerMaruyamaSampler.sample`` (``sde.py:38-58``).  ``noise``: n tensors [B,2C,H,W]."""
     sde = PSLDScalars(config)
@@ -206,8 +216,7 @@ def em_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, record
             if record is not None:
                 record(i, u)
         if denoise:                                                # sde.py:28-36,52-57
-            fbar, _ = reverse_drift(sde, score_fn, u, sde.T - eps)
-            u = u + fbar * eps
+            u = _denoise(sde, score_fn, u, eps)
     return u
 
 
@@ -243,8 +252,7 @@ def sscs_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, reco
             if record is not None:
                 record(i, u)
         if denoise:                                                # sde.py:338-348,364-369
-            fbar, _ = reverse_drift(sde, score_fn, u, sde.T - eps)
-            u = u + fbar * eps
+            u = _denoise(sde, score_fn, u, eps)
     return u
 
 

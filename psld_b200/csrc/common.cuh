@@ -1,0 +1,102 @@
+// Shared helpers for libpsld_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/psld_b200.h"
+
+namespace psld {
+
+void set_error(const char* fmt, ...);
+
+#define PSLD_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::psld::set_error(__VA_ARGS__);        \
+      return PSLD_EINVAL;                    \
+    }                                        \
+  } while (0)
+
+#define PSLD_CHECK_CUDA(expr)                                                          \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::psld::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                     \
+      return PSLD_ECUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+#define PSLD_CHECK_LAUNCH() PSLD_CHECK_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- element-type helpers: 4-wide vector load / store with fp32 math ----------------
+template <typename T>
+struct Vec4;
+
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  static __device__ __forceinline__ void store(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+};
+
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+static inline size_t dtype_size(int dt) { return dt == PSLD_BF16 ? 2 : (dt == PSLD_F64 ? 8 : 4); }
+
+// per-op entry points (implemented in the .cu files, dispatched from capi.cu)
+int run_layout(const psld_op& op, cudaStream_t s);
+int run_temb(const psld_op& op, cudaStream_t s);
+int run_gn(const psld_op& op, cudaStream_t s);
+int run_fir(const psld_op& op, cudaStream_t s);
+int run_conv_simt(const psld_op& op, cudaStream_t s);
+int run_attn_simt(const psld_op& op, cudaStream_t s);
+int prepare_conv_tc(psld_op& op);
+int release_conv_tc(psld_op& op);
+int run_conv_tc(const psld_op& op, cudaStream_t s);
+
+}  // namespace psld

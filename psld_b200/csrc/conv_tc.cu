@@ -1,0 +1,522 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate).
+//
+// Computes, for NHWC bf16 activations, y = scale * (conv_{KSxKS, stride 1, pad KS/2}(cat(x1,x2), W)
+//                                                   + bias + temb[n,:] + residual)
+// i.e. the reference's ddpm_conv3x3 / ddpm_conv1x1 / NIN call sites with their epilogue terms
+// fused (layers.py:85-109,531-540; layerspp.py:242-274,75-91).  >= 97% of the network's FLOPs
+// go through this kernel (conv3x3 71.09 + conv1x1 3.38 + NIN 1.24 of
+// 76.43 GFLOP per sample per NFE).
+//
+// Design (B200-first, not a port: the reference calls cuDNN through ATen):
+//   * GEMM view: M = N*H*W output pixels, N = Cout, K = KS*KS*Cin, K ordered (tap, channel).
+//   * One CTA tile = 128 pixels x BLOCK_N channels; the accumulator lives in TMEM
+//     (128 lanes x BLOCK_N fp32 columns), double-buffered (2 x 256 columns) so the epilogue of
+//     tile i overlaps the MMAs of tile i+1.  Persistent CTAs, one per SM.
+//   * A operand: for every (tap, 64-channel chunk) ONE 4-D TMA box {64 ch, BW, BH, BN} of the
+//     NHWC tensor, shifted by the tap offset; out-of-image rows/columns are zero-filled by the
+//     TMA unit, which is exactly the conv's zero padding - no im2col buffer, no halo code.
+//     The box lands in shared memory as 128 rows x 128 B with the 128B swizzle = the canonical
+//     K-major UMMA layout.
+//   * B operand: weights pre-packed [Cout, K] bf16 (K-major), 2-D TMA box {64, BLOCK_N}.
+//   * torch.cat([h, skip]) inputs (ncsnpp.py:374) are never materialised: the K loop walks two
+//     tensor maps.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
+//     allocator, warps 2-5 = epilogue (tcgen05.ld -> bias/temb/residual/scale -> bf16 -> global).
+//   * 4-stage smem ring (A 16 KB + B 32 KB per stage), mbarrier full/empty pairs,
+//     tcgen05.commit releases stages and publishes accumulators.
+
+#include <cuda.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace psld {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;        // bf16 elements = one 128-byte swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+constexpr int TC_B_BYTES = 256 * TC_BLOCK_K * 2;          // 32 KB (max BLOCK_N = 256)
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;
+
+struct ConvTcParams {
+  const float* bias;
+  const float* temb;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  float* y_nchw;             // when non-null: fp32 NCHW output, first cout_valid channels only
+  int cout_valid;
+  float scale;
+  int temb_off, temb_bstride;
+  int H, W, HW, Cout;
+  int BH, BN_img;            // TMA box: {64, W, BH, BN_img}, W*BH*BN_img == 128
+  int tiles_y;               // H / BH
+  int kchunks1, kchunks;     // 64-channel chunks in source 1 / in total (C1+C2)/64
+  int taps, KS;
+  int block_n, n_tiles_n;
+  int num_tiles;
+  int64_t M;                 // N*H*W
+};
+
+struct ConvTcState {
+  CUtensorMap a1, a2, b;
+  ConvTcParams p;
+  int grid;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFF) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset  bits [16,30) (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                         // layout: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_kb = p.taps * p.kchunks;
+  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.block_n * TC_BLOCK_K * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
+        const int n0 = (m_tile / p.tiles_y) * p.BN_img;
+        const int y0 = (m_tile % p.tiles_y) * p.BH;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
+          const int ky = tap / p.KS, kx = tap - ky * p.KS;
+          const int off = p.KS >> 1;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+          const uint32_t sa = base + stage * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+          if (cc < p.kchunks1)
+            tma_load_4d(sa, &tmA1, full_bar(stage), cc * TC_BLOCK_K, kx - off, y0 + ky - off, n0);
+          else
+            tma_load_4d(sa, &tmA2, full_bar(stage), (cc - p.kchunks1) * TC_BLOCK_K, kx - off,
+                        y0 + ky - off, n0);
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * TC_BLOCK_K, n_tile * p.block_n);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * TC_STAGE_BYTES;
+          const uint64_t adesc = make_sw128_desc(sa);
+          const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));   // frees the smem stage when these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));       // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
+      const bool valid = m < p.M;
+      const int img = valid ? (int)(m / p.HW) : 0;
+      const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
+      for (int ch = 0; ch < p.block_n; ch += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)acc * 256u + (uint32_t)ch;
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        if (valid) {
+          const int co0 = n_tile * p.block_n + ch;
+          const int64_t o = m * p.Cout + co0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (temb) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(temb + co0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = *reinterpret_cast<const uint4*>(p.res + o + j);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+                const float2 f = __bfloat1622float2(h);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
+          }
+          if (p.y_nchw) {
+            // network output head (ncsnpp.py:430): fp32 NCHW, lanes = consecutive pixels
+            const int64_t pix = m - (int64_t)img * p.HW;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int co = co0 + j;
+              if (co < p.cout_valid)
+                p.y_nchw[((int64_t)img * p.cout_valid + co) * p.HW + pix] = v[j] * p.scale;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                __nv_bfloat162 h =
+                    __floats2bfloat162_rn(v[j + 2 * t] * p.scale, v[j + 2 * t + 1] * p.scale);
+                w[t] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(p.y + o + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int BH,
+                          int BN_img) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)W, (cuuint32_t)BH, (cuuint32_t)BN_img};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return PSLD_ECUDA; }
+  return PSLD_OK;
+}
+
+static int encode_w_map(CUtensorMap* tm, const void* ptr, int Cout, int K, int block_n) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight) failed: %d", (int)r); return PSLD_ECUDA; }
+  return PSLD_OK;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int prepare_conv_tc(psld_op& op) {
+  const int N = op.i[PSLD_CONV_N], H = op.i[PSLD_CONV_H], W = op.i[PSLD_CONV_W];
+  const int C1 = op.i[PSLD_CONV_C1], C2 = op.i[PSLD_CONV_C2], Cout = op.i[PSLD_CONV_COUT];
+  const int KS = op.i[PSLD_CONV_KS];
+  auto unsupported = [&](const char* why) {
+    set_error("conv_tc: not eligible (%s): N=%d H=%d W=%d C1=%d C2=%d Cout=%d KS=%d", why, N, H, W,
+              C1, C2, Cout, KS);
+    return PSLD_EUNSUPPORTED;
+  };
+  const bool head = op.i[PSLD_CONV_OUT_LAYOUT] == PSLD_NCHW;   // fp32 NCHW output head
+  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16) return unsupported("input dtype must be bf16");
+  if (op.i[PSLD_CONV_OUT_DTYPE] != (head ? PSLD_F32 : PSLD_BF16))
+    return unsupported("output must be bf16 NHWC or fp32 NCHW");
+  if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC) return unsupported("input layout must be NHWC");
+  if (head && (op.in[2] || op.f[1] < 1.0f || (int)op.f[1] > Cout))
+    return unsupported("NCHW head takes no residual and needs f[1] = valid channels");
+  if (op.i[PSLD_CONV_STRIDE] != 1 || op.i[PSLD_CONV_PAD] != KS / 2 || (KS != 1 && KS != 3))
+    return unsupported("stride 1 / same padding only");
+  if (C1 % TC_BLOCK_K || C2 % TC_BLOCK_K) return unsupported("Cin %% 64 != 0");
+  if (Cout % 32) return unsupported("Cout %% 32 != 0");
+  if (!is_pow2(W) || !is_pow2(H) || W > 128 || W < 4) return unsupported("W,H must be pow2, 4..128");
+  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != PSLD_BF16) return unsupported("residual dtype");
+  if (!op.in[0] || !op.in[4] || !op.out[0] || (C2 > 0 && !op.in[1])) {
+    set_error("conv_tc: null pointer");
+    return PSLD_EINVAL;
+  }
+  int block_n = 0;
+  for (int cand : {256, 128, 64, 32})
+    if (Cout % cand == 0) { block_n = cand; break; }
+  int BH = 128 / W;
+  if (BH > H) BH = H;
+  const int BN_img = 128 / (W * BH);
+  if (BN_img > 256) return unsupported("image too small");
+
+  ConvTcState* st = new (std::nothrow) ConvTcState();
+  if (!st) { set_error("conv_tc: out of host memory"); return PSLD_ECUDA; }
+  int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, BH, BN_img);
+  if (rc == PSLD_OK)
+    rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, BH, BN_img)
+                : encode_act_map(&st->a2, op.in[0], N, H, W, C1, BH, BN_img);
+  const int K = KS * KS * (C1 + C2);
+  if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, block_n);
+  if (rc != PSLD_OK) { delete st; return rc; }
+
+  ConvTcParams& p = st->p;
+  p.bias = (const float*)op.in[5];
+  p.temb = (const float*)op.in[3];
+  p.res = (const __nv_bfloat16*)op.in[2];
+  p.y = head ? nullptr : (__nv_bfloat16*)op.out[0];
+  p.y_nchw = head ? (float*)op.out[0] : nullptr;
+  p.cout_valid = head ? (int)op.f[1] : Cout;
+  p.scale = op.f[0];
+  p.temb_off = op.i[PSLD_CONV_TEMB_OFF];
+  p.temb_bstride = op.i[PSLD_CONV_TEMB_BSTRIDE];
+  p.H = H; p.W = W; p.HW = H * W; p.Cout = Cout;
+  p.BH = BH; p.BN_img = BN_img; p.tiles_y = H / BH;
+  p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
+  p.taps = KS * KS; p.KS = KS;
+  p.block_n = block_n; p.n_tiles_n = Cout / block_n;
+  p.M = (int64_t)N * H * W;
+  const int64_t m_tiles = (int64_t)((N + BN_img - 1) / BN_img) * p.tiles_y;
+  p.num_tiles = (int)(m_tiles * p.n_tiles_n);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  st->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TC_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      delete st;
+      return PSLD_ECUDA;
+    }
+    attr_set = true;
+  }
+  op.aux = st;
+  return PSLD_OK;
+}
+
+int release_conv_tc(psld_op& op) {
+  if (op.aux) {
+    delete (ConvTcState*)op.aux;
+    op.aux = nullptr;
+  }
+  return PSLD_OK;
+}
+
+int run_conv_tc(const psld_op& op, cudaStream_t s) {
+  const ConvTcState* st = (const ConvTcState*)op.aux;
+  PSLD_CHECK_ARG(st != nullptr, "conv_tc: op not prepared (call psld_op_prepare)");
+  conv_tc_kernel<<<st->grid, TC_THREADS, TC_SMEM_BYTES, s>>>(st->a1, st->a2, st->b, st->p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+}  // namespace psld

@@ -1,0 +1,343 @@
+// Fused phase-space update kernels: one vectorised pass over HBM per sampler step.
+//
+// Reference (mandt-lab/PSLD) lines these kernels compute:
+//   SSCSSampler.analytical_dynamics ... main/samplers/sde.py:294-312  (stages HALF_*)
+//   SSCSSampler.euler_score_dynamics .. main/samplers/sde.py:314-329  (stage SCORE)
+//   PSLD.get_score (fp32 coefficients)  main/models/sde/psld.py:230-260
+//   EulerMaruyamaSampler.predictor_update_fn / denoising_fn ... sde.py:16-36, 338-348
+//   PSLD.sde / reverse_sde ............ main/models/sde/psld.py:330-364
+//   PSLD.prior_sampling ............... main/models/sde/psld.py:366-370
+//
+// The reference spends ~619 aten launches + 9 host syncs per SSCS step on this algebra
+// (SURVEY.md §3.1); here all per-step scalars arrive as kernel parameters computed once
+// on the host in float64, and every pair (x, m) is read once and written once.
+//
+// Memory-bound: 4 pairs per thread, 128-bit loads/stores, grid sized to cover the data
+// (one wave is >> 148 SMs at the BASELINE batch sizes).
+
+#include "common.cuh"
+
+namespace psld {
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  static __device__ __forceinline__ uint4 draw(uint64_t seed, uint64_t stream, uint64_t index) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint4 c = make_uint4((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)stream,
+                         (uint32_t)(stream >> 32));
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+      c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    return c;
+  }
+  // 4 standard normals from one draw (Box-Muller on two uniform pairs)
+  static __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t stream, uint64_t index) {
+    uint4 r = draw(seed, stream, index);
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    float u0 = ((float)r.x + 0.5f) * k, u1 = (float)r.y * k;
+    float u2 = ((float)r.z + 0.5f) * k, u3 = (float)r.w * k;
+    u0 = fminf(u0, 0.99999994f);
+    u2 = fminf(u2, 0.99999994f);
+    float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+    float sa, ca, sb, cb;
+    __sincosf(6.283185307179586f * u1, &sa, &ca);
+    __sincosf(6.283185307179586f * u3, &sb, &cb);
+    return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+  }
+};
+
+template <typename S>
+struct St4 { S v[4]; };
+
+template <typename S>
+__device__ __forceinline__ St4<S> load4(const S* p);
+template <>
+__device__ __forceinline__ St4<float> load4<float>(const float* p) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  return {{t.x, t.y, t.z, t.w}};
+}
+template <>
+__device__ __forceinline__ St4<double> load4<double>(const double* p) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  double2 b = *reinterpret_cast<const double2*>(p + 2);
+  return {{a.x, a.y, b.x, b.y}};
+}
+template <typename S>
+__device__ __forceinline__ void store4(S* p, const St4<S>& v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const St4<float>& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<double>(double* p, const St4<double>& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.v[0], v.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v.v[2], v.v[3]);
+}
+
+struct HalfF {  // psld_half_step in the state's arithmetic type
+  template <typename S>
+  struct T { S a_xx, a_xm, a_mx, a_mm, c11, c12, c21, c22; };
+};
+
+template <typename S>
+__device__ __forceinline__ void apply_half(const psld_half_step& h, S (&x)[4], S (&m)[4],
+                                           const float4& zx, const float4& zm) {
+  const S axx = (S)h.a_xx, axm = (S)h.a_xm, amx = (S)h.a_mx, amm = (S)h.a_mm;
+  const S c11 = (S)h.c11, c12 = (S)h.c12, c21 = (S)h.c21, c22 = (S)h.c22;
+  const float zxa[4] = {zx.x, zx.y, zx.z, zx.w}, zma[4] = {zm.x, zm.y, zm.z, zm.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    S nx = axx * x[i] + axm * m[i] + (c11 * (S)zxa[i] + c12 * (S)zma[i]);
+    S nm = amx * x[i] + amm * m[i] + (c21 * (S)zxa[i] + c22 * (S)zma[i]);
+    x[i] = nx;
+    m[i] = nm;
+  }
+}
+
+// score = -L^{-T} eps evaluated exactly as the reference does in fp32:
+//   s_x = (-li11)*e_x - li12*e_m ; s_m = (-li21)*e_x - li22*e_m   (psld.py:252-259)
+__device__ __forceinline__ void score_from_eps(const psld_score_step& sc, float ex, float em,
+                                               float& sx, float& sm) {
+  if (sc.mode == 0) {
+    sx = __fsub_rn(__fmul_rn(-sc.li11, ex), __fmul_rn(sc.li12, em));
+    sm = __fsub_rn(__fmul_rn(-sc.li21, ex), __fmul_rn(sc.li22, em));
+  } else if (sc.mode == 1) {  // score_m: eps is the momentum channel only (psld.py:240-243)
+    sx = 0.0f;
+    sm = __fmul_rn(-sc.li22, ex);
+  } else {                    // score_x (psld.py:245-248)
+    sx = __fmul_rn(-sc.li11, ex);
+    sm = 0.0f;
+  }
+}
+
+__device__ __forceinline__ void load_eps(const float* eps, int mode, int64_t b, int64_t j,
+                                         int64_t chw, float4& ex, float4& em) {
+  if (mode == 0) {
+    const float* p = eps + b * 2 * chw + j;
+    ex = *reinterpret_cast<const float4*>(p);
+    em = *reinterpret_cast<const float4*>(p + chw);
+  } else {
+    ex = *reinterpret_cast<const float4*>(eps + b * chw + j);
+    em = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void get_noise(const float* z, uint64_t seed, uint64_t draw,
+                                          int64_t b, int64_t j, int64_t chw, float4& zx,
+                                          float4& zm) {
+  if (z != nullptr) {
+    const float* p = z + b * 2 * chw + j;
+    zx = *reinterpret_cast<const float4*>(p);
+    zm = *reinterpret_cast<const float4*>(p + chw);
+  } else {
+    uint64_t pair4 = (uint64_t)(b * chw + j) >> 1;  // 2 draws of 4 normals per 4 pairs
+    zx = Philox::normal4(seed, draw, pair4);
+    zm = Philox::normal4(seed, draw, pair4 + 1);
+  }
+}
+
+struct SscsParams {
+  psld_sscs_coeffs c;
+  const float* eps;
+  const float* z_a;
+  const float* z_b;
+  const float* z_c;
+  float* net_in;
+  uint64_t seed, step;
+  int64_t B, chw;
+  int stages;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams p) {
+  const int64_t nvec = p.B * (p.chw >> 2);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = v / (p.chw >> 2);
+    const int64_t j = (v - b * (p.chw >> 2)) << 2;
+    const int64_t ox = b * 2 * p.chw + j;
+    St4<S> xs = load4<S>(u_in + ox), ms = load4<S>(u_in + ox + p.chw);
+    S(&x)[4] = xs.v;
+    S(&m)[4] = ms.v;
+    float4 zx, zm;
+    if (p.stages & PSLD_STAGE_HALF_A) {
+      get_noise(p.z_a, p.seed, 2 * p.step, b, j, p.chw, zx, zm);
+      apply_half<S>(p.c.half_a, x, m, zx, zm);
+    }
+    if (p.stages & PSLD_STAGE_SCORE) {
+      float4 ex, em;
+      load_eps(p.eps, p.c.score.mode, b, j, p.chw, ex, em);
+      const float exa[4] = {ex.x, ex.y, ex.z, ex.w}, ema[4] = {em.x, em.y, em.z, em.w};
+      const S kx = (S)p.c.score.k_x, km = (S)p.c.score.k_m, mi = (S)p.c.score.m_inv;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float sx, sm;
+        score_from_eps(p.c.score, exa[i], ema[i], sx, sm);
+        x[i] = x[i] + kx * ((S)sx + x[i]);             // sde.py:325
+        m[i] = m[i] + km * ((S)sm + mi * m[i]);        // sde.py:326-328
+      }
+    }
+    if (p.stages & PSLD_STAGE_HALF_B) {
+      get_noise(p.z_b, p.seed, 2 * p.step + 1, b, j, p.chw, zx, zm);
+      apply_half<S>(p.c.half_b, x, m, zx, zm);
+    }
+    if (p.stages & PSLD_STAGE_HALF_C) {
+      get_noise(p.z_c, p.seed, 2 * p.step + 2, b, j, p.chw, zx, zm);
+      apply_half<S>(p.c.half_c, x, m, zx, zm);
+    }
+    store4<S>(u_out + ox, xs);
+    store4<S>(u_out + ox + p.chw, ms);
+    if (p.net_in != nullptr) {
+      *reinterpret_cast<float4*>(p.net_in + ox) =
+          make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+      *reinterpret_cast<float4*>(p.net_in + ox + p.chw) =
+          make_float4((float)m[0], (float)m[1], (float)m[2], (float)m[3]);
+    }
+  }
+}
+
+struct EmParams {
+  psld_score_step c;
+  const float* eps;
+  const float* z;
+  float* net_in;
+  uint64_t seed, step;
+  int64_t B, chw;
+  int use_philox;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+em_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams p) {
+  const int64_t nvec = p.B * (p.chw >> 2);
+  const S hb = (S)p.c.half_beta, mi = (S)p.c.m_inv, ga = (S)p.c.gamma, nu = (S)p.c.nu;
+  const S g2x = (S)p.c.g2_x, g2m = (S)p.c.g2_m, dt = (S)p.c.dt;
+  const S gsx = (S)p.c.gs_x, gsm = (S)p.c.gs_m;
+  const bool noisy = (p.z != nullptr) || p.use_philox;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = v / (p.chw >> 2);
+    const int64_t j = (v - b * (p.chw >> 2)) << 2;
+    const int64_t ox = b * 2 * p.chw + j;
+    St4<S> xs = load4<S>(u_in + ox), ms = load4<S>(u_in + ox + p.chw);
+    float4 ex, em, zx = make_float4(0, 0, 0, 0), zm = zx;
+    load_eps(p.eps, p.c.mode, b, j, p.chw, ex, em);
+    if (noisy) get_noise(p.z, p.seed, p.step, b, j, p.chw, zx, zm);
+    const float exa[4] = {ex.x, ex.y, ex.z, ex.w}, ema[4] = {em.x, em.y, em.z, em.w};
+    const float zxa[4] = {zx.x, zx.y, zx.z, zx.w}, zma[4] = {zm.x, zm.y, zm.z, zm.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const S x = xs.v[i], m = ms.v[i];
+      float sx, sm;
+      score_from_eps(p.c, exa[i], ema[i], sx, sm);
+      const S fx = hb * (mi * m - ga * x);              // psld.py:336
+      const S fm = hb * (-nu * m - x);                  // psld.py:337
+      const S fbx = -fx + g2x * (S)sx;                  // psld.py:359
+      const S fbm = -fm + g2m * (S)sm;
+      S nx = x + fbx * dt, nm = m + fbm * dt;           // sde.py:23
+      if (noisy) {
+        nx = nx + gsx * (S)zxa[i];                      // sde.py:24-25
+        nm = nm + gsm * (S)zma[i];
+      }
+      xs.v[i] = nx;
+      ms.v[i] = nm;
+    }
+    store4<S>(u_out + ox, xs);
+    store4<S>(u_out + ox + p.chw, ms);
+    if (p.net_in != nullptr) {
+      *reinterpret_cast<float4*>(p.net_in + ox) =
+          make_float4((float)xs.v[0], (float)xs.v[1], (float)xs.v[2], (float)xs.v[3]);
+      *reinterpret_cast<float4*>(p.net_in + ox + p.chw) =
+          make_float4((float)ms.v[0], (float)ms.v[1], (float)ms.v[2], (float)ms.v[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+prior_kernel(float* __restrict__ u, float m_std, uint64_t seed, int64_t B, int64_t chw) {
+  const int64_t nvec = B * (chw >> 2);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = v / (chw >> 2);
+    const int64_t j = (v - b * (chw >> 2)) << 2;
+    float4 zx, zm;
+    get_noise(nullptr, seed, ~0ull, b, j, chw, zx, zm);
+    float* p = u + b * 2 * chw + j;
+    *reinterpret_cast<float4*>(p) = zx;
+    *reinterpret_cast<float4*>(p + chw) =
+        make_float4(zm.x * m_std, zm.y * m_std, zm.z * m_std, zm.w * m_std);
+  }
+}
+
+static inline int grid_for(int64_t nvec) {
+  // enough CTAs for >= 8 resident per SM on 148 SMs, capped so small problems stay 1 wave
+  int64_t g = ceil_div(nvec, 256);
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace psld
+
+using namespace psld;
+
+extern "C" int psld_sscs_update(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                                const float* eps, const float* z_a, const float* z_b,
+                                const float* z_c, const psld_sscs_coeffs* coeffs, int stages,
+                                uint64_t seed, uint64_t step, int64_t B, int64_t chw,
+                                psld_stream_t stream) {
+  PSLD_CHECK_ARG(u_out && u_in && coeffs, "psld_sscs_update: null pointer");
+  PSLD_CHECK_ARG(B > 0 && chw > 0 && chw % 4 == 0, "psld_sscs_update: need chw %% 4 == 0");
+  PSLD_CHECK_ARG(stages > 0 && stages < 16, "psld_sscs_update: bad stage mask %d", stages);
+  PSLD_CHECK_ARG(!(stages & PSLD_STAGE_SCORE) || eps, "psld_sscs_update: SCORE needs eps");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
+                 "psld_sscs_update: state dtype must be f64 or f32");
+  SscsParams p;
+  p.c = *coeffs;
+  p.eps = eps; p.z_a = z_a; p.z_b = z_b; p.z_c = z_c; p.net_in = net_in;
+  p.seed = seed; p.step = step; p.B = B; p.chw = chw; p.stages = stages;
+  const int grid = grid_for(B * (chw / 4));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    sscs_update_kernel<double><<<grid, 256, 0, s>>>((double*)u_out, (const double*)u_in, p);
+  else
+    sscs_update_kernel<float><<<grid, 256, 0, s>>>((float*)u_out, (const float*)u_in, p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                              const float* eps, const float* z, int use_philox,
+                              const psld_score_step* coeffs, uint64_t seed, uint64_t step,
+                              int64_t B, int64_t chw, psld_stream_t stream) {
+  PSLD_CHECK_ARG(u_out && u_in && coeffs && eps, "psld_em_update: null pointer");
+  PSLD_CHECK_ARG(B > 0 && chw > 0 && chw % 4 == 0, "psld_em_update: need chw %% 4 == 0");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
+                 "psld_em_update: state dtype must be f64 or f32");
+  EmParams p;
+  p.c = *coeffs;
+  p.eps = eps; p.z = z; p.net_in = net_in; p.seed = seed; p.step = step;
+  p.B = B; p.chw = chw; p.use_philox = use_philox;
+  const int grid = grid_for(B * (chw / 4));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    em_update_kernel<double><<<grid, 256, 0, s>>>((double*)u_out, (const double*)u_in, p);
+  else
+    em_update_kernel<float><<<grid, 256, 0, s>>>((float*)u_out, (const float*)u_in, p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
+                                 psld_stream_t stream) {
+  PSLD_CHECK_ARG(u && B > 0 && chw > 0 && chw % 4 == 0, "psld_prior_sample: bad arguments");
+  prior_kernel<<<grid_for(B * (chw / 4)), 256, 0, (cudaStream_t)stream>>>(u, (float)m_std, seed,
+                                                                         B, chw);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}

@@ -1,0 +1,413 @@
+"""Compiles an :class:`psld_b200.ncsnpp.NCSNpp` into a flat program of ``psld_op`` records.
+
+One plan = one (batch, #time rows, precision) instantiation of the reference forward
+(``main/models/score_fn/song_sde/ncsnpp.py:287-438``): weights re-packed into the kernel
+layouts, every activation buffer pre-allocated (NHWC, fp32 or bf16), and the layer sequence
+unrolled into ops the native executor replays (``psld_program_run`` / ``psld_sampler_run``).
+
+Fusions relative to the reference's eager graph:
+  * ``torch.cat([h, skip])`` is never materialised: GroupNorm and the 1x1 shortcut read two
+    sources;
+  * bias, ``Dense_0(SiLU(temb))`` add, shortcut add and the ``1/sqrt(2)`` rescale live in the
+    convolution epilogue;
+  * q, k, v NIN projections are one GEMM with a [C, 3C] weight;
+  * the 2-layer temb MLP and all per-block ``Dense_0`` projections are computed once per call
+    (and for ONE time row when the whole batch shares t, as it does during sampling).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_SQRT1_2 = float(1.0 / np.sqrt(2.0))
+
+
+def _fir_taps(k1d, gain):
+    """``_setup_kernel`` (reference up_or_down_sampling.py:181-188) * gain, as float32."""
+    k = np.asarray(k1d, dtype=np.float32)
+    if k.ndim == 1:
+        k = np.outer(k, k)
+    k /= np.sum(k)
+    return (k * gain).astype(np.float32)
+
+
+class Plan:
+    def __init__(self, net, B, nt, logged, dry=False):
+        self.lib = L.lib()
+        self.net = net
+        self.B, self.nt, self.logged = int(B), int(nt), bool(logged)
+        self.dev = next(net.parameters()).device
+        # dry = structural build on host tensors (tests of the builder logic only): the ops are
+        # never launched and TC eligibility is decided by the same rules as psld_op_prepare.
+        self.dry = bool(dry)
+        if self.dev.type != "cuda" and not self.dry:
+            raise RuntimeError("psld_b200: parameters must be on a CUDA device (no CPU path)")
+        self.bf16 = net.precision == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32
+        self.acode = L.BF16 if self.bf16 else L.F32
+        self.keep = []          # tensors referenced by raw pointers
+        self.ops = []
+        self.pool = {}
+        self.engine_count = {"tc": 0, "simt": 0}
+        self.temb_op = -1
+        self._build()
+        self.n_ops = len(self.ops)
+        self.op_array = (L.Op * self.n_ops)(*self.ops)
+        self.launches = self.lib.psld_program_launches(self.op_array, self.n_ops)
+
+    # ---------------------------------------------------------------- helpers
+    def _new(self, *shape, dtype=None):
+        t = torch.empty(*shape, dtype=dtype or self.adt, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def _acquire(self, *shape):
+        key = tuple(shape)
+        lst = self.pool.setdefault(key, [])
+        if lst:
+            return lst.pop()
+        return self._new(*shape)
+
+    def _release(self, t):
+        self.pool.setdefault(tuple(t.shape), []).append(t)
+
+    def _w(self, t, dtype=torch.float32):
+        t = t.detach().to(device=self.dev, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _op(self, kind, engine=L.ENGINE_SIMT):
+        op = L.Op()
+        op.kind = kind
+        op.engine = engine
+        return op
+
+    def _push(self, op):
+        self.ops.append(op)
+        return len(self.ops) - 1
+
+    # ---------------------------------------------------------------- op builders
+    def op_layout(self, src, dst, N, Cc, HW, direction):
+        op = self._op(L.OP_LAYOUT)
+        op.i[L.LAYOUT_N], op.i[L.LAYOUT_C], op.i[L.LAYOUT_HW] = N, Cc, HW
+        op.i[L.LAYOUT_DIR], op.i[L.LAYOUT_DTYPE] = direction, self.acode
+        op.inp[0], op.out[0] = src.data_ptr(), dst.data_ptr()
+        self._push(op)
+
+    def op_gn(self, x1, x2, gn_mod, silu, HW):
+        """GroupNorm(+SiLU) over cat(x1, x2) -> new [B, HW.., C1+C2] buffer."""
+        C1 = x1.shape[-1]
+        C2 = x2.shape[-1] if x2 is not None else 0
+        Cc = C1 + C2
+        G = gn_mod.num_groups
+        assert gn_mod.num_channels == Cc, (gn_mod.num_channels, Cc)
+        y = self._acquire(*x1.shape[:-1], Cc)
+        nchunk = int(max(1, min(HW // 16 if HW >= 16 else 1, -(-296 // self.B))))
+        op = self._op(L.OP_GN)
+        i = op.i
+        i[L.GN_N], i[L.GN_HW], i[L.GN_C1], i[L.GN_C2], i[L.GN_G] = self.B, HW, C1, C2, G
+        i[L.GN_SILU], i[L.GN_IN_DTYPE], i[L.GN_OUT_DTYPE], i[L.GN_NCHUNK] = int(silu), self.acode, self.acode, nchunk
+        op.f[0] = float(gn_mod.eps)
+        op.inp[0] = x1.data_ptr()
+        op.inp[1] = x2.data_ptr() if x2 is not None else None
+        op.inp[2] = self._w(gn_mod.weight).data_ptr()
+        op.inp[3] = self._w(gn_mod.bias).data_ptr()
+        op.out[0] = y.data_ptr()
+        need = self.B * nchunk * G * 2
+        if self.gn_scratch is None or self.gn_scratch.numel() < need:
+            self.gn_scratch = self._new(max(need, 1 << 16), dtype=torch.float64)
+            for o in self.ops:       # re-point earlier GN ops at the (larger) scratch
+                if o.kind == L.OP_GN:
+                    o.out[1] = self.gn_scratch.data_ptr()
+        op.out[1] = self.gn_scratch.data_ptr()
+        self._push(op)
+        return y
+
+    def op_fir(self, x, taps, up, down, pad0, pad1):
+        N, H, W, Cc = x.shape
+        KH = taps.shape[0]
+        OH = (H * up + pad0 + pad1 - KH) // down + 1
+        OW = (W * up + pad0 + pad1 - KH) // down + 1
+        y = self._acquire(N, OH, OW, Cc)
+        op = self._op(L.OP_FIR)
+        i = op.i
+        i[L.FIR_N], i[L.FIR_H], i[L.FIR_W], i[L.FIR_C] = N, H, W, Cc
+        i[L.FIR_UP], i[L.FIR_DOWN], i[L.FIR_PAD0], i[L.FIR_PAD1] = up, down, pad0, pad1
+        i[L.FIR_KH], i[L.FIR_DTYPE] = KH, self.acode
+        for j, v in enumerate(taps.reshape(-1)):
+            op.f[j] = float(v)
+        op.inp[0], op.out[0] = x.data_ptr(), y.data_ptr()
+        self._push(op)
+        return y
+
+    def op_conv(self, x1, x2, w_oihw, bias, *, ks, stride=1, pad=None, residual=None,
+                temb_off=-1, scale=1.0, out=None, in_nchw=False, out_nchw_f32=False,
+                hw=None, allow_tc=True):
+        """y = scale * (conv(cat(x1,x2), w) + bias + temb + residual); w is [Cout, Cin, ks, ks]."""
+        pad = ks // 2 if pad is None else pad
+        if in_nchw:
+            N, C1, H, W = x1.shape
+        else:
+            N, H, W, C1 = x1.shape
+        C2 = x2.shape[-1] if x2 is not None else 0
+        Cout = w_oihw.shape[0]
+        assert w_oihw.shape[1] == C1 + C2, (tuple(w_oihw.shape), C1, C2)
+        OH = (H + 2 * pad - ks) // stride + 1
+        OW = (W + 2 * pad - ks) // stride + 1
+        if out is None:
+            out = self._new(N, Cout, OH, OW, dtype=torch.float32) if out_nchw_f32 \
+                else self._acquire(N, OH, OW, Cout)
+        op = self._op(L.OP_CONV)
+        i = op.i
+        i[L.CONV_N], i[L.CONV_H], i[L.CONV_W], i[L.CONV_C1], i[L.CONV_C2] = N, H, W, C1, C2
+        i[L.CONV_COUT], i[L.CONV_KS], i[L.CONV_STRIDE], i[L.CONV_PAD] = Cout, ks, stride, pad
+        i[L.CONV_OH], i[L.CONV_OW] = OH, OW
+        i[L.CONV_IN_LAYOUT] = L.NCHW if in_nchw else L.NHWC
+        i[L.CONV_OUT_LAYOUT] = L.NCHW if out_nchw_f32 else L.NHWC
+        i[L.CONV_IN_DTYPE] = L.F32 if in_nchw else self.acode
+        i[L.CONV_OUT_DTYPE] = L.F32 if out_nchw_f32 else self.acode
+        i[L.CONV_RES_DTYPE] = self.acode
+        if temb_off >= 0:
+            i[L.CONV_TEMB_OFF] = temb_off
+            i[L.CONV_TEMB_BSTRIDE] = 0 if self.nt == 1 else self.total_c
+            op.inp[3] = self.temb_proj.data_ptr()
+        op.f[0] = float(scale)
+        op.inp[0] = x1.data_ptr()
+        op.inp[1] = x2.data_ptr() if x2 is not None else None
+        op.inp[2] = residual.data_ptr() if residual is not None else None
+        b32 = self._w(bias) if bias is not None else None
+        op.inp[5] = b32.data_ptr() if b32 is not None else None
+        op.out[0] = out.data_ptr()
+        w = w_oihw.detach().to(self.dev, torch.float32)
+        done = False
+        if self.bf16 and allow_tc and not in_nchw:
+            op.engine = L.ENGINE_TC
+            cout_pad = Cout
+            if out_nchw_f32 and Cout % 32:
+                cout_pad = -(-Cout // 32) * 32       # zero rows; the epilogue writes Cout planes
+            wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+            if cout_pad != Cout:
+                wt = torch.cat([wt, wt.new_zeros(cout_pad - Cout, wt.shape[1])], 0)
+                if b32 is not None:
+                    b32 = self._w(torch.cat([b32, b32.new_zeros(cout_pad - Cout)]))
+                    op.inp[5] = b32.data_ptr()
+            wt = self._w(wt, torch.bfloat16)
+            op.inp[4] = wt.data_ptr()
+            i[L.CONV_COUT] = cout_pad
+            op.i[L.CONV_OUT_DTYPE] = L.F32 if out_nchw_f32 else self.acode
+            op.f[1] = float(Cout)                    # valid output channels (NCHW f32 epilogue)
+            rc = self._tc_eligible(op) if self.dry else self.lib.psld_op_prepare(C.byref(op))
+            if rc == L.OK:
+                done = True
+                self.engine_count["tc"] += 1
+            elif rc != L.EUNSUPPORTED:
+                L.check(rc, "psld_op_prepare(conv)")
+            else:
+                i[L.CONV_COUT] = Cout
+                if bias is not None:
+                    op.inp[5] = self._w(bias).data_ptr()
+        if not done:
+            op.engine = L.ENGINE_SIMT
+            ws = self._w(w.permute(2, 3, 1, 0).reshape(-1, Cout))     # [K, Cout] fp32
+            op.inp[4] = ws.data_ptr()
+            self.engine_count["simt"] += 1
+        self._push(op)
+        return out
+
+    @staticmethod
+    def _tc_eligible(op):
+        """Host mirror of prepare_conv_tc's eligibility rules (csrc/conv_tc.cu), dry builds only."""
+        i = op.i
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        ks = i[L.CONV_KS]
+        ok = (i[L.CONV_IN_DTYPE] == L.BF16 and i[L.CONV_IN_LAYOUT] == L.NHWC
+              and i[L.CONV_STRIDE] == 1 and ks in (1, 3) and i[L.CONV_PAD] == ks // 2
+              and i[L.CONV_C1] % 64 == 0 and i[L.CONV_C2] % 64 == 0 and i[L.CONV_COUT] % 32 == 0
+              and pow2(i[L.CONV_W]) and pow2(i[L.CONV_H]) and 4 <= i[L.CONV_W] <= 128)
+        return L.OK if ok else L.EUNSUPPORTED
+
+    def op_attn(self, qkv, HW, Cc):
+        o = self._acquire(*qkv.shape[:-1], Cc)
+        op = self._op(L.OP_ATTN)
+        op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = self.B, HW, Cc, self.acode
+        op.f[0] = float(int(Cc) ** (-0.5))
+        op.inp[0], op.out[0] = qkv.data_ptr(), o.data_ptr()
+        self._push(op)
+        return o
+
+    # ---------------------------------------------------------------- blocks
+    def resblock(self, m, x1, x2, temb_off):
+        """ResnetBlockBigGANpp.forward (reference layerspp.py:242-274)."""
+        net = self.net
+        N, H, W, _ = x1.shape
+        a = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W)
+        xs1, xs2 = x1, x2
+        fir_tmp = []
+        if m.up or m.down:
+            assert x2 is None
+            if net.fir:
+                if m.up:      # upsample_2d: upfirdn2d(up=2, pad=(2,1)), taps * factor^2 (:195-224)
+                    taps, up, down, p0, p1 = _fir_taps(net.fir_kernel, 4.0), 2, 1, 2, 1
+                else:         # downsample_2d: upfirdn2d(down=2, pad=(1,1)) (:227-257)
+                    taps, up, down, p0, p1 = _fir_taps(net.fir_kernel, 1.0), 1, 2, 1, 1
+            else:
+                if m.up:      # naive_upsample_2d: nearest x2
+                    taps, up, down, p0, p1 = np.ones((2, 2), np.float32), 2, 1, 1, 0
+                else:         # naive_downsample_2d: 2x2 mean
+                    taps, up, down, p0, p1 = np.full((2, 2), 0.25, np.float32), 1, 2, 0, 0
+            a2 = self.op_fir(a, taps, up, down, p0, p1)
+            self._release(a)
+            a = a2
+            xs1 = self.op_fir(x1, taps, up, down, p0, p1)
+            fir_tmp.append(xs1)
+        h = self.op_conv(a, None, m.Conv_0.weight, m.Conv_0.bias, ks=3, temb_off=temb_off)
+        self._release(a)
+        b = self.op_gn(h, None, m.GroupNorm_1, True, h.shape[1] * h.shape[2])
+        self._release(h)
+        if hasattr(m, "Conv_2"):
+            sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1)
+        else:
+            assert xs2 is None
+            sc = xs1
+        scale = _SQRT1_2 if net.skip_rescale else 1.0
+        out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
+                           out=self._new(*b.shape[:-1], m.out_ch))
+        self._release(b)
+        if hasattr(m, "Conv_2"):
+            self._release(sc)
+        for t in fir_tmp:
+            self._release(t)
+        return out
+
+    def attnblock(self, m, x):
+        """AttnBlockpp.forward (reference layerspp.py:75-91)."""
+        N, H, W, Cc = x.shape
+        a = self.op_gn(x, None, m.GroupNorm_0, False, H * W)
+        wqkv = torch.cat([m.NIN_0.W, m.NIN_1.W, m.NIN_2.W], dim=1)          # [C, 3C]
+        bqkv = torch.cat([m.NIN_0.b, m.NIN_1.b, m.NIN_2.b], dim=0)
+        qkv = self.op_conv(a, None, wqkv.t().reshape(3 * Cc, Cc, 1, 1), bqkv, ks=1)
+        self._release(a)
+        o = self.op_attn(qkv, H * W, Cc)
+        self._release(qkv)
+        scale = _SQRT1_2 if self.net.skip_rescale else 1.0
+        out = self.op_conv(o, None, m.NIN_3.W.t().reshape(Cc, Cc, 1, 1), m.NIN_3.b, ks=1,
+                           residual=x, scale=scale, out=self._new(N, H, W, Cc))
+        self._release(o)
+        return out
+
+    # ---------------------------------------------------------------- whole network
+    def _build(self):
+        net, B = self.net, self.B
+        mods = net.all_modules
+        H = net.image_size
+        self.gn_scratch = None
+        self.x_in = self._new(B, net.in_ch, H, H, dtype=torch.float32)        # NCHW fp32 input
+        self.time_buf = self._new(self.nt, dtype=torch.float32)
+        i = 0
+        # ---- time embedding + every Dense_0 projection in one op
+        if not net.noise_cond:
+            raise NotImplementedError("psld_b200 NCSNpp: noise_cond=False is not supported")
+        fourier_w = None
+        if net.embedding_type == "fourier":
+            fourier_w = self._w(mods[i].W); i += 1
+        lin0, lin1 = mods[i], mods[i + 1]; i += 2
+        rbs = [m for m in mods if hasattr(m, "Dense_0")]
+        offs, tot = {}, 0
+        for m in rbs:
+            offs[id(m)] = tot
+            tot += m.out_ch
+        self.total_c = tot
+        wd = self._w(torch.cat([m.Dense_0.weight for m in rbs], 0))
+        bd = self._w(torch.cat([m.Dense_0.bias for m in rbs], 0))
+        E = 2 * net.nf if net.embedding_type == "fourier" else net.nf
+        self.temb_proj = self._new(self.nt, tot, dtype=torch.float32)
+        scratch = self._new(self.nt, E + 8 * net.nf, dtype=torch.float32)
+        op = self._op(L.OP_TEMB)
+        op.i[L.TEMB_NT], op.i[L.TEMB_NF] = self.nt, net.nf
+        op.i[L.TEMB_EMB] = 0 if net.embedding_type == "fourier" else 1
+        op.i[L.TEMB_TOTALC], op.i[L.TEMB_LOGGED] = tot, int(self.logged)
+        op.inp[0] = self.time_buf.data_ptr()
+        op.inp[1] = fourier_w.data_ptr() if fourier_w is not None else None
+        op.inp[2], op.inp[3] = self._w(lin0.weight).data_ptr(), self._w(lin0.bias).data_ptr()
+        op.inp[4], op.inp[5] = self._w(lin1.weight).data_ptr(), self._w(lin1.bias).data_ptr()
+        op.inp[6], op.inp[7] = wd.data_ptr(), bd.data_ptr()
+        op.out[0], op.out[1] = self.temb_proj.data_ptr(), scratch.data_ptr()
+        self.temb_op = self._push(op)
+
+        # ---- input: NCHW fp32 -> NHWC activations
+        x = self._new(B, H, H, net.in_ch)
+        self.op_layout(self.x_in, x, B, net.in_ch, H * H, 0)
+        pyr = x if net.progressive_input != "none" else None
+        hs = [self.op_conv(x, None, mods[i].weight, mods[i].bias, ks=3,
+                           out=self._new(B, H, H, net.nf))]; i += 1
+        for lvl in range(net.num_resolutions):
+            for _ in range(net.num_res_blocks):
+                m = mods[i]; i += 1
+                h = self.resblock(m, hs[-1], None, offs[id(m)])
+                if h.shape[2] in net.attn_resolutions:
+                    h = self.attnblock(mods[i], h); i += 1
+                hs.append(h)
+            if lvl != net.num_resolutions - 1:
+                m = mods[i]; i += 1
+                h = self.resblock(m, hs[-1], None, offs[id(m)])
+                if net.progressive_input == "residual":
+                    pm = mods[i]; i += 1
+                    # conv_downsample_2d: upfirdn2d(pad=(2,2)) then conv(stride 2, pad 0) + bias,
+                    # merged with h: (pyr + h)/sqrt(2)   (ncsnpp.py:350-357)
+                    padded = self.op_fir(pyr, _fir_taps(net.fir_kernel, 1.0), 1, 1, 2, 2)
+                    scale = _SQRT1_2 if net.skip_rescale else 1.0
+                    pyr = self.op_conv(padded, None, pm.Conv2d_0.weight, pm.Conv2d_0.bias, ks=3,
+                                       stride=2, pad=0, residual=h, scale=scale,
+                                       out=self._new(*h.shape), allow_tc=False)
+                    self._release(padded)
+                    h = pyr
+                hs.append(h)
+        h = hs[-1]
+        m = mods[i]; i += 1
+        h = self.resblock(m, h, None, offs[id(m)])
+        h = self.attnblock(mods[i], h); i += 1
+        m = mods[i]; i += 1
+        h = self.resblock(m, h, None, offs[id(m)])
+        for lvl in reversed(range(net.num_resolutions)):
+            for _ in range(net.num_res_blocks + 1):
+                m = mods[i]; i += 1
+                h = self.resblock(m, h, hs.pop(), offs[id(m)])     # cat([h, skip]) is virtual
+            if h.shape[2] in net.attn_resolutions:
+                h = self.attnblock(mods[i], h); i += 1
+            if lvl != 0:
+                m = mods[i]; i += 1
+                h = self.resblock(m, h, None, offs[id(m)])
+        assert not hs
+        a = self.op_gn(h, None, mods[i], True, h.shape[1] * h.shape[2]); i += 1
+        self.eps = self.op_conv(a, None, mods[i].weight, mods[i].bias, ks=3, out_nchw_f32=True); i += 1
+        assert i == len(mods), (i, len(mods))
+
+    # ---------------------------------------------------------------- execution
+    def run(self, stream=None):
+        if self.dry:
+            raise RuntimeError("dry plan cannot run")
+        s = stream if stream is not None else L.stream_ptr(self.dev)
+        L.check(self.lib.psld_program_run(self.op_array, self.n_ops, s), "psld_program_run")
+
+    def release(self):
+        arr = self.__dict__.get("op_array")
+        if arr is not None:
+            for k in range(self.n_ops):
+                if arr[k].aux:
+                    self.lib.psld_op_release(C.byref(arr[k]))
+        self.__dict__["op_array"] = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def build_plan(net, B, nt, logged, dry=False):
+    with torch.no_grad():
+        return Plan(net, B, nt, logged, dry=dry)

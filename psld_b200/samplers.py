@@ -1,0 +1,223 @@
+"""SSCS and Euler-Maruyama samplers on the fused sm_100a phase-space kernels.
+
+Drop-in for the reference's ``SSCSSampler`` / ``EulerMaruyamaSampler``
+(``main/samplers/sde.py:9-58,227-370``; base class ``main/samplers/base.py:4-31``):
+
+  ``cls(config, sde, score_fn, corrector_fn=None)``
+  ``.sample(batch[B,2C,H,W], ts f64[n+1], n_discrete_steps, denoise=True, eps=1e-3) -> Tensor``
+  attributes ``.nfe``, property ``.n_steps``; identity corrector by default.
+
+Two execution paths, both on the GPU, neither with a CPU/eager fallback for the update:
+  * ``score_fn`` is a :class:`psld_b200.ncsnpp.NCSNpp`  ->  the whole loop runs natively in
+    ``psld_sampler_run`` (one C call; per step = network program + ONE fused update kernel);
+  * any other callable ``score_fn(u f32, t f32[B]) -> eps``  ->  a thin Python loop that calls
+    ``score_fn`` and the same fused kernels (``psld_sscs_update`` / ``psld_em_update``).
+
+Noise: ``sampler.noise`` may hold pre-drawn N(0,1) tensors ``[draws,B,2C,H,W]`` (fp32) in the
+reference's ``randn_like`` draw order for parity runs; otherwise the kernels
+draw from Philox4x32-10 (seed = ``config.evaluation.seed`` + rank, cf. wrapper.py:93-99).
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+from .ncsnpp import NCSNpp
+from .registry import register_module
+from .schedule import PSLDSchedule, StepTables
+
+
+class Sampler(abc.ABC):
+    """The abstract sampler (reference base.py:4-31)."""
+
+    def __init__(self, config, sde, score_fn, corrector_fn=None):
+        super().__init__()
+        self.config = config
+        self.sde = sde
+        self.score_fn = score_fn
+        self.corrector_fn = corrector_fn
+
+    @property
+    def n_steps(self):
+        return self.config.evaluation.n_discrete_steps
+
+    @abc.abstractmethod
+    def predictor_update_fn(self):
+        raise NotImplementedError
+
+    def corrector_update_fn(self, x, t, dt):
+        if self.corrector_fn is not None:
+            return self.corrector_fn(x, t, dt)
+        return x, x
+
+    @abc.abstractmethod
+    def sample(self):
+        raise NotImplementedError
+
+
+def _opt(config, key, default):
+    s = getattr(config.evaluation, "sampler", None)
+    try:
+        v = s.get(key, None) if hasattr(s, "get") else getattr(s, key, None)
+    except Exception:
+        v = None
+    return default if v is None else v
+
+
+class _FusedSampler(Sampler):
+    KIND = ""
+
+    def __init__(self, config, sde, score_fn, corrector_fn=None):
+        super().__init__(config, sde, score_fn, corrector_fn=corrector_fn)
+        self.schedule = sde if isinstance(sde, PSLDSchedule) else PSLDSchedule.from_sde(sde)
+        # options (extra keys under evaluation.sampler.*, all optional)
+        sd = str(_opt(config, "state_dtype", os.environ.get("PSLD_B200_STATE", "float64")))
+        self.state_dtype = torch.float64 if sd in ("float64", "f64", "fp64") else torch.float32
+        self.fuse_halves = bool(_opt(config, "fuse_halves", True))
+        self.seed = int(getattr(config.evaluation, "seed", 0)) + int(os.environ.get("RANK", "0"))
+        self.noise = None          # optional pre-drawn noise bank (parity mode)
+        self.record = None         # optional [n, B,2C,H,W] buffer filled with per-step states
+        self.nfe = 0
+
+    # the reference exposes this name; the fused kernels implement it
+    def predictor_update_fn(self, *a, **k):
+        raise NotImplementedError("psld_b200 samplers fuse the predictor step into sample()")
+
+    def _embedding(self):
+        return getattr(self.score_fn, "embedding_type", "fourier")
+
+    def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
+        lib = L.lib()
+        n = int(n_discrete_steps)
+        self.nfe = n
+        native = isinstance(self.score_fn, NCSNpp)
+        if native:
+            dev = next(self.score_fn.parameters()).device
+        else:
+            dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
+        if batch.dim() != 4 or batch.shape[1] % 2:
+            raise ValueError(f"expected a [B,2C,H,W] phase-space batch, got {tuple(batch.shape)}")
+        B, C2, H, W = batch.shape
+        chw = (C2 // 2) * H * W
+        if chw % 4:
+            raise ValueError("C*H*W must be a multiple of 4")
+        with torch.no_grad(), torch.cuda.device(dev):
+            state = batch.to(device=dev, dtype=self.state_dtype, non_blocking=True).contiguous()
+            if state.data_ptr() == batch.data_ptr():
+                state = state.clone()
+            tabs = StepTables(self.schedule, ts.detach().to("cpu", torch.float64), n, self.KIND,
+                              bool(denoise), float(eps), self._embedding())
+            noise = None
+            if self.noise is not None:
+                noise = self.noise.to(device=dev, dtype=torch.float32).contiguous()
+                need = (2 * n if self.KIND == "sscs_sde" else n)
+                if noise.shape[0] < need or tuple(noise.shape[1:]) != (B, C2, H, W):
+                    raise ValueError(f"noise bank must be [{need},{B},{C2},{H},{W}], got {tuple(noise.shape)}")
+            record = None
+            if self.record is not None:
+                record = torch.empty(n, B, C2, H, W, dtype=self.state_dtype, device=dev)
+            sdt = L.dtype_code(self.state_dtype)
+            stream = L.stream_ptr(dev)
+            if native and self.corrector_fn is None:
+                self._run_native(lib, state, tabs, n, denoise, B, chw, noise, record, sdt, stream, dev)
+            else:
+                self._run_generic(lib, state, tabs, n, denoise, B, chw, noise, record, sdt, stream, dev,
+                                  ts)
+            if record is not None:
+                self.record = record
+        return state
+
+    # ------------------------------------------------------------------ native loop
+    def _run_native(self, lib, state, tabs, n, denoise, B, chw, noise, record, sdt, stream, dev):
+        plan = self.score_fn.plan(B, 1, True)
+        plan.x_in.copy_(state)                       # fp32 network input = f32(prior)
+        table = tabs.time_table.to(dev)
+        d = L.SamplerDesc()
+        d.sampler = 0 if self.KIND == "sscs_sde" else 1
+        d.n_steps, d.denoise, d.state_dtype = n, int(bool(denoise)), sdt
+        d.fuse_halves = int(self.fuse_halves and record is None)
+        d.temb_op = plan.temb_op
+        d.B, d.chw, d.seed = B, chw, self.seed
+        d.state, d.net_in, d.eps = state.data_ptr(), plan.x_in.data_ptr(), plan.eps.data_ptr()
+        d.time_table = table.data_ptr()
+        d.noise = noise.data_ptr() if noise is not None else None
+        if tabs.sscs is not None:
+            d.sscs = C.cast(tabs.sscs, C.POINTER(L.SscsCoeffs))
+        if tabs.em is not None:
+            d.em = C.cast(tabs.em, C.POINTER(L.ScoreStep))
+        if tabs.den is not None:
+            d.den = C.pointer(tabs.den)
+        d.record = record.data_ptr() if record is not None else None
+        L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d), stream),
+                "psld_sampler_run")
+        self._keep = (table, noise, tabs, plan)       # keep alive until the stream drains
+
+    # ------------------------------------------------------------------ generic score_fn
+    def _run_generic(self, lib, state, tabs, n, denoise, B, chw, noise, record, sdt, stream, dev,
+                     ts):
+        net_in = state.to(torch.float32)
+        tau32 = tabs.tau32.to(dev)
+        z = (lambda k: L.ptr(noise[k])) if noise is not None else (lambda k: None)
+        sp, ip = L.ptr(state), L.ptr(net_in)
+
+        def score(i):
+            e = self.score_fn(net_in, tau32[i].expand(B))
+            return e.to(torch.float32).contiguous()
+
+        fuse = self.fuse_halves and record is None and self.corrector_fn is None
+        if self.KIND == "sscs_sde":
+            if fuse and n > 0:
+                L.check(lib.psld_sscs_update(sp, sp, sdt, ip, None, z(0), None, None,
+                                             C.byref(tabs.sscs[0]), L.STAGE_HALF_A, self.seed, 0, B,
+                                             chw, stream), "psld_sscs_update")
+            for i in range(n):
+                if not fuse:
+                    L.check(lib.psld_sscs_update(sp, sp, sdt, ip, None, z(2 * i), None, None,
+                                                 C.byref(tabs.sscs[i]), L.STAGE_HALF_A, self.seed,
+                                                 i, B, chw, stream), "psld_sscs_update")
+                e = score(i)
+                stages = L.STAGE_SCORE | L.STAGE_HALF_B
+                if fuse and i + 1 < n:
+                    stages |= L.STAGE_HALF_C
+                L.check(lib.psld_sscs_update(sp, sp, sdt, ip, L.ptr(e), None, z(2 * i + 1),
+                                             z(2 * i + 2) if (noise is not None and 2 * i + 2 < noise.shape[0]) else None,
+                                             C.byref(tabs.sscs[i]), stages, self.seed, i, B, chw,
+                                             stream), "psld_sscs_update")
+                self._post_step(state, net_in, record, i, ts)
+        else:
+            for i in range(n):
+                e = score(i)
+                L.check(lib.psld_em_update(sp, sp, sdt, ip, L.ptr(e), z(i), 0 if noise is not None else 1,
+                                           C.byref(tabs.em[i]), self.seed, i, B, chw, stream),
+                        "psld_em_update")
+                self._post_step(state, net_in, record, i, ts)
+        if denoise:
+            e = score(n)
+            L.check(lib.psld_em_update(sp, sp, sdt, ip, L.ptr(e), None, 0, C.byref(tabs.den),
+                                       self.seed, n, B, chw, stream), "psld_em_update")
+
+    def _post_step(self, state, net_in, record, i, ts):
+        if self.corrector_fn is not None:
+            new, _ = self.corrector_update_fn(state, ts[i], ts[i + 1] - ts[i])
+            state.copy_(new)
+            net_in.copy_(state)
+        if record is not None:
+            record[i].copy_(state)
+
+
+@register_module(category="samplers", name="sscs_sde_b200")
+class SSCSSampler(_FusedSampler):
+    """Symmetric-splitting sampler for PSLD (reference sde.py:227-370)."""
+    KIND = "sscs_sde"
+
+
+@register_module(category="samplers", name="em_sde_b200")
+class EulerMaruyamaSampler(_FusedSampler):
+    """Euler-Maruyama sampler (reference sde.py:8-58)."""
+    KIND = "em_sde"
