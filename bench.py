@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — PSLD CIFAR-10 SSCS sampling throughput (samples/sec) on N B200s.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N>1 under torchrun) prints
+ONE JSON line on rank 0.  A "step" is one SSCS predictor step (one NCSN++ score_fn call + one
+fused phase-space update) over the per-GPU batch; samples/sec = batch_total / (NFE * step time)
+with NFE = 1000 network calls per sample (BASELINE.json configs[1]: n_discrete_steps=1000).
+
+  value ...... device-timed (CUDA events, max over ranks), inputs resident in HBM
+  e2e ........ the same metric through the public API ``SSCSSampler.sample`` from a pinned HOST
+               prior to a HOST result, full 1000-NFE run, H2D/D2H inside the timed region
+  roofline ... dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs / CUDA-event time
+               vs the measured cuBLAS bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port of the reference path on the host cores (rank 0, N=1)
+
+``--impl reference`` times the reference's CPU implementation of the path (oracle port; the
+reference is Python and cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NFE = 1000
+FLOP_PER_SAMPLE_NFE = 76.43e9          # BASELINE.md §2 (CIFAR-10 NCSN++), 2*MAC
+METRIC = "PSLD CIFAR-10 samples/sec (SSCS sampler)"
+UNIT = "samples/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--state", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--e2e-nfe", type=int, default=NFE, help="0 disables the end-to-end run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--profile-ops", type=int, default=2, help="per-op event timing iterations")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0,
+            "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ======================================================================== reference arm (CPU)
+def run_cpu_port(cfg, batch, steps, warmup, threads=None):
+    """Times the oracle port of SSCSSampler.sample on the host cores: `steps` predictor steps
+    (one score_fn call + the half-step algebra each) on `batch` samples."""
+    import numpy as np
+    import torch
+    from oracle import psld_oracle as O
+    from oracle.weights import fill_state_dict, noise_bank, prior
+    from psld_b200 import NCSNpp
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    H = cfg.data.image_size
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    sd = fill_state_dict(shapes, 0)
+    score = O.OracleScoreFn(cfg, sd)
+    ts, n = O.time_grid(cfg)
+    u0 = prior((batch, 3, H, H), 0.5, 1)
+
+    def go(k):
+        nb = noise_bank(2 * k, (batch, 6, H, H), 2)
+        t0 = time.perf_counter()
+        O.sscs_sample(cfg, score, u0, ts, k, nb, denoise=False)
+        return time.perf_counter() - t0
+
+    if warmup > 0:
+        go(warmup)
+    dt = go(steps)
+    per_step = dt / steps
+    return {"value": batch / (NFE * per_step), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle port of SSCSSampler.sample, CIFAR-10 NCSN++ fp32, batch {batch}, "
+                      f"{steps} of {NFE} NFE timed after {warmup} warm-up, extrapolated linearly",
+            "ms_per_step": per_step * 1e3, "sample_nfe_per_sec": batch / per_step}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from psld_b200 import cifar10_config
+    cfg = cifar10_config()
+    batch = args.cpu_batch
+    # bound the run: (steps+warmup) CPU steps of ~0.17 s/sample each must end within minutes
+    per_sample_est = 0.2
+    while batch > 1 and (args.steps + args.warmup) * batch * per_sample_est > 240:
+        batch //= 2
+    r = run_cpu_port(cfg, batch, args.steps, args.warmup)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "PSLD CIFAR-10 NCSN++ (nf=128, ch_mult=[2,2,2], 8 res blocks, "
+                                   "attn@16, fir, fourier), SSCS sampler, 1000 NFE, random-init weights",
+                       "cpu_batch": batch},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================== B200 arm
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from psld_b200 import NCSNpp, PSLD, SSCSSampler, cifar10_config, time_grid
+    from psld_b200 import _lib as L
+    from psld_b200.distributed import env_rank, gather_samples, max_over_ranks
+    from psld_b200.profiling import profile_plan
+    from psld_b200.schedule import StepTables
+    import ctypes as C
+
+    rank, world, local = env_rank()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    cfg = cifar10_config(batch_size=args.batch, n_samples=args.batch * world)
+    cfg.evaluation.sampler["state_dtype"] = args.state
+    torch.manual_seed(1234)
+    net = NCSNpp(cfg).eval().set_precision(args.precision).to(dev)   # random-init weights
+    sde = PSLD(cfg)
+    S = SSCSSampler(cfg, sde, net)
+    B = args.batch
+    chw = 3 * 32 * 32
+    ts, n = time_grid(cfg)
+    plan = net.plan(B, 1, True)
+    lib = L.lib()
+    stream = L.stream_ptr(dev)
+
+    # ---- device-resident loop pieces: K predictor steps of the real 1000-step schedule
+    state_dtype = torch.float32 if args.state == "float32" else torch.float64
+    state = sde.prior_sampling_device((B, 3, 32, 32), seed=1 + rank, device=dev).to(state_dtype)
+    plan.x_in.copy_(state)
+
+    def run_steps(first, count):
+        tabs = StepTables(sde, ts[first:first + count + 1], count, "sscs_sde", False, 1e-3)
+        table = tabs.time_table.to(dev)
+        d = L.SamplerDesc()
+        d.sampler, d.n_steps, d.denoise = 0, count, 0
+        d.state_dtype = L.dtype_code(state_dtype)
+        d.fuse_halves, d.temb_op = 1, plan.temb_op
+        d.B, d.chw, d.seed = B, chw, 99 + rank
+        d.state, d.net_in, d.eps = state.data_ptr(), plan.x_in.data_ptr(), plan.eps.data_ptr()
+        d.time_table = table.data_ptr()
+        d.sscs = C.cast(tabs.sscs, C.POINTER(L.SscsCoeffs))
+        L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d), stream), "sampler_run")
+        return table, tabs
+
+    keep = run_steps(0, max(args.warmup, 3))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    keep2 = run_steps(args.warmup, args.steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop() if clocks is not None else None
+    ms_per_step = ms_total / args.steps
+    value = B * world / (NFE * ms_per_step * 1e-3)
+    # first-half-step launch + per step (program + fused update)
+    launches = 1 + args.steps * (plan.launches + 1)
+    finite = bool(torch.isfinite(state).all().item())
+
+    # ---- per-kernel roofline from CUDA-event timing of every op
+    prof = profile_plan(plan, iters=max(1, args.profile_ops)) if args.profile_ops > 0 else {}
+    roof = None
+    if "conv_tc" in prof:
+        c = prof["conv_tc"]
+        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, bf16)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + ", sustained",
+                "launches_per_step": c["n"], "avg_launch_ms": c["launch_ms"],
+                "share_of_step": c["ms"] / sum(v["ms"] for v in prof.values())}
+    elif "conv_simt" in prof:
+        c = prof["conv_simt"]
+        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_simt_kernel (fp32 FFMA)", "achieved": ach,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": None, "peak_source": pk["src"]}
+    # fused phase-space update alone (HBM-bound), timed at this batch
+    upd = time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts)
+    upd["peak"] = pk["hbm"]
+    upd["frac"] = upd["achieved"] / pk["hbm"]
+
+    # ---- end to end through the public API: pinned host prior -> HOST samples
+    e2e = None
+    if args.e2e_nfe > 0:
+        cfg_e = cifar10_config(batch_size=B, n_samples=B * world, n_discrete_steps=args.e2e_nfe)
+        cfg_e.evaluation.sampler["state_dtype"] = args.state
+        Se = SSCSSampler(cfg_e, sde, net)
+        ts_e, n_e = time_grid(cfg_e)
+        host_prior = sde.prior_sampling([B, 3, 32, 32]).pin_memory()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        out = Se.sample(host_prior, ts_e, n_e, denoise=True, eps=1e-3)
+        x = gather_samples(out)                       # single NCCL all-gather of the x half
+        host = x.to("cpu", non_blocking=False)
+        torch.cuda.synchronize(dev)
+        dt = max_over_ranks(time.perf_counter() - t0, dev)
+        scale = NFE / float(args.e2e_nfe)
+        e2e = {"value": B * world / (dt * scale), "unit": UNIT,
+               "h2d_bytes_per_step": int(host_prior.numel() * 4),
+               "d2h_bytes_per_step": int(host.numel() * host.element_size()),
+               "seconds": dt, "nfe": args.e2e_nfe, "api": "SSCSSampler.sample + gather_samples",
+               "finite": bool(torch.isfinite(host).all().item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_port(cifar10_config(), args.cpu_batch, args.cpu_steps, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {
+                "workload": "PSLD CIFAR-10 NCSN++ (nf=128, ch_mult=[2,2,2], 8 res blocks, attn@16, fir, "
+                            "fourier), SSCS sampler, 1000 NFE, random-init weights (BASELINE configs[1])",
+                "batch_per_gpu": B, "batch_total": B * world, "nfe_per_sample": NFE,
+                "state_dtype": args.state, "noise": "in-kernel Philox4x32-10",
+                "step": "one SSCS predictor step = 1 score_fn call + 1 fused update",
+                "l2": "activations per step (GBs at B=256) exceed the 126 MB L2; no flush needed",
+                "parallelism": f"batch-sharded x{world}, no per-step communication",
+            },
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "roofline_update": upd, "cpu_baseline": cpu,
+            "tensor_frac_of_step": (FLOP_PER_SAMPLE_NFE * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
+            "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+            "engines": plan.engine_count, "finite": finite,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts):
+    """Fused SCORE+HALF_B+HALF_C update alone, CUDA events, 20 launches."""
+    import ctypes as C
+    import torch
+    from psld_b200 import _lib as L
+    from psld_b200.schedule import StepTables
+    tabs = StepTables(sde, ts[:3], 2, "sscs_sde", False, 1e-3)
+    sdt = L.dtype_code(state_dtype)
+    stages = L.STAGE_SCORE | L.STAGE_HALF_B | L.STAGE_HALF_C
+    sp, ip, ep = L.ptr(state), L.ptr(plan.x_in), L.ptr(plan.eps)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total = 0.0
+    reps = 10
+    for r in range(reps + 2):
+        flush.zero_()                                  # evict L2 between timed launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        L.check(lib.psld_sscs_update(sp, sp, sdt, ip, ep, None, None, None, C.byref(tabs.sscs[0]),
+                                     stages, 5, r, B, chw, stream), "update")
+        b.record()
+        torch.cuda.synchronize(dev)
+        if r >= 2:
+            total += a.elapsed_time(b)
+    ms = total / reps
+    sb = 8 if state_dtype == torch.float64 else 4
+    per_pair = 2 * sb * 2 + 8 + 8          # state in+out, eps in, fp32 net_in out (Philox noise)
+    byts = per_pair * B * chw
+    return {"bound": "hbm", "kernel": "sscs_update_kernel (score + 2 half-steps, Philox)",
+            "achieved": byts / (ms * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_pair": per_pair,
+            "pairs": B * chw, "avg_launch_ms": ms, "l2": "256 MB flush between launches",
+            "traffic": None}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

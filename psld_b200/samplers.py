@@ -185,8 +185,8 @@ class _FusedSampler(Sampler):
                 stages = L.STAGE_SCORE | L.STAGE_HALF_B
                 if fuse and i + 1 < n:
                     stages |= L.STAGE_HALF_C
-                L.check(lib.psld_sscs_update(sp, sp, sdt, ip, L.ptr(e), None, z(2 * i + 1),
-                                             z(2 * i + 2) if (noise is not None and 2 * i + 2 < noise.shape[0]) else None,
+                zc = z(2 * i + 2) if (stages & L.STAGE_HALF_C) else None
+                L.check(lib.psld_sscs_update(sp, sp, sdt, ip, L.ptr(e), None, z(2 * i + 1), zc,
                                              C.byref(tabs.sscs[i]), stages, self.seed, i, B, chw,
                                              stream), "psld_sscs_update")
                 self._post_step(state, net_in, record, i, ts)

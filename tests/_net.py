@@ -1,0 +1,33 @@
+"""Test helpers: seeded networks / samplers on the GPU and the oracle beside them."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import psld_oracle as O
+from oracle.weights import fill_state_dict, noise_bank, prior
+from psld_b200 import NCSNpp
+
+
+def make_net(cfg, precision, seed=0, device="cuda"):
+    net = NCSNpp(cfg).eval()
+    net.set_precision(precision)
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
+    net.load_state_dict(sd)
+    if device is not None:
+        net = net.to(device)
+    return net, sd
+
+
+def sampler_inputs(cfg, B, n, kind, seed_p=1, seed_n=2):
+    H = cfg.data.image_size
+    sde = O.PSLDScalars(cfg)
+    per = 2 if kind == "sscs_sde" else 1
+    nb = noise_bank(per * n, (B, 6, H, H), seed_n)
+    u0 = prior((B, 3, H, H), float(np.sqrt(sde.m)), seed_p)
+    return u0, nb
+
+
+def fake_score(u, t):
+    """Same deterministic stand-in network as oracle/make_golden.py (device-agnostic)."""
+    return (torch.tanh(u * 0.3) * 0.7 + 0.1 * torch.sin(torch.roll(u, 1, 1))) * t.view(-1, 1, 1, 1)

@@ -1,0 +1,162 @@
+"""Test helpers: build single ``psld_op`` records and run them through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from psld_b200 import _lib as L
+
+
+def code(t):
+    return L.dtype_code(t.dtype)
+
+
+def run_op(op, prepare=False):
+    lib = L.lib()
+    if prepare:
+        L.check(lib.psld_op_prepare(C.byref(op)), "prepare")
+    try:
+        L.check(lib.psld_op_run(C.byref(op), L.stream_ptr()), "run")
+        torch.cuda.synchronize()
+    finally:
+        if prepare:
+            lib.psld_op_release(C.byref(op))
+
+
+def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=None, temb_off=0,
+            temb_bstride=0, scale=1.0, engine=L.ENGINE_SIMT, out_nchw_f32=False, out=None):
+    """x*: NHWC tensors on cuda.  Returns (op, out, keepalive)."""
+    N, H, W, C1 = x1.shape
+    C2 = x2.shape[-1] if x2 is not None else 0
+    Cout, Cin, ks, _ = w_oihw.shape
+    assert Cin == C1 + C2
+    pad = ks // 2 if pad is None else pad
+    OH = (H + 2 * pad - ks) // stride + 1
+    OW = (W + 2 * pad - ks) // stride + 1
+    dev = x1.device
+    keep = []
+    op = L.Op()
+    op.kind, op.engine = L.OP_CONV, engine
+    i = op.i
+    i[L.CONV_N], i[L.CONV_H], i[L.CONV_W], i[L.CONV_C1], i[L.CONV_C2] = N, H, W, C1, C2
+    i[L.CONV_COUT], i[L.CONV_KS], i[L.CONV_STRIDE], i[L.CONV_PAD] = Cout, ks, stride, pad
+    i[L.CONV_OH], i[L.CONV_OW] = OH, OW
+    i[L.CONV_IN_LAYOUT] = L.NHWC
+    i[L.CONV_OUT_LAYOUT] = L.NCHW if out_nchw_f32 else L.NHWC
+    i[L.CONV_IN_DTYPE] = code(x1)
+    i[L.CONV_OUT_DTYPE] = L.F32 if out_nchw_f32 else code(x1)
+    i[L.CONV_RES_DTYPE] = code(x1)
+    i[L.CONV_TEMB_OFF], i[L.CONV_TEMB_BSTRIDE] = temb_off, temb_bstride
+    op.f[0] = scale
+    cout_k = Cout
+    w = w_oihw.to(dev, torch.float32)
+    b = bias.to(dev, torch.float32).contiguous() if bias is not None else None
+    if engine == L.ENGINE_TC:
+        if out_nchw_f32 and Cout % 32:
+            cout_k = -(-Cout // 32) * 32
+        wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+        if cout_k != Cout:
+            wt = torch.cat([wt, wt.new_zeros(cout_k - Cout, wt.shape[1])], 0)
+            if b is not None:
+                b = torch.cat([b, b.new_zeros(cout_k - Cout)])
+        wp = wt.to(torch.bfloat16).contiguous()
+        i[L.CONV_COUT] = cout_k
+        op.f[1] = float(Cout)
+    else:
+        wp = w.permute(2, 3, 1, 0).reshape(-1, Cout).contiguous()
+    keep += [wp, b]
+    if out is None:
+        if out_nchw_f32:
+            out = torch.full((N, Cout, OH, OW), float("nan"), dtype=torch.float32, device=dev)
+        else:
+            out = torch.full((N, OH, OW, Cout), float("nan"), dtype=x1.dtype, device=dev)
+    op.inp[0] = x1.data_ptr()
+    op.inp[1] = x2.data_ptr() if x2 is not None else None
+    op.inp[2] = residual.data_ptr() if residual is not None else None
+    op.inp[3] = temb.data_ptr() if temb is not None else None
+    op.inp[4] = wp.data_ptr()
+    op.inp[5] = b.data_ptr() if b is not None else None
+    op.out[0] = out.data_ptr()
+    return op, out, keep
+
+
+def conv_ref(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=None, temb_off=0,
+             temb_bstride=0, scale=1.0):
+    """CPU fp32/fp64 reference of the op semantics (inputs NHWC, any device)."""
+    import torch.nn.functional as F
+    ks = w_oihw.shape[-1]
+    pad = ks // 2 if pad is None else pad
+    xx = x1.double().cpu() if x2 is None else torch.cat([x1.double().cpu(), x2.double().cpu()], -1)
+    y = F.conv2d(xx.permute(0, 3, 1, 2), w_oihw.double().cpu(),
+                 bias.double().cpu() if bias is not None else None, stride=stride, padding=pad)
+    Cout = w_oihw.shape[0]
+    if temb is not None:
+        tp = temb.double().cpu()
+        rows = tp.reshape(-1)[temb_off:temb_off + Cout][None].expand(y.shape[0], -1) if temb_bstride == 0 \
+            else tp[:, temb_off:temb_off + Cout]
+        y = y + rows[:, :, None, None]
+    if residual is not None:
+        y = y + residual.double().cpu().permute(0, 3, 1, 2)
+    return (y * scale)     # NCHW float64
+
+
+def gn_op(x1, x2, gamma, beta, G, silu, eps=1e-6, nchunk=4, out_dtype=None):
+    N = x1.shape[0]
+    HW = int(np.prod(x1.shape[1:-1]))
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    out = torch.full((*x1.shape[:-1], C1 + C2), float("nan"), dtype=out_dtype or x1.dtype, device=x1.device)
+    scratch = torch.zeros(N * nchunk * G * 2 + 16, dtype=torch.float64, device=x1.device)
+    op = L.Op()
+    op.kind = L.OP_GN
+    i = op.i
+    i[L.GN_N], i[L.GN_HW], i[L.GN_C1], i[L.GN_C2], i[L.GN_G] = N, HW, C1, C2, G
+    i[L.GN_SILU], i[L.GN_IN_DTYPE], i[L.GN_OUT_DTYPE], i[L.GN_NCHUNK] = int(silu), code(x1), code(out), nchunk
+    op.f[0] = eps
+    op.inp[0] = x1.data_ptr()
+    op.inp[1] = x2.data_ptr() if x2 is not None else None
+    op.inp[2], op.inp[3] = gamma.data_ptr(), beta.data_ptr()
+    op.out[0], op.out[1] = out.data_ptr(), scratch.data_ptr()
+    return op, out, [scratch]
+
+
+def fir_op(x, taps, up, down, pad0, pad1):
+    N, H, W, Cc = x.shape
+    KH = taps.shape[0]
+    OH = (H * up + pad0 + pad1 - KH) // down + 1
+    OW = (W * up + pad0 + pad1 - KH) // down + 1
+    out = torch.full((N, OH, OW, Cc), float("nan"), dtype=x.dtype, device=x.device)
+    op = L.Op()
+    op.kind = L.OP_FIR
+    i = op.i
+    i[L.FIR_N], i[L.FIR_H], i[L.FIR_W], i[L.FIR_C] = N, H, W, Cc
+    i[L.FIR_UP], i[L.FIR_DOWN], i[L.FIR_PAD0], i[L.FIR_PAD1] = up, down, pad0, pad1
+    i[L.FIR_KH], i[L.FIR_DTYPE] = KH, code(x)
+    for j, v in enumerate(np.asarray(taps, np.float32).reshape(-1)):
+        op.f[j] = float(v)
+    op.inp[0], op.out[0] = x.data_ptr(), out.data_ptr()
+    return op, out
+
+
+def attn_op(qkv, Cc):
+    N = qkv.shape[0]
+    HW = int(np.prod(qkv.shape[1:-1]))
+    out = torch.full((*qkv.shape[:-1], Cc), float("nan"), dtype=qkv.dtype, device=qkv.device)
+    op = L.Op()
+    op.kind = L.OP_ATTN
+    op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = N, HW, Cc, code(qkv)
+    op.f[0] = float(int(Cc) ** (-0.5))
+    op.inp[0], op.out[0] = qkv.data_ptr(), out.data_ptr()
+    return op, out
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def max_rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))

@@ -1,0 +1,343 @@
+"""GPU parity tests of every kernel through the C ABI, against the CPU oracle.
+
+Tolerances (stated, per kernel):
+  fused phase-space update, fp64 state ... max-abs/max|ref| <= 1e-13 (same algebra in double)
+  fused phase-space update, fp32 state ... <= 2e-6 relative (fp32 rounding of the state)
+  GroupNorm / FIR / temb / conv fp32 ...... rel-L2 <= 2e-6 (fp32 summation order)
+  bf16 storage paths ...................... rel-L2 <= 6e-3 (8-bit mantissa)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _ops import attn_op, conv_op, conv_ref, fir_op, gn_op, max_rel, rel_l2, run_op
+from oracle import psld_oracle as O
+from oracle.weights import noise_bank, prior
+from psld_b200 import _lib as L
+from psld_b200 import tiny_config
+from psld_b200.schedule import PSLDSchedule, StepTables
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+# ------------------------------------------------------------------ fused phase-space update
+def _half_ref(h, u, z):
+    x, m = torch.chunk(u, 2, 1)
+    zx, zm = torch.chunk(z.double(), 2, 1)
+    return torch.cat([h.a_xx * x + h.a_xm * m + (h.c11 * zx + h.c12 * zm),
+                      h.a_mx * x + h.a_mm * m + (h.c21 * zx + h.c22 * zm)], 1)
+
+
+def _score_ref(sc, u, eps):
+    """Oracle algebra of the SCORE stage from the table entry (psld.py:252-259, sde.py:325-328)."""
+    x, m = torch.chunk(u, 2, 1)
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    if sc.mode == 0:
+        ex, em = torch.chunk(eps, 2, 1)
+        sx = -f32(sc.li11) * ex - f32(sc.li12) * em
+        sm = -f32(sc.li21) * ex - f32(sc.li22) * em
+    elif sc.mode == 1:
+        sx, sm = torch.zeros_like(eps), -f32(sc.li22) * eps
+    else:
+        sx, sm = -f32(sc.li11) * eps, torch.zeros_like(eps)
+    x = x + sc.k_x * (sx.double() + x)
+    m = m + sc.k_m * (sm.double() + sc.m_inv * m)
+    return torch.cat([x, m], 1)
+
+
+@pytest.mark.parametrize("state_dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("gamma", [0.01, 0.0])
+def test_sscs_update_stages(state_dtype, gamma):
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=10)
+    cfg.model.sde.gamma = gamma
+    cfg.model.sde.nu = 4.01 if gamma else 4.0
+    sch = PSLDSchedule(cfg)
+    ts = torch.linspace(0, 0.999, 10, dtype=torch.float64)
+    tabs = StepTables(sch, ts, 9, "sscs_sde", True, 1e-3)
+    B, Cc, H = 3, 3, 8
+    chw = Cc * H * H
+    u0 = prior((B, Cc, H, H), 0.5, 3).double()
+    zs = noise_bank(3, (B, 2 * Cc, H, H), 4)
+    r = _rng(5)
+    e_ch = 2 * Cc if gamma else Cc
+    eps = torch.from_numpy(r.standard_normal((B, e_ch, H, H)).astype(np.float32))
+    co = tabs.sscs[4]
+    lib = L.lib()
+    for stages in [1, 2, 4, 6, 14, 15]:
+        ref = u0.clone()
+        if stages & 1:
+            ref = _half_ref(co.half_a, ref, zs[0])
+        if stages & 2:
+            ref = _score_ref(co.score, ref, eps)
+        if stages & 4:
+            ref = _half_ref(co.half_b, ref, zs[1])
+        if stages & 8:
+            ref = _half_ref(co.half_c, ref, zs[2])
+        u = u0.to(DEV, state_dtype).contiguous()
+        out = torch.empty_like(u)
+        net_in = torch.empty(B, 2 * Cc, H, H, dtype=torch.float32, device=DEV)
+        zd = [z.to(DEV) for z in zs]
+        ed = eps.to(DEV)
+        L.check(lib.psld_sscs_update(L.ptr(out), L.ptr(u), L.dtype_code(state_dtype), L.ptr(net_in),
+                                     L.ptr(ed), L.ptr(zd[0]), L.ptr(zd[1]), L.ptr(zd[2]),
+                                     C.byref(co), stages, 0, 0, B, chw, L.stream_ptr()), "sscs")
+        torch.cuda.synchronize()
+        tol = 1e-13 if state_dtype == torch.float64 else 2e-6
+        assert max_rel(out, ref) <= tol, (stages, max_rel(out, ref))
+        assert torch.equal(net_in.cpu(), out.cpu().to(torch.float32))
+
+
+@pytest.mark.parametrize("state_dtype", [torch.float64, torch.float32])
+def test_em_update(state_dtype):
+    cfg = tiny_config(sampler="em_sde", n_discrete_steps=10)
+    sch = PSLDSchedule(cfg)
+    ts = torch.linspace(0, 0.999, 10, dtype=torch.float64)
+    tabs = StepTables(sch, ts, 9, "em_sde", True, 1e-3)
+    B, Cc, H = 2, 3, 8
+    u0 = prior((B, Cc, H, H), 0.5, 3).double()
+    z = noise_bank(1, (B, 2 * Cc, H, H), 4)[0]
+    eps = torch.from_numpy(_rng(5).standard_normal((B, 2 * Cc, H, H)).astype(np.float32))
+    lib = L.lib()
+    for co, zz in [(tabs.em[3], z), (tabs.den, None)]:
+        x, m = torch.chunk(u0, 2, 1)
+        f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+        ex, em = torch.chunk(eps, 2, 1)
+        sx = (-f32(co.li11) * ex - f32(co.li12) * em).double()
+        sm = (-f32(co.li21) * ex - f32(co.li22) * em).double()
+        fx = co.half_beta * (co.m_inv * m - co.gamma * x)
+        fm = co.half_beta * (-co.nu * m - x)
+        nx = x + (-fx + co.g2_x * sx) * co.dt
+        nm = m + (-fm + co.g2_m * sm) * co.dt
+        if zz is not None:
+            zx, zm = torch.chunk(zz.double(), 2, 1)
+            nx, nm = nx + co.gs_x * zx, nm + co.gs_m * zm
+        ref = torch.cat([nx, nm], 1)
+        u = u0.to(DEV, state_dtype).contiguous()
+        out = torch.empty_like(u)
+        L.check(lib.psld_em_update(L.ptr(out), L.ptr(u), L.dtype_code(state_dtype), None,
+                                   L.ptr(eps.to(DEV)), L.ptr(zz.to(DEV)) if zz is not None else None,
+                                   0, C.byref(co), 0, 0, B, Cc * H * H, L.stream_ptr()), "em")
+        torch.cuda.synchronize()
+        tol = 1e-13 if state_dtype == torch.float64 else 2e-6
+        assert max_rel(out, ref) <= tol, max_rel(out, ref)
+
+
+def test_philox_noise_and_prior():
+    lib = L.lib()
+    B, chw = 64, 3072
+    u = torch.empty(B, 6, 32, 32, dtype=torch.float32, device=DEV)
+    L.check(lib.psld_prior_sample(L.ptr(u), 0.5, 123, B, chw, L.stream_ptr()), "prior")
+    x, m = torch.chunk(u.double().cpu(), 2, 1)
+    n = x.numel()
+    assert abs(x.mean()) < 5 / np.sqrt(n) and abs(x.var() - 1) < 0.02
+    assert abs(m.mean()) < 5 * 0.5 / np.sqrt(n) and abs(m.var() - 0.25) < 0.005
+    assert abs(float((x * m).mean())) < 5 * 0.5 / np.sqrt(n)
+    # different seeds decorrelate, same seed reproduces
+    u2 = torch.empty_like(u)
+    L.check(lib.psld_prior_sample(L.ptr(u2), 0.5, 123, B, chw, L.stream_ptr()), "prior")
+    assert torch.equal(u, u2)
+    L.check(lib.psld_prior_sample(L.ptr(u2), 0.5, 124, B, chw, L.stream_ptr()), "prior")
+    assert abs(float((u * u2).mean())) < 0.01
+    # a pure-noise half step with Philox has the requested 2x2 covariance
+    co = L.SscsCoeffs()
+    co.half_a.c11, co.half_a.c21, co.half_a.c22 = 0.7, -0.3, 0.4
+    z = torch.zeros(B, 6, 32, 32, dtype=torch.float64, device=DEV)
+    out = torch.empty_like(z)
+    L.check(lib.psld_sscs_update(L.ptr(out), L.ptr(z), L.F64, None, None, None, None, None,
+                                 C.byref(co), 1, 7, 3, B, chw, L.stream_ptr()), "sscs")
+    ox, om = torch.chunk(out.cpu(), 2, 1)
+    assert abs(ox.var() - 0.49) < 0.01 and abs(om.var() - (0.09 + 0.16)) < 0.01
+    assert abs(float((ox * om).mean()) - (-0.21)) < 0.01
+
+
+# ------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 0), (3, 8, 8, 256, 128), (2, 32, 32, 32, 64),
+                                   (1, 4, 4, 24, 0)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_groupnorm(dtype, tol, shape, silu):
+    N, H, W, C1, C2 = shape
+    r = _rng(11)
+    Cc = C1 + C2
+    G = min(Cc // 4, 32)
+    x1 = _t(r.standard_normal((N, H, W, C1)) * 2 + 0.7, dtype)
+    x2 = _t(r.standard_normal((N, H, W, C2)) * 0.5 - 1.0, dtype) if C2 else None
+    ga = _t(1 + 0.2 * r.standard_normal(Cc))
+    be = _t(0.1 * r.standard_normal(Cc))
+    op, out, keep = gn_op(x1, x2, ga, be, G, silu, nchunk=3)
+    run_op(op)
+    xx = x1.float().cpu() if x2 is None else torch.cat([x1.float().cpu(), x2.float().cpu()], -1)
+    ref = F.group_norm(xx.permute(0, 3, 1, 2), G, ga.cpu(), be.cpu(), eps=1e-6)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(out.float().permute(0, 3, 1, 2), ref) <= tol
+
+
+# ------------------------------------------------------------------ FIR / upfirdn2d
+def test_upfirdn2d_golden(golden_dir):
+    g = np.load(f"{golden_dir}/upfirdn.npz")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    lib = L.lib()
+    for name in ["down", "up", "pad", "generic", "crop"]:
+        up, down, p0, p1, gain = g["arg_" + name]
+        k = (g["k"] * gain).astype(np.float32)
+        y = torch.from_numpy(g["y_" + name])
+        out = torch.full(tuple(y.shape), float("nan"), dtype=torch.float32, device=DEV)
+        taps = (C.c_float * 16)(*k.reshape(-1))
+        L.check(lib.psld_upfirdn2d(L.ptr(x), L.ptr(out), taps, 4, 4, x.shape[0] * x.shape[1],
+                                   x.shape[2], x.shape[3], int(up), int(up), int(down), int(down),
+                                   int(p0), int(p1), int(p0), int(p1), L.stream_ptr()), "upfirdn2d")
+        torch.cuda.synchronize()
+        assert rel_l2(out, y) <= 2e-6, (name, rel_l2(out, y))
+        # NHWC op, fp32 and bf16, vectorised (C%4==0) and scalar channel counts
+        for Cc in (5, 8):
+            xn = torch.from_numpy(_rng(3).standard_normal((2, 8, 8, Cc)).astype(np.float32)).to(DEV)
+            ref = O.upfirdn2d(xn.cpu().permute(0, 3, 1, 2), k, up=int(up), down=int(down),
+                              pad=(int(p0), int(p1)))
+            for dt, tol in [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)]:
+                op, o = fir_op(xn.to(dt), k, int(up), int(down), int(p0), int(p1))
+                run_op(op)
+                refd = O.upfirdn2d(xn.to(dt).float().cpu().permute(0, 3, 1, 2), k, up=int(up),
+                                   down=int(down), pad=(int(p0), int(p1)))
+                assert rel_l2(o.float().permute(0, 3, 1, 2), refd) <= tol, (name, Cc, dt)
+
+
+# ------------------------------------------------------------------ convolution, CUDA-core engine
+CONV_SIMT_CASES = [
+    # N, H, W, C1, C2, Cout, ks, stride, pad
+    (2, 8, 8, 6, 0, 32, 3, 1, 1),       # input conv
+    (2, 8, 8, 32, 0, 6, 3, 1, 1),       # output conv
+    (2, 9, 9, 6, 0, 32, 3, 2, 0),       # pyramid stride-2 conv after FIR pad
+    (1, 16, 16, 64, 32, 64, 1, 1, 0),   # 1x1 shortcut over a virtual concat
+    (3, 8, 8, 96, 0, 64, 3, 1, 1),
+    (1, 5, 7, 20, 12, 10, 3, 1, 1),     # ragged everything
+]
+
+
+@pytest.mark.parametrize("case", CONV_SIMT_CASES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.bfloat16, 6e-3)])
+def test_conv_simt(case, dtype, tol):
+    N, H, W, C1, C2, Cout, ks, stride, pad = case
+    r = _rng(sum(case))
+    x1 = _t(r.standard_normal((N, H, W, C1)), dtype)
+    x2 = _t(r.standard_normal((N, H, W, C2)), dtype) if C2 else None
+    w = _t(r.standard_normal((Cout, C1 + C2, ks, ks)) / np.sqrt((C1 + C2) * ks * ks))
+    b = _t(0.1 * r.standard_normal(Cout))
+    OH = (H + 2 * pad - ks) // stride + 1
+    OW = (W + 2 * pad - ks) // stride + 1
+    res = _t(r.standard_normal((N, OH, OW, Cout)), dtype)
+    temb = _t(r.standard_normal((N, Cout + 5)))
+    kw = dict(stride=stride, pad=pad, residual=res, temb=temb, temb_off=5, temb_bstride=Cout + 5,
+              scale=0.7071)
+    op, out, keep = conv_op(x1, x2, w, b, **kw)
+    run_op(op)
+    wq = w if dtype == torch.float32 else w
+    ref = conv_ref(x1, x2, wq, b, **kw)
+    assert rel_l2(out.float().permute(0, 3, 1, 2), ref) <= tol
+    # NCHW fp32 head, shared temb row
+    op, out, keep = conv_op(x1, x2, w, b, stride=stride, pad=pad, temb=temb[:1].contiguous(),
+                            temb_off=2, temb_bstride=0, out_nchw_f32=True)
+    run_op(op)
+    ref = conv_ref(x1, x2, w, b, stride=stride, pad=pad, temb=temb[:1], temb_off=2, temb_bstride=0)
+    assert rel_l2(out, ref) <= (3e-6 if dtype == torch.float32 else 1e-5)
+
+
+# ------------------------------------------------------------------ convolution, tcgen05 engine
+CONV_TC_CASES = [
+    # N, H, W, C1, C2, Cout, ks
+    (2, 32, 32, 64, 0, 64, 1),
+    (2, 32, 32, 64, 0, 128, 3),
+    (1, 16, 16, 128, 0, 256, 3),
+    (3, 8, 8, 128, 64, 128, 1),        # two-source 1x1 shortcut, BN_img = 2 with an odd batch
+    (3, 8, 8, 256, 0, 256, 3),
+    (2, 16, 16, 256, 0, 768, 1),       # fused q|k|v projection, 3 N-tiles
+    (5, 4, 4, 64, 0, 96, 3),           # 4x4 maps, 8 images per tile, Cout = 3 x 32
+    (1, 64, 64, 64, 0, 32, 3),         # CelebA-size map
+    (2, 32, 32, 256, 256, 256, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES)
+def test_conv_tc(case):
+    N, H, W, C1, C2, Cout, ks = case
+    r = _rng(sum(case) + 1)
+    x1 = _t(r.standard_normal((N, H, W, C1)), torch.bfloat16)
+    x2 = _t(r.standard_normal((N, H, W, C2)), torch.bfloat16) if C2 else None
+    w = _t(r.standard_normal((Cout, C1 + C2, ks, ks)) / np.sqrt((C1 + C2) * ks * ks))
+    b = _t(0.1 * r.standard_normal(Cout))
+    res = _t(r.standard_normal((N, H, W, Cout)), torch.bfloat16)
+    temb = _t(r.standard_normal((N, Cout + 32)))
+    kw = dict(residual=res, temb=temb, temb_off=32, temb_bstride=Cout + 32, scale=0.7071)
+    op, out, keep = conv_op(x1, x2, w, b, engine=L.ENGINE_TC, **kw)
+    run_op(op, prepare=True)
+    ref = conv_ref(x1, x2, w.to(torch.bfloat16), b, **kw)      # same bf16-rounded weights
+    err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
+    assert err <= 4e-3, err                                     # bf16 output rounding only
+    # plain (no epilogue terms), checks the accumulation itself at fp32-output precision
+    op, out2, keep2 = conv_op(x1, x2, w, None, engine=L.ENGINE_TC, out_nchw_f32=True)
+    run_op(op, prepare=True)
+    ref2 = conv_ref(x1, x2, w.to(torch.bfloat16), None)
+    err2 = rel_l2(out2, ref2)
+    assert err2 <= 2e-5, err2
+
+
+def test_conv_tc_output_head():
+    """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
+    r = _rng(77)
+    x = _t(r.standard_normal((2, 32, 32, 128)), torch.bfloat16)
+    w = _t(r.standard_normal((6, 128, 3, 3)) / 34.0)
+    b = _t(0.1 * r.standard_normal(6))
+    op, out, keep = conv_op(x, None, w, b, engine=L.ENGINE_TC, out_nchw_f32=True)
+    run_op(op, prepare=True)
+    ref = conv_ref(x, None, w.to(torch.bfloat16), b)
+    assert out.shape == (2, 6, 32, 32)
+    assert rel_l2(out, ref) <= 2e-5
+
+
+def test_conv_tc_rejects_ineligible():
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 48, 3, 3, device=DEV)
+    op, out, keep = conv_op(x, None, w, None, engine=L.ENGINE_TC)
+    rc = L.lib().psld_op_prepare(C.byref(op))
+    assert rc == L.EUNSUPPORTED
+    assert b"Cin" in L.lib().psld_last_error()
+
+
+# ------------------------------------------------------------------ attention core
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 8, 8, 256), (2, 16, 16, 256), (1, 4, 4, 32)])
+def test_attention(dtype, tol, shape):
+    N, H, W, Cc = shape
+    r = _rng(9)
+    qkv = _t(r.standard_normal((N, H, W, 3 * Cc)), dtype)
+    op, out = attn_op(qkv, Cc)
+    run_op(op)
+    q, k, v = qkv.float().cpu().reshape(N, H * W, 3 * Cc).split(Cc, dim=-1)
+    wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
+    ref = torch.einsum("bqk,bkc->bqc", wgt, v)
+    assert rel_l2(out.float().reshape(N, H * W, Cc), ref) <= tol
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_codes():
+    lib = L.lib()
+    co = L.SscsCoeffs()
+    rc = lib.psld_sscs_update(None, None, L.F64, None, None, None, None, None, C.byref(co), 1, 0, 0,
+                              1, 12, None)
+    assert rc == L.EINVAL and b"null" in lib.psld_last_error()
+    u = torch.zeros(1, 6, 1, 1, dtype=torch.float64, device=DEV)
+    rc = lib.psld_sscs_update(L.ptr(u), L.ptr(u), L.F64, None, None, None, None, None, C.byref(co),
+                              1, 0, 0, 1, 3, None)
+    assert rc == L.EINVAL

@@ -1,0 +1,146 @@
+"""Sampler parity on the GPU: per-step states and final samples vs golden vectors produced by
+the reference sampler (identical weights, identical pre-drawn noise).
+
+Tolerances, relative to max|ref| (trajectories with random weights expand):
+  sampler algebra alone (fake score, fp64 state) ... max-abs/max|ref| <= 1e-6 and rel-L2 <= 1e-6
+      (limited by the fp32 score network boundary, not by the fused update: ~1e-8 measured on CPU)
+  tiny NCSN++, fp32 network, fp64 state, 100 NFE .... rel-L2 <= 2e-4, max-abs/max|ref| <= 5e-4
+  bf16 network path (stated separately) ............. rel-L2 <= 5e-2
+"""
+import numpy as np
+import pytest
+import torch
+
+from _net import fake_score, make_net, sampler_inputs
+from _ops import max_rel, rel_l2
+from oracle import psld_oracle as O
+from psld_b200 import EulerMaruyamaSampler, PSLD, SSCSSampler, time_grid, tiny_config
+
+pytestmark = pytest.mark.gpu
+
+SAMPLERS = {"sscs_sde": SSCSSampler, "em_sde": EulerMaruyamaSampler}
+
+
+def _golden_cfg(tag):
+    kw = {
+        "sscs_fake_uniform": (dict(sampler="sscs_sde", n_discrete_steps=50), {}),
+        "em_fake_uniform": (dict(sampler="em_sde", n_discrete_steps=50), {}),
+        "sscs_fake_quad": (dict(sampler="sscs_sde", n_discrete_steps=40, stride_type="quadratic"),
+                           dict(nu=4.02, gamma=0.02, beta_min=0.5, beta_max=12.0)),
+        "em_fake_quad": (dict(sampler="em_sde", n_discrete_steps=40, stride_type="quadratic"),
+                         dict(nu=4.02, gamma=0.02, beta_min=0.5, beta_max=12.0)),
+        "sscs_fake_nodenoise": (dict(sampler="sscs_sde", n_discrete_steps=30, denoise=False), {}),
+    }[tag]
+    cfg = tiny_config(**kw[0])
+    cfg.model.sde.update(kw[1])
+    cfg.data.image_size = 8
+    return cfg
+
+
+def _run(cfg, score_fn, u0, nb, state_dtype=torch.float64, fuse=False, record=True):
+    kind = cfg.evaluation.sampler.name
+    S = SAMPLERS[kind](cfg, PSLD(cfg), score_fn)
+    S.state_dtype = state_dtype
+    S.fuse_halves = fuse
+    S.noise = torch.stack(nb).cuda() if nb is not None else None
+    S.record = True if record else None
+    ts, n = time_grid(cfg)
+    out = S.sample(u0.cuda(), ts.cuda(), n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    torch.cuda.synchronize()
+    return out, (S.record if record else None), n
+
+
+def _check_against_golden(g, out, rec, tol_l2, tol_max):
+    ref = torch.from_numpy(g["final"])
+    e_l2, e_mx = rel_l2(out, ref), max_rel(out, ref)
+    worst = 0.0
+    if rec is not None:
+        for i in g["probe"]:
+            s_ref = torch.from_numpy(g[f"state_{int(i)}"])
+            worst = max(worst, max_rel(rec[int(i)][: s_ref.shape[0]], s_ref))
+        st = g["stats"]
+        sums = rec.double().reshape(rec.shape[0], -1)
+        l2 = (sums ** 2).sum(1).cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(l2 - st[:, 3]) / st[:, 3])) / 2)
+    print(f"final rel-L2 {e_l2:.3e} max-abs/max|ref| {e_mx:.3e} worst per-step {worst:.3e}")
+    assert e_l2 <= tol_l2 and e_mx <= tol_max and worst <= tol_max, (e_l2, e_mx, worst)
+
+
+@pytest.mark.parametrize("tag", ["sscs_fake_uniform", "em_fake_uniform", "sscs_fake_quad",
+                                 "em_fake_quad", "sscs_fake_nodenoise"])
+def test_sampler_algebra_vs_reference_golden(golden_dir, tag):
+    """Fused update kernels + host schedule vs the reference sampler (generic score_fn path)."""
+    g = np.load(f"{golden_dir}/sampler_{tag}.npz")
+    cfg = _golden_cfg(tag)
+    n = int(g["n"])
+    u0, nb = sampler_inputs(cfg, int(g["B"]), n, cfg.evaluation.sampler.name)
+    out, rec, n2 = _run(cfg, fake_score, u0, nb)
+    assert n2 == n
+    _check_against_golden(g, out, rec, 1e-6, 1e-6)
+    # fused half-steps give the same trajectory end point
+    out_f, _, _ = _run(cfg, fake_score, u0, nb, fuse=True, record=False)
+    assert max_rel(out_f, out) <= 1e-6
+    # fp32 state (throughput mode) stays within fp32 rounding accumulated over the steps
+    out32, _, _ = _run(cfg, fake_score, u0, nb, state_dtype=torch.float32, fuse=True, record=False)
+    assert rel_l2(out32, torch.from_numpy(g["final"])) <= 2e-5
+
+
+@pytest.mark.parametrize("kind,fname", [("em_sde", "sampler_tiny_em100.npz"),
+                                        ("sscs_sde", "sampler_tiny_sscs100.npz")])
+def test_native_sampler_vs_reference_golden(golden_dir, kind, fname):
+    """BASELINE.json configs[0] (tiny NCSN++, 100 steps, 8 samples): whole native loop
+    (psld_sampler_run: NCSN++ program + fused update per step) vs the reference."""
+    g = np.load(f"{golden_dir}/{fname}")
+    cfg = tiny_config(sampler=kind)
+    net, _ = make_net(cfg, "fp32")
+    n = int(g["n"])
+    u0, nb = sampler_inputs(cfg, int(g["B"]), n, kind)
+    out, rec, _ = _run(cfg, net, u0, nb)
+    _check_against_golden(g, out, rec, 2e-4, 5e-4)
+    # fused halves + fp32 state: same answer to fp32 accuracy
+    out_f, _, _ = _run(cfg, net, u0, nb, state_dtype=torch.float32, fuse=True, record=False)
+    assert rel_l2(out_f, torch.from_numpy(g["final"])) <= 5e-4
+    # bf16 network path, stated separately
+    net16, _ = make_net(cfg, "bf16")
+    out16, _, _ = _run(cfg, net16, u0, nb, fuse=True, record=False)
+    e16 = rel_l2(out16, torch.from_numpy(g["final"]))
+    print(f"bf16 network path: final rel-L2 {e16:.3e}")
+    assert e16 <= 5e-2
+
+
+def test_native_equals_generic_path():
+    """psld_sampler_run (native loop) and the Python loop over the same kernels agree exactly."""
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=6)
+    net, _ = make_net(cfg, "fp32")
+    u0, nb = sampler_inputs(cfg, 2, 5, "sscs_sde")
+    a, _, _ = _run(cfg, net, u0, nb, record=False)
+    b, _, _ = _run(cfg, lambda u, t: net(u, t), u0, nb, record=False)
+    assert max_rel(a, b) <= 1e-6     # only log(t) differs: host fp32 log vs device logf
+
+
+def test_score_m_mode_vs_oracle():
+    """gamma = 0 ablation (reference scripts_psld/ablations/.../sample_uncond_psld.sh:6-16):
+    out_ch = 3, score only in momentum space (psld.py:240-243)."""
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=12)
+    cfg.model.sde.update(nu=4.0, gamma=0.0)
+    cfg.data.image_size = 8
+
+    def fake3(u, t):
+        return fake_score(u, t)[:, 3:]
+
+    u0, nb = sampler_inputs(cfg, 2, 11, "sscs_sde")
+    out, _, n = _run(cfg, fake3, u0, nb, record=False)
+    ts, _ = O.time_grid(cfg)
+    ref = O.sscs_sample(cfg, fake3, u0, ts, n, nb)
+    assert max_rel(out, ref) <= 1e-6
+
+
+def test_philox_mode_runs_and_is_reproducible():
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=8)
+    net, _ = make_net(cfg, "bf16")
+    u0, _ = sampler_inputs(cfg, 4, 7, "sscs_sde")
+    a, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=True, record=False)
+    b, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=True, record=False)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    c, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=False, record=False)
+    assert max_rel(c, a) <= 1e-5     # fused and unfused draw the same Philox streams

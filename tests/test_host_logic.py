@@ -1,0 +1,126 @@
+"""CPU: host-side logic of the product (schedule tables, registry, program builder) and the
+C-ABI library surface.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from emulate import run_plan
+from oracle import psld_oracle as O
+from oracle.weights import fill_state_dict
+from psld_b200 import (NCSNpp, PSLD, PSLDSchedule, SSCSSampler, StepTables, get_module, mid_config,
+                       register_module, time_grid, tiny_config)
+from psld_b200 import _lib as L
+from psld_b200.program import build_plan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "psld_b200.h")).read()
+    declared = set(re.findall(r"PSLD_API\s+(?:const\s+)?\w+\*?\s+(psld_\w+)\s*\(", hdr))
+    assert declared == set(L.EXPORTS.keys()), declared ^ set(L.EXPORTS.keys())
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.psld_version() == L.VERSION
+    # struct sizes agree with the header's layout rules
+    assert C.sizeof(L.HalfStep) == 64 and C.sizeof(L.ScoreStep) == 112
+    assert C.sizeof(L.SscsCoeffs) == 3 * 64 + 112
+    assert C.sizeof(L.Op) == 8 + 4 * L.OP_NI + 4 * L.OP_NF + 8 * 2 * L.OP_NP + 8
+
+
+def test_schedule_tables_vs_golden(golden_dir):
+    g = np.load(f"{golden_dir}/scalars.npz")
+    cols = {c: i for i, c in enumerate(g["columns"])}
+    for row in g["table"]:
+        v = lambda k: row[cols[k]]
+        cfg = tiny_config()
+        cfg.model.sde.update(nu=v("nu"), gamma=v("gamma"), beta_min=v("beta0"), beta_max=v("beta1"),
+                             decomp_mode="upper" if v("upper") else "lower")
+        sch = PSLDSchedule(cfg)
+        ts = torch.tensor([v("t"), v("t") + v("dt")], dtype=torch.float64)
+        tab = StepTables(sch, ts, 1, "sscs_sde", False, 1e-3)
+        h = tab.sscs[0].half_a
+        np.testing.assert_allclose([h.a_xx, h.a_xm, h.a_mx, h.a_mm],
+                                   [v("a_xx"), v("a_xm"), v("a_mx"), v("a_mm")], rtol=1e-14, atol=1e-17)
+        np.testing.assert_allclose([h.c11, h.c12, h.c21, h.c22],
+                                   [v("c11"), v("c12"), v("c21"), v("c22")], rtol=1e-12, atol=1e-17)
+        s = tab.sscs[0].score
+        f32 = lambda k: float(np.float32(v(k)))
+        assert [s.li11, s.li12, s.li21, s.li22] == [f32("i11"), f32("i12"), f32("i21"), f32("i22")]
+        np.testing.assert_allclose(s.k_x, v("dt") * v("gamma") * v("beta_tau"), rtol=1e-11)
+        np.testing.assert_allclose(s.k_m, v("dt") * v("m") * v("nu") * v("beta_tau"), rtol=1e-11)
+        assert s.mode == (1 if v("gamma") == 0 and not v("upper") else 0)
+
+
+def test_time_grid_and_denoise_rounding():
+    for stride in ("uniform", "quadratic"):
+        cfg = tiny_config(stride_type=stride, n_discrete_steps=37)
+        ts, n = time_grid(cfg)
+        ts2, n2 = O.time_grid(cfg)
+        assert n == n2 == 36
+        np.testing.assert_allclose(ts.numpy(), ts2, atol=3e-16)
+    tab = StepTables(PSLDSchedule(cfg), ts, n, "em_sde", True, 1e-3)
+    # the reference's denoise step runs at t = fl32(T - eps) with dt = fl32(eps) (sde.py:52-57)
+    assert tab.den.dt == float(np.float32(1e-3))
+    assert tab.n_calls == n + 1
+    assert abs(float(tab.tau32[-1]) - (1.0 - float(np.float32(0.999)))) < 1e-9
+
+
+def test_nan_guard_raises_like_reference():
+    cfg = tiny_config()
+    cfg.model.sde.numerical_eps = -1.0       # forces sqrt of a negative variance
+    with pytest.raises(ValueError, match="Numerical precision error"):
+        StepTables(PSLDSchedule(cfg), torch.linspace(0, 0.999, 5, dtype=torch.float64), 4,
+                   "sscs_sde", True, 1e-3)
+
+
+def test_registry_semantics():
+    assert get_module("samplers", "sscs_sde_b200") is SSCSSampler
+    assert get_module("score_fn", "ncsnpp_b200") is NCSNpp
+    assert get_module("sde", "psld_b200") is PSLD
+    with pytest.raises(ValueError):
+        get_module("samplers", "nope")
+    with pytest.raises(ValueError):
+        register_module(category="samplers", name="sscs_sde_b200")(SSCSSampler)
+
+
+def test_sde_object_surface():
+    sde = PSLD(tiny_config())
+    assert sde.T == 1.0 and sde.mode == "score_xm" and sde.type == "psld-score_xm"
+    assert sde.m_inv == 4.0 and sde.m == 0.25
+    u = sde.prior_sampling([4, 3, 8, 8])
+    assert tuple(u.shape) == (4, 6, 8, 8)
+    assert float(sde.beta_t(0.3)) == 8.0 and float(sde.b_t(0.5)) == 4.0
+
+
+@pytest.mark.parametrize("cfg_fn,precision,tol", [(tiny_config, "fp32", 1e-5), (mid_config, "fp32", 1e-5),
+                                                  (mid_config, "bf16", 3e-2)])
+def test_program_builder_vs_golden(golden_dir, cfg_fn, precision, tol):
+    """The op program (weights packing, wiring, fused epilogues, temb offsets) interpreted on the
+    host reproduces the reference forward."""
+    cfg = cfg_fn()
+    name = "tiny" if cfg_fn is tiny_config else "mid"
+    g = np.load(f"{golden_dir}/forward_{name}.npz")
+    net = NCSNpp(cfg).eval()
+    net.precision = precision
+    net.load_state_dict(fill_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 0))
+    x, t, y = (torch.from_numpy(g[k]) for k in ("x", "t", "y"))
+    plan = build_plan(net, x.shape[0], x.shape[0], False, dry=True)
+    out = run_plan(plan, x, t)
+    assert float((out - y).norm() / y.norm()) <= tol
+    assert plan.launches == L.lib().psld_program_launches(plan.op_array, plan.n_ops) > plan.n_ops
+    if precision == "bf16":
+        assert plan.engine_count["tc"] >= 40 and plan.engine_count["simt"] <= 3
+
+
+def test_no_cpu_fallback():
+    net = NCSNpp(tiny_config())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 6, 32, 32), torch.ones(1))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        build_plan(net, 1, 1, False)

@@ -1,0 +1,144 @@
+"""CPU: pins the oracle restatement against golden vectors produced by the reference itself
+(``oracle/make_golden.py``).  The reference ships no tests/golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import psld_oracle as O
+from oracle.weights import fill_state_dict, noise_bank, prior
+from psld_b200 import mid_config, tiny_config
+from _net import fake_score
+from test_gpu_sampler import _golden_cfg
+
+
+def test_scalars(golden_dir):
+    g = np.load(f"{golden_dir}/scalars.npz")
+    cols = {c: i for i, c in enumerate(g["columns"])}
+    for row in g["table"]:
+        v = lambda k: row[cols[k]]
+        cfg = tiny_config()
+        cfg.model.sde.update(nu=v("nu"), gamma=v("gamma"), beta_min=v("beta0"), beta_max=v("beta1"),
+                             decomp_mode="upper" if v("upper") else "lower")
+        s = O.PSLDScalars(cfg)
+        a, c = s.half_step(v("t"), v("dt") / 2)
+        np.testing.assert_allclose(a, [v("a_xx"), v("a_xm"), v("a_mx"), v("a_mm")], rtol=1e-13, atol=1e-16)
+        np.testing.assert_allclose(c, [v("c11"), v("c12"), v("c21"), v("c22")], rtol=1e-10, atol=1e-16)
+        cov = s.cov(0.0, s.mm_0, 1.0 - v("t"))
+        np.testing.assert_allclose(cov, [v("XX"), v("XM"), v("MM")], rtol=1e-12, atol=1e-18)
+        np.testing.assert_allclose(s.get_inv_coeff(cov), [v("i11"), v("i12"), v("i21"), v("i22")],
+                                   rtol=1e-10, atol=1e-16)
+        assert s.m_inv == v("m_inv") and s.m == v("m") and s.mm_0 == v("mm_0")
+
+
+def test_survey_known_answers():
+    """SURVEY.md §4 golden scalars (nu=4.01, gamma=0.01, beta=8, h=5e-4)."""
+    s = O.PSLDScalars(tiny_config())
+    a, c = s.half_step(0.0, 5e-4)
+    np.testing.assert_allclose(a, [0.9999720216609386, -0.007967904555066366, 0.0019919761387665914,
+                                   0.9920041171058721], rtol=1e-13)
+    np.testing.assert_allclose([c[0], c[2], c[3]], [0.006331273141002044, -0.00250690112338919,
+                                                    0.06302147561799819], rtol=1e-10)
+    ic = s.get_inv_coeff(s.cov(0.0, s.mm_0, 1.0))
+    np.testing.assert_allclose(ic, [1.000007398133583, -1.3064602171464342e-05, 0, 2.000011531445317],
+                               rtol=1e-10, atol=1e-18)
+    ic = s.get_inv_coeff(s.cov(0.0, s.mm_0, 1e-3))
+    np.testing.assert_allclose(ic, [109.63789430671079, -20.20633787397167, 0, 7.6699136770391005],
+                               rtol=1e-9, atol=1e-18)
+    assert s.m_inv == 4.0 and s.m == 0.25 and abs(s.mm_0 - 0.01) < 1e-18
+    # L^T L^{-T} = I
+    for tau in (1.0, 0.3, 1e-3):
+        var = s.cov(0.0, s.mm_0, tau)
+        l = s.get_coeff(var); li = s.get_inv_coeff(var)
+        Lm = np.array([[l[0], l[1]], [l[2], l[3]]]); Li = np.array([[li[0], li[1]], [li[2], li[3]]])
+        np.testing.assert_allclose(Lm.T @ Li, np.eye(2), atol=1e-12)
+
+
+def test_upfirdn(golden_dir):
+    g = np.load(f"{golden_dir}/upfirdn.npz")
+    x = torch.from_numpy(g["x"])
+    for name in ["down", "up", "pad", "generic", "crop"]:
+        up, down, p0, p1, gain = g["arg_" + name]
+        y = O.upfirdn2d(x, g["k"] * gain, up=int(up), down=int(down), pad=(int(p0), int(p1)))
+        np.testing.assert_allclose(y.numpy(), g["y_" + name], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", tiny_config()), ("mid", mid_config())])
+def test_forward(golden_dir, name, cfg):
+    g = np.load(f"{golden_dir}/forward_{name}.npz")
+    from psld_b200 import NCSNpp
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    sd = fill_state_dict(shapes, int(g["seed"]))
+    y = O.ncsnpp_forward(cfg, sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=1e-5 * np.abs(g["y"]).max())
+
+
+def test_modules(golden_dir):
+    """Single ResnetBlockBigGANpp (plain/down/up/cat), AttnBlockpp and pyramid Downsample."""
+    g = np.load(f"{golden_dir}/modules_tiny.npz")
+    cfg = tiny_config()
+    from psld_b200 import NCSNpp
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    sd = fill_state_dict(shapes, 0)
+    sf = cfg.model.score_fn
+    t = torch.from_numpy(g["t"])
+    xp = torch.log(t)[:, None] * sd["all_modules.0.W"][None] * 2 * np.pi
+    temb = torch.cat([torch.sin(xp), torch.cos(xp)], -1)
+    F = torch.nn.functional
+    temb = F.linear(temb, sd["all_modules.1.weight"], sd["all_modules.1.bias"])
+    temb = F.linear(F.silu(temb), sd["all_modules.2.weight"], sd["all_modules.2.bias"])
+    for kind in g["kinds"]:
+        idx, cls, ud = str(kind).split(":")
+        x = torch.from_numpy(g[f"in_{idx}"])
+        p = f"all_modules.{idx}"
+        if cls == "ResnetBlockBigGANpp":
+            y = O.resblock(sd, p, x, temb, sf, up=ud[0] == "1", down=ud[1] == "1")
+        elif cls == "AttnBlockpp":
+            y = O.attnblock(sd, p, x)
+        else:
+            y = O.conv_downsample_2d(x, sd[p + ".Conv2d_0.weight"], sf.fir_kernel) \
+                + sd[p + ".Conv2d_0.bias"].reshape(1, -1, 1, 1)
+        ref = g[f"out_{idx}"]
+        np.testing.assert_allclose(y.numpy(), ref, rtol=0, atol=2e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("tag", ["sscs_fake_uniform", "em_fake_uniform", "sscs_fake_quad",
+                                 "em_fake_quad", "sscs_fake_nodenoise"])
+def test_sampler_algebra(golden_dir, tag):
+    g = np.load(f"{golden_dir}/sampler_{tag}.npz")
+    cfg = _golden_cfg(tag)
+    kind = cfg.evaluation.sampler.name
+    ts, n = O.time_grid(cfg)
+    assert n == int(g["n"])
+    np.testing.assert_allclose(ts, g["ts"], rtol=0, atol=3e-16)
+    B = int(g["B"])
+    sde = O.PSLDScalars(cfg)
+    u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+    nb = noise_bank((2 if kind == "sscs_sde" else 1) * n, (B, 6, 8, 8), 2)
+    states = {}
+    fn = O.sscs_sample if kind == "sscs_sde" else O.em_sample
+    out = fn(cfg, fake_score, u0, ts, n, nb, denoise=cfg.evaluation.denoise,
+             record=lambda i, u: states.__setitem__(i, u.clone()))
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-7 * np.abs(ref).max()
+    for i in g["probe"]:
+        r = g[f"state_{int(i)}"]
+        assert np.abs(states[int(i)].numpy()[: r.shape[0]] - r).max() <= 5e-7 * np.abs(r).max()
+
+
+@pytest.mark.parametrize("kind,fname", [("em_sde", "sampler_tiny_em100.npz"),
+                                        ("sscs_sde", "sampler_tiny_sscs100.npz")])
+def test_sampler_with_network(golden_dir, kind, fname):
+    """BASELINE.json configs[0] through the oracle (a few seconds of CPU)."""
+    g = np.load(f"{golden_dir}/{fname}")
+    cfg = tiny_config(sampler=kind)
+    from psld_b200 import NCSNpp
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    sd = fill_state_dict(shapes, 0)
+    ts, n = O.time_grid(cfg)
+    B = int(g["B"])
+    u0 = prior((B, 3, 32, 32), 0.5, 1)
+    nb = noise_bank((2 if kind == "sscs_sde" else 1) * n, (B, 6, 32, 32), 2)
+    fn = O.sscs_sample if kind == "sscs_sde" else O.em_sample
+    out = fn(cfg, O.OracleScoreFn(cfg, sd), u0, ts, n, nb)
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
