@@ -1,0 +1,300 @@
+// tcgen05 single-head attention core for the NCSN++ AttnBlockpp (reference layerspp.py:82-86):
+//   w = softmax_keys( einsum(q, k) * C^-0.5 ) ;  h = einsum(w, v)
+// over HW = 64/128/256 tokens of C = 64..256 channels per sample (16x16 and 8x8 maps).
+//
+// One CTA = one sample x 128 queries.  All HW keys fit in one accumulator, so there is no
+// online-softmax rescaling:
+//   S[128 x HW]  = Q K^T      tcgen05.mma, A = Q chunk, B = K chunk (both K-major, 64-channel
+//                             chunks streamed by TMA through a 3-slot ring), accumulator in TMEM
+//   P            = exp2(S*c - max*c) -> bf16, written by the 128 softmax threads (one row each)
+//                  straight into shared memory in the 128B-swizzled K-major UMMA layout
+//   O[128 x C]   = P V        per 64-channel group g: A = P, B = V_g as an MN-major operand
+//                             (V is [keys, channels] in memory = contiguous along N)
+//   out          = O / rowsum  -> bf16 NHWC
+// TMEM: HW columns for S + C columns for O (<= 512).  q|k|v arrive packed along the channel axis
+// of one [N, HW, 3C] tensor (the fused NIN_0/1/2 GEMM), addressed with ONE 3-D tensor map.
+
+#include <cuda.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace psld {
+
+constexpr int AT_SLOT_BYTES = 16384 + 32768;   // Q chunk [128 x 64] + K chunk / V group [<=256 x 64]
+constexpr int AT_SLOTS = 3;
+constexpr int AT_P_BYTES = 128 * 256 * 2;      // P as 4 K-major tiles of [128 x 64] bf16
+constexpr int AT_SMEM_BYTES = AT_SLOTS * AT_SLOT_BYTES + AT_P_BYTES + 1024 + 256;
+constexpr int AT_THREADS = 192;
+
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  int HW, C, N;
+  int q_rows;        // rows of the Q box: min(128, HW)
+  float scale_log2;  // C^-0.5 * log2(e)
+};
+
+struct AttnTcState {
+  CUtensorMap tq, tkv;
+  AttnTcParams p;
+  dim3 grid;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+               const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t p_base = base + AT_SLOTS * AT_SLOT_BYTES;
+  const uint32_t bar_base = p_base + AT_P_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (AT_SLOTS + s); };
+  const uint32_t s_full = bar_base + 8u * (2 * AT_SLOTS);
+  const uint32_t p_ready = s_full + 8u;
+  const uint32_t o_full = s_full + 16u;
+  const uint32_t tmem_slot = s_full + 24u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, q0 = blockIdx.x * 128;
+  const int nck = p.C / 64;          // channel chunks (S GEMM K loop) = channel groups (PV GEMM)
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    for (int s = 0; s < AT_SLOTS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_S = tmem_base;                 // columns [0, HW)
+  const uint32_t tmem_O = tmem_base + 256u;          // columns [256, 256 + C)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      // Q/K channel chunks
+      for (int c = 0; c < nck; ++c) {
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(p.q_rows + p.HW) * 128u);
+        const uint32_t sq = base + slot * AT_SLOT_BYTES;
+        tma_load_3d(sq, &tmQ, full_bar(slot), c * 64, q0, n);
+        tma_load_3d(sq + 16384, &tmKV, full_bar(slot), p.C + c * 64, 0, n);
+        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+      // V channel groups
+      for (int g = 0; g < nck; ++g) {
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.HW * 128u);
+        const uint32_t sv = base + slot * AT_SLOT_BYTES + 16384;
+        tma_load_3d(sv, &tmKV, full_bar(slot), 2 * p.C + g * 64, 0, n);
+        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      // S = Q K^T : M = 128, N = HW, both operands K-major
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.HW >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+      for (int c = 0; c < nck; ++c) {
+        mbar_wait(full_bar(slot), phase);
+        tc_fence_after();
+        const uint32_t sq = base + slot * AT_SLOT_BYTES;
+        const uint64_t adesc = make_sw128_desc(sq);
+        const uint64_t bdesc = make_sw128_desc(sq + 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s,
+                      (c > 0 || k > 0) ? 1u : 0u);
+        tc_commit(empty_bar(slot));
+        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+      tc_commit(s_full);
+      // O_g = P V_g : M = 128, N = 64, A = P (K-major over keys), B = V_g (MN-major)
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) |
+                               ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(p_ready, 0);
+      tc_fence_after();
+      for (int g = 0; g < nck; ++g) {
+        mbar_wait(full_bar(slot), phase);
+        tc_fence_after();
+        const uint32_t sv = base + slot * AT_SLOT_BYTES + 16384;
+        for (int ks = 0; ks < p.HW / 16; ++ks) {
+          const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)(ks >> 2) * 16384u) +
+                                 (uint64_t)(2 * (ks & 3));
+          const uint64_t bdesc = make_sw128_desc(sv + (uint32_t)ks * 2048u);   // 16 keys x 128 B
+          tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(empty_bar(slot));
+        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    // ===== softmax + epilogue: 128 threads, one query row each =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+    for (int ch = 0; ch < p.HW; ch += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_S + lane_addr + (uint32_t)ch, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float mxs = mx * p.scale_log2;
+    float sum = 0.f;
+    for (int ch = 0; ch < p.HW; ch += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_S + lane_addr + (uint32_t)ch, r);
+      tmem_ld_wait();
+      // P tile (ch / 64), 16-byte chunks (ch % 64) / 8 .. +3, swizzled by (row % 8)
+      const uint32_t tile = p_base + (uint32_t)(ch >> 6) * 16384u + (uint32_t)row * 128u;
+      const int cbase = (ch & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float e0 = exp2f(fmaf(__uint_as_float(r[q * 8 + 2 * t]), p.scale_log2, -mxs));
+          const float e1 = exp2f(fmaf(__uint_as_float(r[q * 8 + 2 * t + 1]), p.scale_log2, -mxs));
+          __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+          // accumulate the sum from the ROUNDED values so that P / sum is a true softmax of P
+          const float2 f = __bfloat1622float2(h);
+          sum += f.x + f.y;
+          w[t] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const uint32_t dst = tile + (uint32_t)(((cbase + q) ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+    }
+    // make the generic-proxy smem writes visible to the tensor-core (async) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    mbar_arrive(p_ready);
+    const float inv = 1.0f / sum;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int q = q0 + row;
+    const bool valid = q < p.HW;
+    __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * p.C;
+    for (int ch = 0; ch < p.C; ch += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_O + lane_addr + (uint32_t)ch, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]) * inv,
+                                                     __uint_as_float(r[j + 2 * t + 1]) * inv);
+            w[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(orow + ch + j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int encode_qkv_map(CUtensorMap* tm, const void* ptr, int N, int HW, int C3, int rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)C3, (cuuint64_t)HW, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)C3 * 2, (cuuint64_t)HW * C3 * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(qkv) failed: %d", (int)r); return PSLD_ECUDA; }
+  return PSLD_OK;
+}
+
+int prepare_attn_tc(psld_op& op) {
+  const int N = op.i[PSLD_ATTN_N], HW = op.i[PSLD_ATTN_HW], C = op.i[PSLD_ATTN_C];
+  auto unsupported = [&](const char* why) {
+    set_error("attn_tc: not eligible (%s): N=%d HW=%d C=%d", why, N, HW, C);
+    return PSLD_EUNSUPPORTED;
+  };
+  if (op.i[PSLD_ATTN_DTYPE] != PSLD_BF16) return unsupported("dtype must be bf16");
+  if (C % 64 || C < 64 || C > 256) return unsupported("C must be 64..256, multiple of 64");
+  if (HW != 64 && HW != 128 && HW != 256) return unsupported("HW must be 64, 128 or 256");
+  if (!op.in[0] || !op.out[0]) { set_error("attn_tc: null pointer"); return PSLD_EINVAL; }
+  AttnTcState* st = new (std::nothrow) AttnTcState();
+  if (!st) { set_error("attn_tc: out of host memory"); return PSLD_ECUDA; }
+  const int q_rows = HW < 128 ? HW : 128;
+  int rc = encode_qkv_map(&st->tq, op.in[0], N, HW, 3 * C, q_rows);
+  if (rc == PSLD_OK) rc = encode_qkv_map(&st->tkv, op.in[0], N, HW, 3 * C, HW);
+  if (rc != PSLD_OK) { delete st; return rc; }
+  st->p.out = (__nv_bfloat16*)op.out[0];
+  st->p.HW = HW; st->p.C = C; st->p.N = N; st->p.q_rows = q_rows;
+  st->p.scale_log2 = op.f[0] * 1.4426950408889634f;
+  st->grid = dim3((unsigned)((HW + 127) / 128), (unsigned)N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AT_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      delete st;
+      return PSLD_ECUDA;
+    }
+    attr_set = true;
+  }
+  op.aux = st;
+  return PSLD_OK;
+}
+
+int release_attn_tc(psld_op& op) {
+  if (op.aux) {
+    delete (AttnTcState*)op.aux;
+    op.aux = nullptr;
+  }
+  return PSLD_OK;
+}
+
+int run_attn_tc(const psld_op& op, cudaStream_t s) {
+  const AttnTcState* st = (const AttnTcState*)op.aux;
+  PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
+  attn_tc_kernel<<<st->grid, AT_THREADS, AT_SMEM_BYTES, s>>>(st->tq, st->tkv, st->p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+}  // namespace psld

@@ -42,7 +42,8 @@ static int dispatch(const psld_op& op, cudaStream_t s) {
     case PSLD_OP_FIR: return run_fir(op, s);
     case PSLD_OP_CONV:
       return op.engine == PSLD_ENGINE_TC ? run_conv_tc(op, s) : run_conv_simt(op, s);
-    case PSLD_OP_ATTN: return run_attn_simt(op, s);
+    case PSLD_OP_ATTN:
+      return op.engine == PSLD_ENGINE_TC ? run_attn_tc(op, s) : run_attn_simt(op, s);
     default:
       set_error("unknown op kind %d", op.kind);
       return PSLD_EINVAL;
@@ -71,12 +72,14 @@ extern "C" int psld_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 extern "C" int psld_op_prepare(psld_op* op) {
   PSLD_CHECK_ARG(op != nullptr, "psld_op_prepare: null op");
   if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC) return prepare_conv_tc(*op);
+  if (op->kind == PSLD_OP_ATTN && op->engine == PSLD_ENGINE_TC) return prepare_attn_tc(*op);
   return PSLD_OK;
 }
 
 extern "C" int psld_op_release(psld_op* op) {
   PSLD_CHECK_ARG(op != nullptr, "psld_op_release: null op");
   if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC) return release_conv_tc(*op);
+  if (op->kind == PSLD_OP_ATTN && op->engine == PSLD_ENGINE_TC) return release_attn_tc(*op);
   return PSLD_OK;
 }
 

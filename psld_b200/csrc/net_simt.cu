@@ -149,16 +149,65 @@ int run_temb(const psld_op& op, cudaStream_t s) {
 }
 
 // ======================================================================== GroupNorm
-// Pass 1: per-(sample, pixel-chunk) partial sums per group, accumulated in fp32 per thread
-// over a short run and combined in fp64 (so E[x^2]-E[x]^2 cancels in double).
-// Pass 2: y = silu?((x - mean) * rstd * gamma + beta), written as ONE concatenated tensor.
+// Pass 1 (stats): per-(sample, pixel-chunk) partial sums per group.  Each thread owns 8 channels
+// (one 16-byte bf16 load / two float4 loads per pixel) and walks its pixels 4 at a time with the
+// loads issued back to back (memory-level parallelism is what bounds this kernel, not bandwidth:
+// the first version ran at 1.4 TB/s with one dependent load in flight per thread).  Sums are
+// accumulated in fp32 over short runs and combined in fp64, so E[x^2]-E[x]^2 cancels in double.
+// Pass 2 (apply): y = silu?((x - mean) * rstd * gamma + beta), written as ONE concatenated tensor.
 template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+      v[2 * t] = f.x;
+      v[2 * t + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+      w[t] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// accurate SiLU for the fp32 path, fast-intrinsic SiLU when the result is rounded to bf16 anyway
+template <bool kFast>
+__device__ __forceinline__ float silu_t(float x) {
+  if (kFast) return x * __frcp_rn(1.0f + __expf(-x));
+  return x / (1.0f + expf(-x));
+}
+
+constexpr int GN_UNROLL = 4;
+
+template <typename T, int VW>   // VW = channels per thread (8, or 4 when C % 8 != 0)
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ part,
                 int HW, int C1, int C2, int G, int nchunk) {
   extern __shared__ double sh[];  // [2*G]
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int C = C1 + C2, vpr = C >> 2, cpg = C / G;
+  const int C = C1 + C2, vpr = C / VW, cpg = C / G;
   const int rows_per_iter = blockDim.x / vpr;
   const int per = (HW + nchunk - 1) / nchunk;
   const int p0 = chunk * per, p1 = min(HW, p0 + per);
@@ -166,36 +215,66 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
   __syncthreads();
   const int tv = threadIdx.x % vpr, tr = threadIdx.x / vpr;
   if (tr < rows_per_iter) {
-    const int c = tv << 2;
-    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
-    int cnt = 0;
-    for (int p = p0 + tr; p < p1; p += rows_per_iter) {
-      const int64_t row = (int64_t)n * HW + p;
-      float4 v = c < C1 ? Vec4<T>::load(x1 + row * C1 + c) : Vec4<T>::load(x2 + row * C2 + (c - C1));
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]);
-      q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
-      if (++cnt == 32) {
+    const int c = tv * VW;
+    const bool first = c < C1;
+    const T* src = first ? x1 + c : x2 + (c - C1);
+    const int ld = first ? C1 : C2;
+    float s[VW], q[VW];
+    double ds[VW], dq[VW];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { ds[k] += s[k]; dq[k] += q[k]; s[k] = 0; q[k] = 0; }
+    for (int k = 0; k < VW; ++k) { s[k] = 0.f; q[k] = 0.f; ds[k] = 0.0; dq[k] = 0.0; }
+    int cnt = 0;
+    int p = p0 + tr;
+    for (; p + (GN_UNROLL - 1) * rows_per_iter < p1; p += GN_UNROLL * rows_per_iter) {
+      float v[GN_UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const T* ptr = src + ((int64_t)n * HW + p + u * rows_per_iter) * ld;
+        if (VW == 8) Vec8<T>::load(ptr, v[u]);
+        else { const float4 t = Vec4<T>::load(ptr); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
+      }
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < VW; ++k) { s[k] += v[u][k]; q[k] = fmaf(v[u][k], v[u][k], q[k]); }
+      cnt += GN_UNROLL;
+      if (cnt >= 32) {
+#pragma unroll
+        for (int k = 0; k < VW; ++k) { ds[k] += s[k]; dq[k] += q[k]; s[k] = 0.f; q[k] = 0.f; }
         cnt = 0;
       }
     }
+    for (; p < p1; p += rows_per_iter) {
+      float v[8];
+      const T* ptr = src + ((int64_t)n * HW + p) * ld;
+      if (VW == 8) Vec8<T>::load(ptr, v);
+      else { const float4 t = Vec4<T>::load(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ds[k] += s[k]; dq[k] += q[k];
-      const int g = (c + k) / cpg;
-      atomicAdd(&sh[2 * g], ds[k]);
-      atomicAdd(&sh[2 * g + 1], dq[k]);
+      for (int k = 0; k < VW; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
     }
+    // fold the thread's VW channels into their groups before touching shared memory
+    int gprev = c / cpg;
+    double as = 0.0, aq = 0.0;
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      const int g = (c + k) / cpg;
+      if (g != gprev) {
+        atomicAdd(&sh[2 * gprev], as);
+        atomicAdd(&sh[2 * gprev + 1], aq);
+        as = 0.0; aq = 0.0; gprev = g;
+      }
+      as += ds[k] + (double)s[k];
+      aq += dq[k] + (double)q[k];
+    }
+    atomicAdd(&sh[2 * gprev], as);
+    atomicAdd(&sh[2 * gprev + 1], aq);
   }
   __syncthreads();
   double* dst = part + ((int64_t)n * nchunk + chunk) * 2 * G;
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
 }
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int VW, bool kFast>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
                 const double* __restrict__ part, const float* __restrict__ gamma,
@@ -203,7 +282,7 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
                 int nchunk, int nchunk_apply, float eps, int silu) {
   extern __shared__ float shf[];  // mean[G], rstd[G]
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int C = C1 + C2, vpr = C >> 2, cpg = C / G;
+  const int C = C1 + C2, vpr = C / VW, cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double su = 0, sq = 0;
     for (int k = 0; k < nchunk; ++k) {
@@ -224,24 +303,51 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
   if (tr >= rows_per_iter) return;
   const int per = (HW + nchunk_apply - 1) / nchunk_apply;
   const int p0 = chunk * per, p1 = min(HW, p0 + per);
-  const int c = tv << 2;
-  float sc[4], bi[4];
+  const int c = tv * VW;
+  const bool first = c < C1;
+  const TI* src = first ? x1 + c : x2 + (c - C1);
+  const int ld = first ? C1 : C2;
+  float sc[VW], bi[VW];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < VW; ++k) {
     const int g = (c + k) / cpg;
     sc[k] = shf[G + g] * gamma[c + k];
     bi[k] = beta[c + k] - sc[k] * shf[g];
   }
-  for (int p = p0 + tr; p < p1; p += rows_per_iter) {
-    const int64_t row = (int64_t)n * HW + p;
-    float4 v = c < C1 ? Vec4<TI>::load(x1 + row * C1 + c) : Vec4<TI>::load(x2 + row * C2 + (c - C1));
-    float o[4] = {fmaf(v.x, sc[0], bi[0]), fmaf(v.y, sc[1], bi[1]), fmaf(v.z, sc[2], bi[2]),
-                  fmaf(v.w, sc[3], bi[3])};
-    if (silu) {
+  int p = p0 + tr;
+  for (; p + (GN_UNROLL - 1) * rows_per_iter < p1; p += GN_UNROLL * rows_per_iter) {
+    float v[GN_UNROLL][8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const TI* ptr = src + ((int64_t)n * HW + p + u * rows_per_iter) * ld;
+      if (VW == 8) Vec8<TI>::load(ptr, v[u]);
+      else { const float4 t = Vec4<TI>::load(ptr); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
     }
-    Vec4<TO>::store(y + row * C + c, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        float o = fmaf(v[u][k], sc[k], bi[k]);
+        v[u][k] = silu ? silu_t<kFast>(o) : o;
+      }
+      TO* dst = y + ((int64_t)n * HW + p + u * rows_per_iter) * C + c;
+      if (VW == 8) Vec8<TO>::store(dst, v[u]);
+      else Vec4<TO>::store(dst, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+    }
+  }
+  for (; p < p1; p += rows_per_iter) {
+    float v[8];
+    const TI* ptr = src + ((int64_t)n * HW + p) * ld;
+    if (VW == 8) Vec8<TI>::load(ptr, v);
+    else { const float4 t = Vec4<TI>::load(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      float o = fmaf(v[k], sc[k], bi[k]);
+      v[k] = silu ? silu_t<kFast>(o) : o;
+    }
+    TO* dst = y + ((int64_t)n * HW + p) * C + c;
+    if (VW == 8) Vec8<TO>::store(dst, v);
+    else Vec4<TO>::store(dst, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -256,33 +362,32 @@ int run_gn(const psld_op& op, cudaStream_t s) {
                  "gn: need C %% G == 0, C1,C2 %% 4 == 0, C <= 1024 (C1=%d C2=%d G=%d)", C1, C2, G);
   PSLD_CHECK_ARG(op.in[0] && (C2 == 0 || op.in[1]) && op.in[2] && op.in[3] && op.out[0] &&
                  op.out[1], "gn: null pointer");
-  PSLD_CHECK_ARG(idt == odt || idt == PSLD_F32 || true, "gn: dtype");
+  PSLD_CHECK_ARG(idt == odt, "gn: input and output dtypes must match (%d vs %d)", idt, odt);
+  const bool v8 = (C1 % 8 == 0) && (C2 % 8 == 0);
   double* part = (double*)op.out[1];
   dim3 grid(nchunk, N);
   const size_t sh1 = 2 * G * sizeof(double), sh2 = 2 * G * sizeof(float);
-  if (idt == PSLD_BF16)
-    gn_stats_kernel<__nv_bfloat16><<<grid, 256, sh1, s>>>(
-        (const __nv_bfloat16*)op.in[0], (const __nv_bfloat16*)op.in[1], part, HW, C1, C2, G, nchunk);
-  else
-    gn_stats_kernel<float><<<grid, 256, sh1, s>>>((const float*)op.in[0], (const float*)op.in[1],
-                                                 part, HW, C1, C2, G, nchunk);
+#define GN_STATS(T, VW)                                                                        \
+  gn_stats_kernel<T, VW><<<grid, 256, sh1, s>>>((const T*)op.in[0], (const T*)op.in[1], part, HW, \
+                                                C1, C2, G, nchunk)
+  if (idt == PSLD_BF16) { if (v8) GN_STATS(__nv_bfloat16, 8); else GN_STATS(__nv_bfloat16, 4); }
+  else { if (v8) GN_STATS(float, 8); else GN_STATS(float, 4); }
+#undef GN_STATS
   PSLD_CHECK_LAUNCH();
-  // apply pass: more CTAs per sample than the stats pass (pure streaming)
-  int nca = (int)ceil_div((int64_t)HW * (C / 4), 256 * 8);
+  // apply pass: pure streaming, ~16 KB of input per CTA
+  const int vw = v8 ? 8 : 4;
+  int nca = (int)ceil_div((int64_t)HW * (C / vw), 256 * 2 * GN_UNROLL);
   if (nca < 1) nca = 1;
   dim3 grid2(nca, N);
   const float eps = op.f[0];
   const float* ga = (const float*)op.in[2];
   const float* be = (const float*)op.in[3];
-#define GN_APPLY(TI, TO)                                                                        \
-  gn_apply_kernel<TI, TO><<<grid2, 256, sh2, s>>>((const TI*)op.in[0], (const TI*)op.in[1], part, \
-                                                  ga, be, (TO*)op.out[0], HW, C1, C2, G, nchunk,  \
-                                                  nca, eps, silu)
-  if (idt == PSLD_BF16 && odt == PSLD_BF16) GN_APPLY(__nv_bfloat16, __nv_bfloat16);
-  else if (idt == PSLD_F32 && odt == PSLD_F32) GN_APPLY(float, float);
-  else if (idt == PSLD_F32 && odt == PSLD_BF16) GN_APPLY(float, __nv_bfloat16);
-  else if (idt == PSLD_BF16 && odt == PSLD_F32) GN_APPLY(__nv_bfloat16, float);
-  else { set_error("gn: unsupported dtypes %d -> %d", idt, odt); return PSLD_EINVAL; }
+#define GN_APPLY(T, VW, FAST)                                                                   \
+  gn_apply_kernel<T, T, VW, FAST><<<grid2, 256, sh2, s>>>((const T*)op.in[0], (const T*)op.in[1], \
+                                                          part, ga, be, (T*)op.out[0], HW, C1, C2, \
+                                                          G, nchunk, nca, eps, silu)
+  if (idt == PSLD_BF16) { if (v8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 4, true); }
+  else { if (v8) GN_APPLY(float, 8, false); else GN_APPLY(float, 4, false); }
 #undef GN_APPLY
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;

@@ -14,6 +14,8 @@ KIND_NAMES = {L.OP_LAYOUT: "layout", L.OP_TEMB: "temb", L.OP_GN: "groupnorm", L.
 def op_name(op):
     if op.kind == L.OP_CONV:
         return "conv_tc" if op.engine == L.ENGINE_TC else "conv_simt"
+    if op.kind == L.OP_ATTN:
+        return "attn_tc" if op.engine == L.ENGINE_TC else "attn_simt"
     return KIND_NAMES.get(op.kind, "?")
 
 

@@ -106,7 +106,10 @@ class Plan:
         G = gn_mod.num_groups
         assert gn_mod.num_channels == Cc, (gn_mod.num_channels, Cc)
         y = self._acquire(*x1.shape[:-1], Cc)
-        nchunk = int(max(1, min(HW // 16 if HW >= 16 else 1, -(-296 // self.B))))
+        # stats pass: ~64 KB of input per CTA, but enough CTAs to fill 148 SMs at small batch
+        per_img = HW * Cc * (2 if self.bf16 else 4)
+        nchunk = max(-(-per_img // 65536), -(-592 // self.B))
+        nchunk = int(max(1, min(nchunk, max(1, HW // 32))))
         op = self._op(L.OP_GN)
         i = op.i
         i[L.GN_N], i[L.GN_HW], i[L.GN_C1], i[L.GN_C2], i[L.GN_G] = self.B, HW, C1, C2, G
@@ -236,6 +239,18 @@ class Plan:
         op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = self.B, HW, Cc, self.acode
         op.f[0] = float(int(Cc) ** (-0.5))
         op.inp[0], op.out[0] = qkv.data_ptr(), o.data_ptr()
+        if self.bf16:
+            op.engine = L.ENGINE_TC
+            if self.dry:
+                rc = L.OK if (Cc % 64 == 0 and 64 <= Cc <= 256 and HW in (64, 128, 256)) else L.EUNSUPPORTED
+            else:
+                rc = self.lib.psld_op_prepare(C.byref(op))
+            if rc == L.EUNSUPPORTED:
+                op.engine = L.ENGINE_SIMT
+            elif rc != L.OK:
+                L.check(rc, "psld_op_prepare(attn)")
+        self.engine_count["attn_tc" if op.engine == L.ENGINE_TC else "attn_simt"] = \
+            self.engine_count.get("attn_tc" if op.engine == L.ENGINE_TC else "attn_simt", 0) + 1
         self._push(op)
         return o
 

@@ -140,12 +140,12 @@ def fir_op(x, taps, up, down, pad0, pad1):
     return op, out
 
 
-def attn_op(qkv, Cc):
+def attn_op(qkv, Cc, engine=L.ENGINE_SIMT):
     N = qkv.shape[0]
     HW = int(np.prod(qkv.shape[1:-1]))
     out = torch.full((*qkv.shape[:-1], Cc), float("nan"), dtype=qkv.dtype, device=qkv.device)
     op = L.Op()
-    op.kind = L.OP_ATTN
+    op.kind, op.engine = L.OP_ATTN, engine
     op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = N, HW, Cc, code(qkv)
     op.f[0] = float(int(Cc) ** (-0.5))
     op.inp[0], op.out[0] = qkv.data_ptr(), out.data_ptr()

@@ -126,9 +126,11 @@ def test_em_update(state_dtype):
         ref = torch.cat([nx, nm], 1)
         u = u0.to(DEV, state_dtype).contiguous()
         out = torch.empty_like(u)
+        ed = eps.to(DEV)
+        zd = zz.to(DEV) if zz is not None else None      # keep the device tensors alive
         L.check(lib.psld_em_update(L.ptr(out), L.ptr(u), L.dtype_code(state_dtype), None,
-                                   L.ptr(eps.to(DEV)), L.ptr(zz.to(DEV)) if zz is not None else None,
-                                   0, C.byref(co), 0, 0, B, Cc * H * H, L.stream_ptr()), "em")
+                                   L.ptr(ed), L.ptr(zd), 0, C.byref(co), 0, 0, B, Cc * H * H,
+                                   L.stream_ptr()), "em")
         torch.cuda.synchronize()
         tol = 1e-13 if state_dtype == torch.float64 else 2e-6
         assert max_rel(out, ref) <= tol, max_rel(out, ref)
@@ -328,6 +330,22 @@ def test_attention(dtype, tol, shape):
     wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
     ref = torch.einsum("bqk,bkc->bqc", wgt, v)
     assert rel_l2(out.float().reshape(N, H * W, Cc), ref) <= tol
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 8, 8, 256), (2, 16, 16, 64), (1, 8, 16, 128),
+                                   (4, 8, 8, 64)])
+def test_attention_tc(shape):
+    """tcgen05 attention core (S = QK^T and O = PV in TMEM) vs the fp32 definition."""
+    N, H, W, Cc = shape
+    r = _rng(19)
+    qkv = _t(r.standard_normal((N, H, W, 3 * Cc)) * 1.5, torch.bfloat16)
+    op, out = attn_op(qkv, Cc, engine=L.ENGINE_TC)
+    run_op(op, prepare=True)
+    q, k, v = qkv.float().cpu().reshape(N, H * W, 3 * Cc).split(Cc, dim=-1)
+    wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
+    ref = torch.einsum("bqk,bkc->bqc", wgt, v)
+    err = rel_l2(out.float().reshape(N, H * W, Cc), ref)
+    assert err <= 8e-3, err          # P and the output are rounded to bf16
 
 
 # ------------------------------------------------------------------ error behaviour

@@ -4,8 +4,9 @@ the reference sampler (identical weights, identical pre-drawn noise).
 Tolerances, relative to max|ref| (trajectories with random weights expand):
   sampler algebra alone (fake score, fp64 state) ... max-abs/max|ref| <= 1e-6 and rel-L2 <= 1e-6
       (limited by the fp32 score network boundary, not by the fused update: ~1e-8 measured on CPU)
-  tiny NCSN++, fp32 network, fp64 state, 100 NFE .... rel-L2 <= 2e-4, max-abs/max|ref| <= 5e-4
-  bf16 network path (stated separately) ............. rel-L2 <= 5e-2
+  tiny NCSN++, fp32 network, fp64 state, 100 NFE .... rel-L2 <= 1e-5, max-abs/max|ref| <= 1e-5
+      (measured on B200: 3.4e-7 / 3.9e-7)
+  bf16 network path (stated separately) ............. rel-L2 <= 2e-2 (measured 2.7e-3)
 """
 import numpy as np
 import pytest
@@ -96,16 +97,16 @@ def test_native_sampler_vs_reference_golden(golden_dir, kind, fname):
     n = int(g["n"])
     u0, nb = sampler_inputs(cfg, int(g["B"]), n, kind)
     out, rec, _ = _run(cfg, net, u0, nb)
-    _check_against_golden(g, out, rec, 2e-4, 5e-4)
+    _check_against_golden(g, out, rec, 1e-5, 1e-5)
     # fused halves + fp32 state: same answer to fp32 accuracy
     out_f, _, _ = _run(cfg, net, u0, nb, state_dtype=torch.float32, fuse=True, record=False)
-    assert rel_l2(out_f, torch.from_numpy(g["final"])) <= 5e-4
+    assert rel_l2(out_f, torch.from_numpy(g["final"])) <= 5e-5
     # bf16 network path, stated separately
     net16, _ = make_net(cfg, "bf16")
     out16, _, _ = _run(cfg, net16, u0, nb, fuse=True, record=False)
     e16 = rel_l2(out16, torch.from_numpy(g["final"]))
     print(f"bf16 network path: final rel-L2 {e16:.3e}")
-    assert e16 <= 5e-2
+    assert e16 <= 2e-2
 
 
 def test_native_equals_generic_path():
