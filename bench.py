@@ -211,12 +211,13 @@ def main_b200(args):
     plan.x_in.copy_(state)
 
     def run_steps(first, count):
-        tabs = StepTables(sde, ts[first:first + count + 1], count, "sscs_sde", False, 1e-3)
+        tabs = StepTables(sde, ts[first:first + count + 1], count, "sscs_sde", False, 1e-3,
+                          merge_noise=True)
         table = tabs.time_table.to(dev)
         d = L.SamplerDesc()
         d.sampler, d.n_steps, d.denoise = 0, count, 0
         d.state_dtype = L.dtype_code(state_dtype)
-        d.fuse_halves, d.temb_op = 1, plan.temb_op
+        d.fuse_halves, d.temb_op = 2, plan.temb_op     # one fused pass, one merged draw per step
         d.B, d.chw, d.seed = B, chw, 99 + rank
         d.state, d.net_in, d.eps = state.data_ptr(), plan.x_in.data_ptr(), plan.eps.data_ptr()
         d.time_table = table.data_ptr()
@@ -266,6 +267,8 @@ def main_b200(args):
     upd = time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts)
     upd["peak"] = pk["hbm"]
     upd["frac"] = upd["achieved"] / pk["hbm"]
+    if "achieved" in upd.get("large", {}):
+        upd["large"]["frac"] = upd["large"]["achieved"] / pk["hbm"]
 
     # ---- end to end through the public API: pinned host prior -> HOST samples
     e2e = None
@@ -322,37 +325,51 @@ def main_b200(args):
         dist.destroy_process_group()
 
 
-def time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts):
-    """Fused SCORE+HALF_B+HALF_C update alone, CUDA events, 20 launches."""
+def time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts, big_pairs=1 << 24):
+    """Fused per-step update (score step + both half-steps, one merged Philox draw) alone, CUDA
+    events: at the bench batch (latency-bound: ~25 MB) and at >= 2^24 pairs (bandwidth-bound)."""
     import ctypes as C
     import torch
     from psld_b200 import _lib as L
     from psld_b200.schedule import StepTables
-    tabs = StepTables(sde, ts[:3], 2, "sscs_sde", False, 1e-3)
+    tabs = StepTables(sde, ts[:3], 2, "sscs_sde", False, 1e-3, merge_noise=True)
     sdt = L.dtype_code(state_dtype)
-    stages = L.STAGE_SCORE | L.STAGE_HALF_B | L.STAGE_HALF_C
-    sp, ip, ep = L.ptr(state), L.ptr(plan.x_in), L.ptr(plan.eps)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    total = 0.0
-    reps = 10
-    for r in range(reps + 2):
-        flush.zero_()                                  # evict L2 between timed launches
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        L.check(lib.psld_sscs_update(sp, sp, sdt, ip, ep, None, None, None, C.byref(tabs.sscs[0]),
-                                     stages, 5, r, B, chw, stream), "update")
-        b.record()
-        torch.cuda.synchronize(dev)
-        if r >= 2:
-            total += a.elapsed_time(b)
-    ms = total / reps
+    stages = L.STAGE_SCORE | L.STAGE_HALF_B
     sb = 8 if state_dtype == torch.float64 else 4
     per_pair = 2 * sb * 2 + 8 + 8          # state in+out, eps in, fp32 net_in out (Philox noise)
-    byts = per_pair * B * chw
-    return {"bound": "hbm", "kernel": "sscs_update_kernel (score + 2 half-steps, Philox)",
-            "achieved": byts / (ms * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_pair": per_pair,
-            "pairs": B * chw, "avg_launch_ms": ms, "l2": "256 MB flush between launches",
-            "traffic": None}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def measure(st, xin, eps, Bq, reps=10):
+        sp, ip, ep = L.ptr(st), L.ptr(xin), L.ptr(eps)
+        total = 0.0
+        for r in range(reps + 2):
+            flush.zero_()                               # evict L2 between timed launches
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L.check(lib.psld_sscs_update(sp, sp, sdt, ip, ep, None, None, None, C.byref(tabs.sscs[0]),
+                                         stages, 5, r, Bq, chw, stream), "update")
+            b.record()
+            torch.cuda.synchronize(dev)
+            if r >= 2:
+                total += a.elapsed_time(b)
+        return total / reps
+
+    ms = measure(state, plan.x_in, plan.eps, B)
+    out = {"bound": "hbm", "kernel": "sscs_update_kernel (score step + merged half-steps, Philox)",
+           "achieved": per_pair * B * chw / (ms * 1e-3) / 1e9, "unit": "GB/s",
+           "bytes_per_pair": per_pair, "pairs": B * chw, "avg_launch_ms": ms,
+           "l2": "256 MB flush between launches", "traffic": None}
+    Bb = max(B, -(-big_pairs // chw))
+    try:
+        st = torch.randn(Bb, 6, chw // 3, dtype=torch.float32, device=dev).to(state_dtype)
+        xin = torch.empty(Bb, 6, chw // 3, dtype=torch.float32, device=dev)
+        eps = torch.randn(Bb, 6, chw // 3, dtype=torch.float32, device=dev)
+        msb = measure(st, xin, eps, Bb, reps=5)
+        out["large"] = {"pairs": Bb * chw, "avg_launch_ms": msb,
+                        "achieved": per_pair * Bb * chw / (msb * 1e-3) / 1e9}
+    except RuntimeError as e:   # pragma: no cover
+        out["large"] = {"error": str(e)[:80]}
+    return out
 
 
 if __name__ == "__main__":

@@ -237,7 +237,10 @@ typedef struct {
   int32_t n_steps;      /* predictor steps n                                            */
   int32_t denoise;      /* 1: final denoising step (one more network call)              */
   int32_t state_dtype;  /* PSLD_F64 | PSLD_F32                                          */
-  int32_t fuse_halves;  /* SSCS: fuse half B of step i with half A of step i+1          */
+  int32_t fuse_halves;  /* SSCS: 0 = A | net | SCORE+B per step (3 state passes / 2 steps);
+                           1 = SCORE+B+C in one pass (C = half A of step i+1, own draw);
+                           2 = same, with B and C pre-merged by the host into half_b (one
+                               Gaussian draw, exact in law; only without pre-drawn noise)    */
   int32_t temb_op;      /* index of the PSLD_OP_TEMB op in the program                  */
   int64_t B, chw;
   uint64_t seed;

@@ -162,7 +162,9 @@ extern "C" int psld_sampler_run(const psld_op* ops, int n_ops, const psld_sample
       rc = run_net(ops, n_ops, d->temb_op, d->time_table + i, s);
       if (rc) return rc;
       int stages = PSLD_STAGE_SCORE | PSLD_STAGE_HALF_B;
-      if (d->fuse_halves && i + 1 < n) stages |= PSLD_STAGE_HALF_C;
+      // fuse_halves 1: half C (= half A of step i+1) as a separate draw in the same pass;
+      // fuse_halves 2: the host merged B and C into one half-step with one draw (exact in law)
+      if (d->fuse_halves == 1 && i + 1 < n) stages |= PSLD_STAGE_HALF_C;
       rc = psld_sscs_update(d->state, d->state, d->state_dtype, d->net_in, d->eps, nullptr,
                             z(2 * i + 1), z(2 * i + 2), &d->sscs[i], stages, d->seed, i, d->B,
                             d->chw, s);

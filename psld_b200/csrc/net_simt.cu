@@ -398,11 +398,11 @@ int run_gn(const psld_op& op, cudaStream_t s) {
 // zero-stuffed (x up), (pad0,pad1)-padded / cropped input  (op/upfirdn2d.py:159-200).
 struct FirTaps { float k[16]; };
 
-template <typename T>
+template <typename T, int VW>
 __global__ void __launch_bounds__(256)
 fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C,
            int OH, int OW, int up, int down, int pad0, int KH) {
-  const int vpr = C >> 2;
+  const int vpr = C / VW;
   const int64_t total = (int64_t)N * OH * OW * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -411,24 +411,37 @@ fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int 
     const int ox = (int)(r % OW); r /= OW;
     const int oy = (int)(r % OH);
     const int n = (int)(r / OH);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[VW];
+#pragma unroll
+    for (int k = 0; k < VW; ++k) acc[k] = 0.f;
+    // valid taps only: uy = oy*down + ky - pad0 must be a non-negative multiple of `up`
+#pragma unroll 4
     for (int ky = 0; ky < KH; ++ky) {
       const int uy = oy * down + ky - pad0;          // coordinate in the zero-stuffed image
       if (uy < 0 || uy % up != 0) continue;
       const int iy = uy / up;
       if (iy >= H) continue;
+#pragma unroll 4
       for (int kx = 0; kx < KH; ++kx) {
         const int ux = ox * down + kx - pad0;
         if (ux < 0 || ux % up != 0) continue;
         const int ix = ux / up;
         if (ix >= W) continue;
         const float w = taps.k[(KH - 1 - ky) * KH + (KH - 1 - kx)];   // true convolution: flipped
-        float4 v = Vec4<T>::load(x + (((int64_t)n * H + iy) * W + ix) * C + (cv << 2));
-        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        const T* src = x + (((int64_t)n * H + iy) * W + ix) * C + cv * VW;
+        float v[8];
+        if (VW == 8) Vec8<T>::load(src, v);
+        else { const float4 t = Vec4<T>::load(src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+#pragma unroll
+        for (int k = 0; k < VW; ++k) acc[k] = fmaf(w, v[k], acc[k]);
       }
     }
-    Vec4<T>::store(y + (((int64_t)n * OH + oy) * OW + ox) * C + (cv << 2), acc);
+    T* dst = y + (((int64_t)n * OH + oy) * OW + ox) * C + cv * VW;
+    if (VW == 8) { float o[8]; 
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = acc[k < VW ? k : 0];
+      Vec8<T>::store(dst, o); }
+    else Vec4<T>::store(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
   }
 }
 
@@ -480,14 +493,14 @@ int run_fir(const psld_op& op, cudaStream_t s) {
   FirTaps taps;
   for (int i = 0; i < 16; ++i) taps.k[i] = i < KH * KH ? op.f[i] : 0.f;
   if (C % 4 == 0) {
-    const int grid = ew_grid((int64_t)N * OH * OW * (C / 4));
-    if (dt == PSLD_BF16)
-      fir_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)op.in[0],
-                                                   (__nv_bfloat16*)op.out[0], taps, N, H, W, C, OH,
-                                                   OW, up, down, pad0, KH);
-    else
-      fir_kernel<float><<<grid, 256, 0, s>>>((const float*)op.in[0], (float*)op.out[0], taps, N, H,
-                                           W, C, OH, OW, up, down, pad0, KH);
+    const int vw = C % 8 == 0 ? 8 : 4;
+    const int grid = (int)ceil_div((int64_t)N * OH * OW * (C / vw), 256);
+#define FIR_LAUNCH(T, VW)                                                                     \
+  fir_kernel<T, VW><<<grid, 256, 0, s>>>((const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, OH, \
+                                         OW, up, down, pad0, KH)
+    if (dt == PSLD_BF16) { if (vw == 8) FIR_LAUNCH(__nv_bfloat16, 8); else FIR_LAUNCH(__nv_bfloat16, 4); }
+    else { if (vw == 8) FIR_LAUNCH(float, 8); else FIR_LAUNCH(float, 4); }
+#undef FIR_LAUNCH
   } else {
     const int grid = ew_grid((int64_t)N * OH * OW * C);
     const int64_t sn = (int64_t)H * W * C, sy = (int64_t)W * C, sx = C, sc = 1;

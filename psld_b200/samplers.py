@@ -78,6 +78,7 @@ class _FusedSampler(Sampler):
         sd = str(_opt(config, "state_dtype", os.environ.get("PSLD_B200_STATE", "float64")))
         self.state_dtype = torch.float64 if sd in ("float64", "f64", "fp64") else torch.float32
         self.fuse_halves = bool(_opt(config, "fuse_halves", True))
+        self.merge_noise = bool(_opt(config, "merge_noise", True))   # Philox mode only
         self.seed = int(getattr(config.evaluation, "seed", 0)) + int(os.environ.get("RANK", "0"))
         self.noise = None          # optional pre-drawn noise bank (parity mode)
         self.record = None         # optional [n, B,2C,H,W] buffer filled with per-step states
@@ -111,8 +112,11 @@ class _FusedSampler(Sampler):
             state = batch.to(device=dev, dtype=self.state_dtype, non_blocking=True).contiguous()
             if state.data_ptr() == batch.data_ptr():
                 state = state.clone()
+            merged = (self.KIND == "sscs_sde" and self.noise is None and self.fuse_halves
+                      and self.merge_noise and self.record is None and self.corrector_fn is None)
             tabs = StepTables(self.schedule, ts.detach().to("cpu", torch.float64), n, self.KIND,
-                              bool(denoise), float(eps), self._embedding())
+                              bool(denoise), float(eps), self._embedding(), merge_noise=merged)
+            self._merged = merged
             noise = None
             if self.noise is not None:
                 noise = self.noise.to(device=dev, dtype=torch.float32).contiguous()
@@ -141,7 +145,7 @@ class _FusedSampler(Sampler):
         d = L.SamplerDesc()
         d.sampler = 0 if self.KIND == "sscs_sde" else 1
         d.n_steps, d.denoise, d.state_dtype = n, int(bool(denoise)), sdt
-        d.fuse_halves = int(self.fuse_halves and record is None)
+        d.fuse_halves = (2 if self._merged else 1) if (self.fuse_halves and record is None) else 0
         d.temb_op = plan.temb_op
         d.B, d.chw, d.seed = B, chw, self.seed
         d.state, d.net_in, d.eps = state.data_ptr(), plan.x_in.data_ptr(), plan.eps.data_ptr()
@@ -183,7 +187,7 @@ class _FusedSampler(Sampler):
                                                  i, B, chw, stream), "psld_sscs_update")
                 e = score(i)
                 stages = L.STAGE_SCORE | L.STAGE_HALF_B
-                if fuse and i + 1 < n:
+                if fuse and not self._merged and i + 1 < n:
                     stages |= L.STAGE_HALF_C
                 zc = z(2 * i + 2) if (stages & L.STAGE_HALF_C) else None
                 L.check(lib.psld_sscs_update(sp, sp, sdt, ip, L.ptr(e), None, z(2 * i + 1), zc,

@@ -203,11 +203,30 @@ def _fill_score(dst: L.ScoreStep, sch: PSLDSchedule, rows, i):
     dst.gs_m = float(rows["gs_m"][i])
 
 
+def _merge_halves(hb: L.HalfStep, hc: L.HalfStep, dst: L.HalfStep):
+    """One Gaussian draw for two consecutive half-steps: u'' = A_c (A_b u + L_b z_b) + L_c z_c has
+    mean A_c A_b u and covariance A_c L_b L_b^T A_c^T + L_c L_c^T, so it equals (in law, exactly)
+    A_bc u + L_bc z with L_bc the lower Cholesky factor of that covariance.  Used only when the
+    noise comes from the in-kernel generator (nothing to match draw by draw)."""
+    import numpy as np
+    Ab = np.array([[hb.a_xx, hb.a_xm], [hb.a_mx, hb.a_mm]])
+    Ac = np.array([[hc.a_xx, hc.a_xm], [hc.a_mx, hc.a_mm]])
+    Lb = np.array([[hb.c11, hb.c12], [hb.c21, hb.c22]])
+    Lc = np.array([[hc.c11, hc.c12], [hc.c21, hc.c22]])
+    A = Ac @ Ab
+    S = Ac @ Lb @ Lb.T @ Ac.T + Lc @ Lc.T
+    l11 = math.sqrt(S[0, 0]); l21 = S[1, 0] / l11; l22 = math.sqrt(S[1, 1] - l21 * l21)
+    if any(math.isnan(v) for v in (l11, l21, l22)):
+        raise ValueError("Numerical precision error.")
+    dst.a_xx, dst.a_xm, dst.a_mx, dst.a_mm = A[0, 0], A[0, 1], A[1, 0], A[1, 1]
+    dst.c11, dst.c12, dst.c21, dst.c22 = l11, 0.0, l21, l22
+
+
 class StepTables:
     """ctypes tables for one ``sample()`` call."""
 
     def __init__(self, sch: PSLDSchedule, ts, n: int, sampler: str, denoise: bool, eps: float,
-                 embedding: str = "fourier"):
+                 embedding: str = "fourier", merge_noise: bool = False):
         ts = torch.as_tensor(ts, dtype=_F64).cpu()
         assert ts.numel() >= n + 1
         self.n = n
@@ -226,6 +245,9 @@ class StepTables:
                     if i + 1 < n:
                         _fill_half(tab[i].half_c, a, c, i + 1)
                     _fill_score(tab[i].score, sch, rows, i)
+                if merge_noise:      # half B of step i and half A of step i+1 share one draw
+                    for i in range(n - 1):
+                        _merge_halves(tab[i].half_b, tab[i].half_c, tab[i].half_b)
                 self.sscs = tab
             elif sampler == "em_sde":
                 rows = _score_rows(sch, tau, dt, torch.sqrt(dt))  # sde.py:24 `g * sqrt(dt)`

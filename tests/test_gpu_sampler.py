@@ -38,11 +38,12 @@ def _golden_cfg(tag):
     return cfg
 
 
-def _run(cfg, score_fn, u0, nb, state_dtype=torch.float64, fuse=False, record=True):
+def _run(cfg, score_fn, u0, nb, state_dtype=torch.float64, fuse=False, record=True, merge=False):
     kind = cfg.evaluation.sampler.name
     S = SAMPLERS[kind](cfg, PSLD(cfg), score_fn)
     S.state_dtype = state_dtype
     S.fuse_halves = fuse
+    S.merge_noise = merge
     S.noise = torch.stack(nb).cuda() if nb is not None else None
     S.record = True if record else None
     ts, n = time_grid(cfg)
@@ -145,3 +146,25 @@ def test_philox_mode_runs_and_is_reproducible():
     assert torch.isfinite(a).all() and torch.equal(a, b)
     c, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=False, record=False)
     assert max_rel(c, a) <= 1e-5     # fused and unfused draw the same Philox streams
+    # merged draw (one Gaussian per fused pair of half-steps): reproducible, finite
+    m1, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=True, record=False, merge=True)
+    m2, _, _ = _run(cfg, net, u0, None, state_dtype=torch.float32, fuse=True, record=False, merge=True)
+    assert torch.isfinite(m1).all() and torch.equal(m1, m2)
+
+
+def test_merged_noise_is_exact_in_law():
+    """Merging half B of step i with half A of step i+1 into one draw keeps the law of the chain:
+    with a zero score network the end state is Gaussian with a known 2x2 covariance per pair."""
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=6, denoise=False)
+    cfg.data.image_size = 64
+    zero = lambda u, t: torch.zeros_like(u)
+    B = 16
+    u0 = torch.zeros(B, 6, 64, 64)
+    outs = {}
+    for merge in (False, True):
+        out, _, _ = _run(cfg, zero, u0, None, fuse=True, record=False, merge=merge)
+        x, m = torch.chunk(out.double().cpu(), 2, 1)
+        outs[merge] = (float(x.var()), float((x * m).mean()), float(m.var()))
+    n = B * 3 * 64 * 64
+    for a, b in zip(outs[False], outs[True]):
+        assert abs(a - b) <= 6 * max(abs(a), 1e-3) / np.sqrt(n) * 2 + 1e-6, (outs)
