@@ -181,6 +181,10 @@ enum { PSLD_TEMB_NT = 0, PSLD_TEMB_NF, PSLD_TEMB_EMB, PSLD_TEMB_TOTALC, PSLD_TEM
  *   in[0] = x1 [N,HW,C1], in[1] = x2 [N,HW,C2] or NULL (virtual torch.cat([x1,x2],1),
  *   ncsnpp.py:374), in[2] = gamma [C], in[3] = beta [C];  out[0] = y [N,HW,C1+C2],
  *   out[1] = scratch, >= N*NCHUNK*G*2 doubles
+ *   in[4], in[5] = optional producer-side statistics of x1 / x2: fp32 [N*HW/32, C/4, 2] holding
+ *   (sum, sum of squares) per 32 pixels x 4 channels, written by the PSLD_OP_CONV that produced
+ *   the tensor (its out[1]).  When every source has them the full-tensor statistics pass is
+ *   replaced by a fold over these micro-groups.
  *   i: N, HW, C1, C2, G, SILU, IN_DTYPE, OUT_DTYPE, NCHUNK ; f[0] = eps                 */
 enum { PSLD_GN_N = 0, PSLD_GN_HW, PSLD_GN_C1, PSLD_GN_C2, PSLD_GN_G, PSLD_GN_SILU,
        PSLD_GN_IN_DTYPE, PSLD_GN_OUT_DTYPE, PSLD_GN_NCHUNK };
@@ -197,6 +201,8 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
  *   in[0] = x1, in[1] = x2 or NULL, in[2] = residual [N,OH,OW,Cout] or NULL,
  *   in[3] = temb proj (f32) or NULL, in[4] = weight, in[5] = bias f32 [Cout] or NULL
  *   out[0] = y
+ *   out[1] = optional fp32 [N*OH*OW/32, Cout/4, 2] micro-group statistics of y for the GroupNorm
+ *            that consumes it (TC engine, bf16 NHWC output, OH*OW % 32 == 0), or NULL
  *   weight layout: SIMT engine f32 [K, Cout] ; TC engine bf16 [Cout, K], K = (ky*KW+kx)*Cin + c
  *   i: N, H, W, C1, C2, COUT, KS (1|3), STRIDE, PAD, OH, OW, IN_LAYOUT, OUT_LAYOUT,
  *      IN_DTYPE, OUT_DTYPE, RES_DTYPE, TEMB_OFF, TEMB_BSTRIDE ; f[0] = scale            */

@@ -50,6 +50,7 @@ struct ConvTcParams {
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
   float* y_nchw;             // when non-null: fp32 NCHW output, first cout_valid channels only
+  float* mg_stats;           // optional [M/32, Cout/4, 2] micro-group (sum, sumsq) of the output
   int cout_valid;
   float scale;
   int temb_off, temb_bstride;
@@ -187,18 +188,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const bool valid = m < p.M;
       const int img = valid ? (int)(m / p.HW) : 0;
       const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
+      const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
+      const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
       for (int ch = 0; ch < p.block_n; ch += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                (uint32_t)acc * 256u + (uint32_t)ch;
         tmem_ld32(taddr, r);
         tmem_ld_wait();
-        if (valid) {
-          const int co0 = n_tile * p.block_n + ch;
-          const int64_t o = m * p.Cout + co0;
-          float v[32];
+        const int co0 = n_tile * p.block_n + ch;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+        if (valid) {
+          const int64_t o = m * p.Cout + co0;
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -227,6 +230,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           if (p.y_nchw) {
             // network output head (ncsnpp.py:430): fp32 NCHW, lanes = consecutive pixels
             const int64_t pix = m - (int64_t)img * p.HW;
@@ -234,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int j = 0; j < 32; ++j) {
               const int co = co0 + j;
               if (co < p.cout_valid)
-                p.y_nchw[((int64_t)img * p.cout_valid + co) * p.HW + pix] = v[j] * p.scale;
+                p.y_nchw[((int64_t)img * p.cout_valid + co) * p.HW + pix] = v[j];
             }
           } else {
 #pragma unroll
@@ -242,8 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               uint32_t w[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                __nv_bfloat162 h =
-                    __floats2bfloat162_rn(v[j + 2 * t] * p.scale, v[j + 2 * t + 1] * p.scale);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
                 w[t] = *reinterpret_cast<uint32_t*>(&h);
               }
               *reinterpret_cast<uint4*>(p.y + o + j) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -251,6 +255,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
         __syncwarp();
+        if (stats) {
+          // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
+          // granularity: (sum, sum of squares) over this warp's 32 pixels.  16 values per lane are
+          // transposed-and-reduced across the warp with 16 shuffles (halving butterfly); the
+          // consumer GroupNorm combines micro-groups into its groups (gn_finalize_kernel).
+          float a[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
+            a[2 * g] = (x0 + x1) + (x2 + x3);
+            a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+          }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send = hi ? a[j] : a[j + w];
+              const float keep = hi ? a[j + w] : a[j];
+              a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+            }
+          }
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+          if ((lane & 1) == 0) {
+            const int idx = lane >> 1;     // = bit4*8 + bit3*4 + bit2*2 + bit1
+            p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + idx] = a[0];
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -351,6 +383,12 @@ int prepare_conv_tc(psld_op& op) {
   p.y = head ? nullptr : (__nv_bfloat16*)op.out[0];
   p.y_nchw = head ? (float*)op.out[0] : nullptr;
   p.cout_valid = head ? (int)op.f[1] : Cout;
+  p.mg_stats = (float*)op.out[1];
+  if (p.mg_stats && (head || (H * W) % 32 != 0)) {
+    delete st;
+    set_error("conv_tc: micro-group stats need NHWC bf16 output and H*W %% 32 == 0");
+    return PSLD_EINVAL;
+  }
   p.scale = op.f[0];
   p.temb_off = op.i[PSLD_CONV_TEMB_OFF];
   p.temb_bstride = op.i[PSLD_CONV_TEMB_BSTRIDE];

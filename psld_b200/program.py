@@ -53,6 +53,8 @@ class Plan:
         self.ops = []
         self.pool = {}
         self.engine_count = {"tc": 0, "simt": 0}
+        self.mg = {}            # data_ptr of an activation -> its micro-group statistics tensor
+        self.fused_stats = True
         self.temb_op = -1
         self._build()
         self.n_ops = len(self.ops)
@@ -74,6 +76,14 @@ class Plan:
 
     def _release(self, t):
         self.pool.setdefault(tuple(t.shape), []).append(t)
+        st = self.mg.pop(t.data_ptr(), None)
+        if st is not None:
+            self.pool.setdefault(("mg",) + tuple(st.shape), []).append(st)
+
+    def _mg_buffer(self, rows, cout):
+        key = ("mg", rows // 32, cout // 4, 2)
+        lst = self.pool.setdefault(key, [])
+        return lst.pop() if lst else self._new(rows // 32, cout // 4, 2, dtype=torch.float32)
 
     def _w(self, t, dtype=torch.float32):
         t = t.detach().to(device=self.dev, dtype=dtype).contiguous()
@@ -120,6 +130,12 @@ class Plan:
         op.inp[2] = self._w(gn_mod.weight).data_ptr()
         op.inp[3] = self._w(gn_mod.bias).data_ptr()
         op.out[0] = y.data_ptr()
+        s1 = self.mg.get(x1.data_ptr())
+        s2 = self.mg.get(x2.data_ptr()) if x2 is not None else None
+        if s1 is not None and (x2 is None or s2 is not None) and (Cc // G) % 4 == 0:
+            op.inp[4] = s1.data_ptr()
+            op.inp[5] = s2.data_ptr() if s2 is not None else None
+            self.engine_count["gn_fused_stats"] = self.engine_count.get("gn_fused_stats", 0) + 1
         need = self.B * nchunk * G * 2
         if self.gn_scratch is None or self.gn_scratch.numel() < need:
             self.gn_scratch = self._new(max(need, 1 << 16), dtype=torch.float64)
@@ -149,7 +165,7 @@ class Plan:
 
     def op_conv(self, x1, x2, w_oihw, bias, *, ks, stride=1, pad=None, residual=None,
                 temb_off=-1, scale=1.0, out=None, in_nchw=False, out_nchw_f32=False,
-                hw=None, allow_tc=True):
+                hw=None, allow_tc=True, want_stats=True):
         """y = scale * (conv(cat(x1,x2), w) + bias + temb + residual); w is [Cout, Cin, ks, ks]."""
         pad = ks // 2 if pad is None else pad
         if in_nchw:
@@ -203,7 +219,16 @@ class Plan:
             i[L.CONV_COUT] = cout_pad
             op.i[L.CONV_OUT_DTYPE] = L.F32 if out_nchw_f32 else self.acode
             op.f[1] = float(Cout)                    # valid output channels (NCHW f32 epilogue)
+            mg = None
+            if self.fused_stats and want_stats and not out_nchw_f32 and (OH * OW) % 32 == 0 and Cout % 32 == 0:
+                mg = self._mg_buffer(N * OH * OW, Cout)
+                op.out[1] = mg.data_ptr()
             rc = self._tc_eligible(op) if self.dry else self.lib.psld_op_prepare(C.byref(op))
+            if rc == L.OK and mg is not None:
+                self.mg[out.data_ptr()] = mg
+            elif mg is not None:
+                op.out[1] = None
+                self.pool.setdefault(("mg",) + tuple(mg.shape), []).append(mg)
             if rc == L.OK:
                 done = True
                 self.engine_count["tc"] += 1
@@ -284,7 +309,7 @@ class Plan:
         b = self.op_gn(h, None, m.GroupNorm_1, True, h.shape[1] * h.shape[2])
         self._release(h)
         if hasattr(m, "Conv_2"):
-            sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1)
+            sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
         else:
             assert xs2 is None
             sc = xs1
@@ -304,7 +329,7 @@ class Plan:
         a = self.op_gn(x, None, m.GroupNorm_0, False, H * W)
         wqkv = torch.cat([m.NIN_0.W, m.NIN_1.W, m.NIN_2.W], dim=1)          # [C, 3C]
         bqkv = torch.cat([m.NIN_0.b, m.NIN_1.b, m.NIN_2.b], dim=0)
-        qkv = self.op_conv(a, None, wqkv.t().reshape(3 * Cc, Cc, 1, 1), bqkv, ks=1)
+        qkv = self.op_conv(a, None, wqkv.t().reshape(3 * Cc, Cc, 1, 1), bqkv, ks=1, want_stats=False)
         self._release(a)
         o = self.op_attn(qkv, H * W, Cc)
         self._release(qkv)

@@ -26,7 +26,8 @@ def run_op(op, prepare=False):
 
 
 def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=None, temb_off=0,
-            temb_bstride=0, scale=1.0, engine=L.ENGINE_SIMT, out_nchw_f32=False, out=None):
+            temb_bstride=0, scale=1.0, engine=L.ENGINE_SIMT, out_nchw_f32=False, out=None,
+            mg_stats=False):
     """x*: NHWC tensors on cuda.  Returns (op, out, keepalive)."""
     N, H, W, C1 = x1.shape
     C2 = x2.shape[-1] if x2 is not None else 0
@@ -79,6 +80,10 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
     op.inp[4] = wp.data_ptr()
     op.inp[5] = b.data_ptr() if b is not None else None
     op.out[0] = out.data_ptr()
+    if mg_stats:
+        mg = torch.full((N * OH * OW // 32, Cout // 4, 2), float("nan"), dtype=torch.float32, device=dev)
+        op.out[1] = mg.data_ptr()
+        keep.append(mg)
     return op, out, keep
 
 
@@ -102,7 +107,13 @@ def conv_ref(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=No
     return (y * scale)     # NCHW float64
 
 
-def gn_op(x1, x2, gamma, beta, G, silu, eps=1e-6, nchunk=4, out_dtype=None):
+def mg_ref(y_nhwc):
+    """Micro-group statistics [rows/32, C/4, 2] of an NHWC tensor (fp64)."""
+    v = y_nhwc.double().cpu().reshape(-1, 32, y_nhwc.shape[-1] // 4, 4)
+    return torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1)
+
+
+def gn_op(x1, x2, gamma, beta, G, silu, eps=1e-6, nchunk=4, out_dtype=None, mg1=None, mg2=None):
     N = x1.shape[0]
     HW = int(np.prod(x1.shape[1:-1]))
     C1 = x1.shape[-1]
@@ -118,6 +129,8 @@ def gn_op(x1, x2, gamma, beta, G, silu, eps=1e-6, nchunk=4, out_dtype=None):
     op.inp[0] = x1.data_ptr()
     op.inp[1] = x2.data_ptr() if x2 is not None else None
     op.inp[2], op.inp[3] = gamma.data_ptr(), beta.data_ptr()
+    op.inp[4] = mg1.data_ptr() if mg1 is not None else None
+    op.inp[5] = mg2.data_ptr() if mg2 is not None else None
     op.out[0], op.out[1] = out.data_ptr(), scratch.data_ptr()
     return op, out, [scratch]
 

@@ -58,6 +58,15 @@ def run_plan(plan, x, t):
             xx = _f(x1) if x2 is None else torch.cat([_f(x1), _f(x2)], -1)
             assert xx.shape[-1] == i[L.GN_C1] + i[L.GN_C2]
             y = F.group_norm(xx.permute(0, 3, 1, 2), i[L.GN_G], g(op.inp[2]), g(op.inp[3]), eps=f[0])
+            if op.inp[4]:      # producer-side micro-group statistics must describe exactly x1 / x2
+                for src, st in ((x1, g(op.inp[4])), (x2, g(op.inp[5]))):
+                    if src is None:
+                        continue
+                    v = _f(src).reshape(-1, 32, src.shape[-1] // 4, 4)
+                    ref = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1)
+                    assert st is not None and tuple(st.shape) == tuple(ref.shape), (st.shape, ref.shape)
+                    # bf16 plans: the producer summed unrounded fp32 values, tolerate the rounding
+                    assert float((st - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
             if i[L.GN_SILU]:
                 y = F.silu(y)
             g(op.out[0]).copy_(y.permute(0, 2, 3, 1))
@@ -95,6 +104,9 @@ def run_plan(plan, x, t):
                 y = y + _f(g(op.inp[2])).permute(0, 3, 1, 2)
             y = y * f[0]
             out = g(op.out[0])
+            if op.out[1]:
+                v = y.permute(0, 2, 3, 1).reshape(-1, 32, cout // 4, 4)
+                g(op.out[1]).copy_(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1))
             if i[L.CONV_OUT_LAYOUT] == L.NCHW:
                 valid = int(f[1]) if op.engine == L.ENGINE_TC else cout
                 out.copy_(y[:, :valid])

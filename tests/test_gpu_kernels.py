@@ -13,7 +13,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from _ops import attn_op, conv_op, conv_ref, fir_op, gn_op, max_rel, rel_l2, run_op
+from _ops import attn_op, conv_op, conv_ref, fir_op, gn_op, max_rel, mg_ref, rel_l2, run_op
 from oracle import psld_oracle as O
 from oracle.weights import noise_bank, prior
 from psld_b200 import _lib as L
@@ -282,11 +282,26 @@ def test_conv_tc(case):
     res = _t(r.standard_normal((N, H, W, Cout)), torch.bfloat16)
     temb = _t(r.standard_normal((N, Cout + 32)))
     kw = dict(residual=res, temb=temb, temb_off=32, temb_bstride=Cout + 32, scale=0.7071)
-    op, out, keep = conv_op(x1, x2, w, b, engine=L.ENGINE_TC, **kw)
+    want_mg = (H * W) % 32 == 0
+    op, out, keep = conv_op(x1, x2, w, b, engine=L.ENGINE_TC, mg_stats=want_mg, **kw)
     run_op(op, prepare=True)
     ref = conv_ref(x1, x2, w.to(torch.bfloat16), b, **kw)      # same bf16-rounded weights
     err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
     assert err <= 4e-3, err                                     # bf16 output rounding only
+    if want_mg:
+        # fused GroupNorm micro-group statistics of the (unrounded) output
+        mg = keep[-1]
+        mref = mg_ref(ref.permute(0, 2, 3, 1))
+        assert torch.isfinite(mg).all()
+        assert float((mg.double().cpu() - mref).abs().max()) <= 2e-4 * float(mref.abs().max())
+        # and a GroupNorm consuming them equals the GroupNorm that re-reads the tensor
+        G = min(Cout // 4, 32)
+        ga = _t(1 + 0.2 * r.standard_normal(Cout)); be = _t(0.1 * r.standard_normal(Cout))
+        op1, o1, k1 = gn_op(out, None, ga, be, G, True, nchunk=2)
+        run_op(op1)
+        op2, o2, k2 = gn_op(out, None, ga, be, G, True, nchunk=2, mg1=mg)
+        run_op(op2)
+        assert rel_l2(o2.float(), o1.float()) <= 3e-3
     # plain (no epilogue terms), checks the accumulation itself at fp32-output precision
     op, out2, keep2 = conv_op(x1, x2, w, None, engine=L.ENGINE_TC, out_nchw_f32=True)
     run_op(op, prepare=True)
