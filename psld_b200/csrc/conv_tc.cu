@@ -21,7 +21,9 @@
 //   * torch.cat([h, skip]) inputs (ncsnpp.py:374) are never materialised: the K loop walks two
 //     tensor maps.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
-//     allocator, warps 2-5 = epilogue (tcgen05.ld -> bias/temb/residual/scale -> bf16 -> global).
+//     allocator, warps 2-9 = epilogue (tcgen05.ld -> bias/temb/residual/scale -> bf16 -> global;
+//     two warps per TMEM lane quarter, each taking every other 32-column chunk, with the residual
+//     of the next chunk prefetched while the current one is processed).
 //   * 4-stage smem ring (A 16 KB + B 32 KB per stage), mbarrier full/empty pairs,
 //     tcgen05.commit releases stages and publishes accumulators.
 
@@ -41,7 +43,7 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BLOCK_K * 2;          // 32 KB (max BLOCK_N = 256)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TC_TMEM_COLS = 512;
 
 struct ConvTcParams {
@@ -98,7 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -176,8 +178,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 2) >> 2;    // this warp takes the 32-column chunks with index % 2 == half
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -190,13 +193,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
       const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
       const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
-      for (int ch = 0; ch < p.block_n; ch += 32) {
+      const bool has_res = valid && p.res != nullptr;
+      uint4 rq[4];                                       // residual of the chunk being processed
+      if (has_res && half * 32 < p.block_n) {
+        const __nv_bfloat16* rp = p.res + m * p.Cout + n_tile * p.block_n + half * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rq[t] = *reinterpret_cast<const uint4*>(rp + 8 * t);
+      }
+      for (int ch = half * 32; ch < p.block_n; ch += 64) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                (uint32_t)acc * 256u + (uint32_t)ch;
         tmem_ld32(taddr, r);
-        tmem_ld_wait();
         const int co0 = n_tile * p.block_n + ch;
+        uint4 rn[4];                                     // prefetch the next chunk's residual
+        const bool more = ch + 64 < p.block_n;
+        if (has_res && more) {
+          const __nv_bfloat16* rp = p.res + m * p.Cout + co0 + 64;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) rn[t] = *reinterpret_cast<const uint4*>(rp + 8 * t);
+        }
+        tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
@@ -219,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (p.res) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 q = *reinterpret_cast<const uint4*>(p.res + o + j);
+              const uint4 q = rq[j >> 3];
               const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -253,6 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               *reinterpret_cast<uint4*>(p.y + o + j) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
+        }
+        if (has_res && more) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) rq[t] = rn[t];
         }
         __syncwarp();
         if (stats) {

@@ -304,7 +304,7 @@ class Plan:
             a = a2
             xs1 = self.op_fir(x1, taps, up, down, p0, p1)
             fir_tmp.append(xs1)
-        h = self.op_conv(a, None, m.Conv_0.weight, m.Conv_0.bias, ks=3, temb_off=temb_off)
+        h = self.op_conv(a, None, m.Conv_0.weight, None, ks=3, temb_off=temb_off)  # bias: see temb
         self._release(a)
         b = self.op_gn(h, None, m.GroupNorm_1, True, h.shape[1] * h.shape[2])
         self._release(h)
@@ -362,7 +362,9 @@ class Plan:
             tot += m.out_ch
         self.total_c = tot
         wd = self._w(torch.cat([m.Dense_0.weight for m in rbs], 0))
-        bd = self._w(torch.cat([m.Dense_0.bias for m in rbs], 0))
+        # Conv_0's bias is folded into the Dense_0 bias: both are per-(n, channel) terms added
+        # to the same accumulator (layerspp.py:260-263), so the conv epilogue adds ONE vector
+        bd = self._w(torch.cat([m.Dense_0.bias + m.Conv_0.bias for m in rbs], 0))
         E = 2 * net.nf if net.embedding_type == "fourier" else net.nf
         self.temb_proj = self._new(self.nt, tot, dtype=torch.float32)
         scratch = self._new(self.nt, E + 8 * net.nf, dtype=torch.float32)
