@@ -146,7 +146,8 @@ PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B,
 #define PSLD_OP_ATTN 6   /* softmax(q k^T / sqrt(C)) v                                  */
 
 #define PSLD_ENGINE_SIMT 0 /* fp32 FFMA implicit GEMM (any shape)                       */
-#define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0)  */
+#define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0;
+                              stride 1 'same' padding, or 3x3 stride 2 without padding)     */
 
 #define PSLD_OP_NI 28
 #define PSLD_OP_NF 24
@@ -165,8 +166,9 @@ typedef struct {
 } psld_op;
 
 /* --- PSLD_OP_LAYOUT: in[0] -> out[0].  i: N, C, HW, dir (0: NCHW f32 -> NHWC T, 1: NHWC T
- *     -> NCHW f32), dtype (T) */
-enum { PSLD_LAYOUT_N = 0, PSLD_LAYOUT_C, PSLD_LAYOUT_HW, PSLD_LAYOUT_DIR, PSLD_LAYOUT_DTYPE };
+ *     -> NCHW f32), dtype (T), CPAD (dir 0 only: NHWC channel count >= C, zero padded; 0 = C) */
+enum { PSLD_LAYOUT_N = 0, PSLD_LAYOUT_C, PSLD_LAYOUT_HW, PSLD_LAYOUT_DIR, PSLD_LAYOUT_DTYPE,
+       PSLD_LAYOUT_CPAD };
 
 /* --- PSLD_OP_TEMB (ncsnpp.py:292-311, layerspp.py:32-41,262-263, layers.py:500-514):
  *   in[0] = time [nt] f32 (forward time tau, or log(tau) when i[LOGGED]=1)

@@ -23,7 +23,7 @@ ENGINE_SIMT, ENGINE_TC = 0, 1
 OP_NI, OP_NF, OP_NP = 28, 24, 8
 
 # slot indices
-(LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE) = range(5)
+(LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE, LAYOUT_CPAD) = range(6)
 (TEMB_NT, TEMB_NF, TEMB_EMB, TEMB_TOTALC, TEMB_LOGGED) = range(5)
 (GN_N, GN_HW, GN_C1, GN_C2, GN_G, GN_SILU, GN_IN_DTYPE, GN_OUT_DTYPE, GN_NCHUNK) = range(9)
 (FIR_N, FIR_H, FIR_W, FIR_C, FIR_UP, FIR_DOWN, FIR_PAD0, FIR_PAD1, FIR_KH, FIR_DTYPE) = range(10)

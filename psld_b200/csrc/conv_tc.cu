@@ -56,8 +56,10 @@ struct ConvTcParams {
   int cout_valid;
   float scale;
   int temb_off, temb_bstride;
-  int H, W, HW, Cout;
-  int BH, BN_img;            // TMA box: {64, W, BH, BN_img}, W*BH*BN_img == 128
+  int H, W, HW, Cout;        // OUTPUT map size (== input size for the stride-1 'same' case)
+  int stride, pad;           // 1/KS/2, or 2/0 (3x3 stride-2 conv on a pre-padded input)
+  int BH, BN_img;            // output rows / images per tile: W*BH*BN_img == 128; the TMA box is
+                             // {64, W*stride, BH*stride, BN_img} traversed with element stride
   int tiles_y;               // H / BH
   int kchunks1, kchunks;     // 64-channel chunks in source 1 / in total (C1+C2)/64
   int taps, KS;
@@ -129,16 +131,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < total_kb; ++kb) {
           const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
           const int ky = tap / p.KS, kx = tap - ky * p.KS;
-          const int off = p.KS >> 1;
+          const int off = p.pad;
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), stage_tx);
           const uint32_t sa = base + stage * TC_STAGE_BYTES;
           const uint32_t sb = sa + TC_A_BYTES;
           if (cc < p.kchunks1)
-            tma_load_4d(sa, &tmA1, full_bar(stage), cc * TC_BLOCK_K, kx - off, y0 + ky - off, n0);
+            tma_load_4d(sa, &tmA1, full_bar(stage), cc * TC_BLOCK_K, kx - off,
+                        y0 * p.stride + ky - off, n0);
           else
             tma_load_4d(sa, &tmA2, full_bar(stage), (cc - p.kchunks1) * TC_BLOCK_K, kx - off,
-                        y0 + ky - off, n0);
+                        y0 * p.stride + ky - off, n0);
           tma_load_2d(sb, &tmB, full_bar(stage), kb * TC_BLOCK_K, n_tile * p.block_n);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -322,14 +325,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 }
 
 // ---------------------------------------------------------------- host side
-static int encode_act_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int BH,
-                          int BN_img) {
+// Activation map over the INPUT tensor [N, H, W, C]; the box covers OW x BH x BN output positions
+// visited with element stride `stride` (TMA loads ceil(box / stride) elements per dimension).
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int OW,
+                          int BH, int BN_img, int stride) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)W, (cuuint32_t)BH, (cuuint32_t)BN_img};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(OW * stride), (cuuint32_t)(BH * stride),
+                       (cuuint32_t)BN_img};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -369,11 +375,20 @@ int prepare_conv_tc(psld_op& op) {
   if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC) return unsupported("input layout must be NHWC");
   if (head && (op.in[2] || op.f[1] < 1.0f || (int)op.f[1] > Cout))
     return unsupported("NCHW head takes no residual and needs f[1] = valid channels");
-  if (op.i[PSLD_CONV_STRIDE] != 1 || op.i[PSLD_CONV_PAD] != KS / 2 || (KS != 1 && KS != 3))
-    return unsupported("stride 1 / same padding only");
+  const int stride = op.i[PSLD_CONV_STRIDE], pad = op.i[PSLD_CONV_PAD];
+  const bool same = stride == 1 && pad == KS / 2 && (KS == 1 || KS == 3);
+  const bool down2 = stride == 2 && pad == 0 && KS == 3 && C2 == 0;   // conv_downsample_2d's conv
+  if (!same && !down2) return unsupported("stride 1 'same' or 3x3 stride 2 pad 0 only");
+  const int OH = op.i[PSLD_CONV_OH], OW = op.i[PSLD_CONV_OW];
+  if (OH != (H + 2 * pad - KS) / stride + 1 || OW != (W + 2 * pad - KS) / stride + 1) {
+    set_error("conv_tc: OH/OW mismatch");
+    return PSLD_EINVAL;
+  }
   if (C1 % TC_BLOCK_K || C2 % TC_BLOCK_K) return unsupported("Cin %% 64 != 0");
   if (Cout % 32) return unsupported("Cout %% 32 != 0");
-  if (!is_pow2(W) || !is_pow2(H) || W > 128 || W < 4) return unsupported("W,H must be pow2, 4..128");
+  if (!is_pow2(OW) || !is_pow2(OH) || OW > 128 || OW < 4)
+    return unsupported("output W,H must be pow2, 4..128");
+  if (stride == 2 && OW * stride > 256) return unsupported("stride-2 box too wide");
   if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != PSLD_BF16) return unsupported("residual dtype");
   if (!op.in[0] || !op.in[4] || !op.out[0] || (C2 > 0 && !op.in[1])) {
     set_error("conv_tc: null pointer");
@@ -382,17 +397,17 @@ int prepare_conv_tc(psld_op& op) {
   int block_n = 0;
   for (int cand : {256, 128, 64, 32})
     if (Cout % cand == 0) { block_n = cand; break; }
-  int BH = 128 / W;
-  if (BH > H) BH = H;
-  const int BN_img = 128 / (W * BH);
+  int BH = 128 / OW;
+  if (BH > OH) BH = OH;
+  const int BN_img = 128 / (OW * BH);
   if (BN_img > 256) return unsupported("image too small");
 
   ConvTcState* st = new (std::nothrow) ConvTcState();
   if (!st) { set_error("conv_tc: out of host memory"); return PSLD_ECUDA; }
-  int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, BH, BN_img);
+  int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   if (rc == PSLD_OK)
-    rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, BH, BN_img)
-                : encode_act_map(&st->a2, op.in[0], N, H, W, C1, BH, BN_img);
+    rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, OW, BH, BN_img, stride)
+                : encode_act_map(&st->a2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   const int K = KS * KS * (C1 + C2);
   if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, block_n);
   if (rc != PSLD_OK) { delete st; return rc; }
@@ -405,7 +420,7 @@ int prepare_conv_tc(psld_op& op) {
   p.y_nchw = head ? (float*)op.out[0] : nullptr;
   p.cout_valid = head ? (int)op.f[1] : Cout;
   p.mg_stats = (float*)op.out[1];
-  if (p.mg_stats && (head || (H * W) % 32 != 0)) {
+  if (p.mg_stats && (head || (OH * OW) % 32 != 0)) {
     delete st;
     set_error("conv_tc: micro-group stats need NHWC bf16 output and H*W %% 32 == 0");
     return PSLD_EINVAL;
@@ -413,12 +428,13 @@ int prepare_conv_tc(psld_op& op) {
   p.scale = op.f[0];
   p.temb_off = op.i[PSLD_CONV_TEMB_OFF];
   p.temb_bstride = op.i[PSLD_CONV_TEMB_BSTRIDE];
-  p.H = H; p.W = W; p.HW = H * W; p.Cout = Cout;
-  p.BH = BH; p.BN_img = BN_img; p.tiles_y = H / BH;
+  p.H = OH; p.W = OW; p.HW = OH * OW; p.Cout = Cout;
+  p.stride = stride; p.pad = pad;
+  p.BH = BH; p.BN_img = BN_img; p.tiles_y = OH / BH;
   p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
   p.taps = KS * KS; p.KS = KS;
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
-  p.M = (int64_t)N * H * W;
+  p.M = (int64_t)N * OH * OW;
   const int64_t m_tiles = (int64_t)((N + BN_img - 1) / BN_img) * p.tiles_y;
   p.num_tiles = (int)(m_tiles * p.n_tiles_n);
   int dev = 0, sms = 148;

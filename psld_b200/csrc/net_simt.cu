@@ -16,17 +16,20 @@
 namespace psld {
 
 // ======================================================================== layout
+// NCHW fp32 -> NHWC T with the channel axis zero-padded to CP >= C (CP = 64 lets the 6-channel
+// network input go through the tensor-core convolution, whose K chunks are 64 channels)
 template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int HW) {
-  const int64_t total = (int64_t)N * C * HW;
+nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int HW,
+                    int CP) {
+  const int64_t total = (int64_t)N * CP * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int64_t r = i / C;
+    const int c = (int)(i % CP);
+    const int64_t r = i / CP;
     const int p = (int)(r % HW);
     const int n = (int)(r / HW);
-    out[i] = from_f32<T>(in[((int64_t)n * C + c) * HW + p]);
+    out[i] = c < C ? from_f32<T>(in[((int64_t)n * C + c) * HW + p]) : from_f32<T>(0.f);
   }
 }
 
@@ -54,14 +57,17 @@ int run_layout(const psld_op& op, cudaStream_t s) {
   const int N = op.i[PSLD_LAYOUT_N], C = op.i[PSLD_LAYOUT_C], HW = op.i[PSLD_LAYOUT_HW];
   const int dir = op.i[PSLD_LAYOUT_DIR], dt = op.i[PSLD_LAYOUT_DTYPE];
   PSLD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && op.in[0] && op.out[0], "layout: bad arguments");
-  const int grid = ew_grid((int64_t)N * C * HW);
+  int CP = op.i[PSLD_LAYOUT_CPAD];
+  if (CP <= 0) CP = C;
+  PSLD_CHECK_ARG(CP >= C && (dir == 0 || CP == C), "layout: bad channel padding");
+  const int grid = ew_grid((int64_t)N * CP * HW);
   if (dir == 0) {
     if (dt == PSLD_BF16)
       nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const float*)op.in[0],
-                                                            (__nv_bfloat16*)op.out[0], N, C, HW);
+                                                            (__nv_bfloat16*)op.out[0], N, C, HW, CP);
     else
       nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)op.in[0], (float*)op.out[0],
-                                                    N, C, HW);
+                                                    N, C, HW, CP);
   } else {
     if (dt == PSLD_BF16)
       nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)op.in[0],
@@ -448,10 +454,12 @@ int run_gn(const psld_op& op, cudaStream_t s) {
 // zero-stuffed (x up), (pad0,pad1)-padded / cropped input  (op/upfirdn2d.py:159-200).
 struct FirTaps { float k[16]; };
 
-template <typename T, int VW>
+// UP / DOWN are compile-time (the three cases the network uses: 2/1, 1/2, 1/1); 0 = runtime.
+template <typename T, int VW, int UP, int DOWN>
 __global__ void __launch_bounds__(256)
 fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C,
-           int OH, int OW, int up, int down, int pad0, int KH) {
+           int OH, int OW, int up_rt, int down_rt, int pad0, int KH) {
+  const int up = UP ? UP : up_rt, down = DOWN ? DOWN : down_rt;
   const int vpr = C / VW;
   const int64_t total = (int64_t)N * OH * OW * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -487,11 +495,14 @@ fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int 
       }
     }
     T* dst = y + (((int64_t)n * OH + oy) * OW + ox) * C + cv * VW;
-    if (VW == 8) { float o[8]; 
+    if (VW == 8) {
+      float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = acc[k < VW ? k : 0];
-      Vec8<T>::store(dst, o); }
-    else Vec4<T>::store(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      Vec8<T>::store(dst, o);
+    } else {
+      Vec4<T>::store(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
   }
 }
 
@@ -545,12 +556,20 @@ int run_fir(const psld_op& op, cudaStream_t s) {
   if (C % 4 == 0) {
     const int vw = C % 8 == 0 ? 8 : 4;
     const int grid = (int)ceil_div((int64_t)N * OH * OW * (C / vw), 256);
-#define FIR_LAUNCH(T, VW)                                                                     \
-  fir_kernel<T, VW><<<grid, 256, 0, s>>>((const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, OH, \
-                                         OW, up, down, pad0, KH)
+#define FIR_LAUNCH2(T, VW, U, D)                                                              \
+  fir_kernel<T, VW, U, D><<<grid, 256, 0, s>>>((const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, \
+                                               OH, OW, up, down, pad0, KH)
+#define FIR_LAUNCH(T, VW)                                          \
+  do {                                                             \
+    if (up == 2 && down == 1) FIR_LAUNCH2(T, VW, 2, 1);            \
+    else if (up == 1 && down == 2) FIR_LAUNCH2(T, VW, 1, 2);       \
+    else if (up == 1 && down == 1) FIR_LAUNCH2(T, VW, 1, 1);       \
+    else FIR_LAUNCH2(T, VW, 0, 0);                                 \
+  } while (0)
     if (dt == PSLD_BF16) { if (vw == 8) FIR_LAUNCH(__nv_bfloat16, 8); else FIR_LAUNCH(__nv_bfloat16, 4); }
     else { if (vw == 8) FIR_LAUNCH(float, 8); else FIR_LAUNCH(float, 4); }
 #undef FIR_LAUNCH
+#undef FIR_LAUNCH2
   } else {
     const int grid = ew_grid((int64_t)N * OH * OW * C);
     const int64_t sn = (int64_t)H * W * C, sy = (int64_t)W * C, sx = C, sc = 1;

@@ -101,10 +101,10 @@ class Plan:
         return len(self.ops) - 1
 
     # ---------------------------------------------------------------- op builders
-    def op_layout(self, src, dst, N, Cc, HW, direction):
+    def op_layout(self, src, dst, N, Cc, HW, direction, cpad=0):
         op = self._op(L.OP_LAYOUT)
         op.i[L.LAYOUT_N], op.i[L.LAYOUT_C], op.i[L.LAYOUT_HW] = N, Cc, HW
-        op.i[L.LAYOUT_DIR], op.i[L.LAYOUT_DTYPE] = direction, self.acode
+        op.i[L.LAYOUT_DIR], op.i[L.LAYOUT_DTYPE], op.i[L.LAYOUT_CPAD] = direction, self.acode, cpad
         op.inp[0], op.out[0] = src.data_ptr(), dst.data_ptr()
         self._push(op)
 
@@ -174,6 +174,9 @@ class Plan:
             N, H, W, C1 = x1.shape
         C2 = x2.shape[-1] if x2 is not None else 0
         Cout = w_oihw.shape[0]
+        if x2 is None and w_oihw.shape[1] < C1:       # zero-padded input channels (6 -> 64)
+            w_oihw = torch.cat([w_oihw.detach(), w_oihw.new_zeros(
+                Cout, C1 - w_oihw.shape[1], *w_oihw.shape[2:])], 1)
         assert w_oihw.shape[1] == C1 + C2, (tuple(w_oihw.shape), C1, C2)
         OH = (H + 2 * pad - ks) // stride + 1
         OW = (W + 2 * pad - ks) // stride + 1
@@ -252,10 +255,11 @@ class Plan:
         i = op.i
         pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
         ks = i[L.CONV_KS]
-        ok = (i[L.CONV_IN_DTYPE] == L.BF16 and i[L.CONV_IN_LAYOUT] == L.NHWC
-              and i[L.CONV_STRIDE] == 1 and ks in (1, 3) and i[L.CONV_PAD] == ks // 2
+        same = i[L.CONV_STRIDE] == 1 and ks in (1, 3) and i[L.CONV_PAD] == ks // 2
+        down2 = i[L.CONV_STRIDE] == 2 and i[L.CONV_PAD] == 0 and ks == 3 and i[L.CONV_C2] == 0
+        ok = (i[L.CONV_IN_DTYPE] == L.BF16 and i[L.CONV_IN_LAYOUT] == L.NHWC and (same or down2)
               and i[L.CONV_C1] % 64 == 0 and i[L.CONV_C2] % 64 == 0 and i[L.CONV_COUT] % 32 == 0
-              and pow2(i[L.CONV_W]) and pow2(i[L.CONV_H]) and 4 <= i[L.CONV_W] <= 128)
+              and pow2(i[L.CONV_OW]) and pow2(i[L.CONV_OH]) and 4 <= i[L.CONV_OW] <= 128)
         return L.OK if ok else L.EUNSUPPORTED
 
     def op_attn(self, qkv, HW, Cc):
@@ -381,8 +385,11 @@ class Plan:
         self.temb_op = self._push(op)
 
         # ---- input: NCHW fp32 -> NHWC activations
-        x = self._new(B, H, H, net.in_ch)
-        self.op_layout(self.x_in, x, B, net.in_ch, H * H, 0)
+        # bf16 plans zero-pad the 6 input channels to 64 so that the input conv and the first
+        # pyramid conv are tensor-core eligible (K chunks are 64 channels)
+        cpad = 64 if (self.bf16 and net.in_ch < 64) else net.in_ch
+        x = self._new(B, H, H, cpad)
+        self.op_layout(self.x_in, x, B, net.in_ch, H * H, 0, cpad)
         pyr = x if net.progressive_input != "none" else None
         hs = [self.op_conv(x, None, mods[i].weight, mods[i].bias, ks=3,
                            out=self._new(B, H, H, net.nf))]; i += 1
@@ -404,7 +411,7 @@ class Plan:
                     scale = _SQRT1_2 if net.skip_rescale else 1.0
                     pyr = self.op_conv(padded, None, pm.Conv2d_0.weight, pm.Conv2d_0.bias, ks=3,
                                        stride=2, pad=0, residual=h, scale=scale,
-                                       out=self._new(*h.shape), allow_tc=False)
+                                       out=self._new(*h.shape))
                     self._release(padded)
                     h = pyr
                 hs.append(h)

@@ -35,7 +35,8 @@ def run_plan(plan, x, t):
         if op.kind == L.OP_LAYOUT:
             src, dst = g(op.inp[0]), g(op.out[0])
             if i[L.LAYOUT_DIR] == 0:
-                dst.copy_(src.permute(0, 2, 3, 1))
+                dst.zero_()
+                dst[..., : i[L.LAYOUT_C]].copy_(src.permute(0, 2, 3, 1))
             else:
                 dst.copy_(_f(src).permute(0, 3, 1, 2))
         elif op.kind == L.OP_TEMB:

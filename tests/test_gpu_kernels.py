@@ -310,6 +310,26 @@ def test_conv_tc(case):
     assert err2 <= 2e-5, err2
 
 
+@pytest.mark.parametrize("case", [(2, 17, 17, 256, 256), (3, 33, 33, 64, 256), (1, 65, 65, 64, 128),
+                                  (5, 9, 9, 128, 64)])
+def test_conv_tc_stride2(case):
+    """3x3 stride-2 conv on a FIR-padded map (conv_downsample_2d, up_or_down_sampling.py:178):
+    the TMA box walks the input with element stride 2."""
+    N, H, W, Cin, Cout = case
+    r = _rng(sum(case))
+    x = _t(r.standard_normal((N, H, W, Cin)), torch.bfloat16)
+    w = _t(r.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9))
+    b = _t(0.1 * r.standard_normal(Cout))
+    OH = (H - 3) // 2 + 1
+    res = _t(r.standard_normal((N, OH, OH, Cout)), torch.bfloat16)
+    kw = dict(stride=2, pad=0, residual=res, scale=0.7071)
+    op, out, keep = conv_op(x, None, w, b, engine=L.ENGINE_TC, **kw)
+    run_op(op, prepare=True)
+    ref = conv_ref(x, None, w.to(torch.bfloat16), b, **kw)
+    err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
+    assert err <= 4e-3, err
+
+
 def test_conv_tc_output_head():
     """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
     r = _rng(77)
