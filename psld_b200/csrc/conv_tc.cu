@@ -29,6 +29,8 @@
 
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -43,7 +45,7 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BLOCK_K * 2;          // 32 KB (max BLOCK_N = 256)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TC_THREADS = 352;        // A-TMA warp + MMA warp + 8 epilogue warps + B-TMA warp
 constexpr int TC_TMEM_COLS = 512;
 
 struct ConvTcParams {
@@ -72,122 +74,245 @@ struct ConvTcState {
   CUtensorMap a1, a2, b;
   ConvTcParams p;
   int grid;
+  bool pair;      // 2-CTA (cta_group::2) variant
 };
 
 // ---------------------------------------------------------------- the kernel
+// kPair = false: one CTA per tile (tcgen05 cta_group::1, M = 128).
+// kPair = true : a cluster of two CTAs (one TPC) works on two vertically adjacent M tiles with ONE
+//   tcgen05.mma.cta_group::2 stream (M = 256) issued by the leader CTA.  Each CTA loads its own
+//   A tile and only HALF of the weight tile (block_n/2 rows); the tensor core reads the B halves
+//   from both CTAs' shared memory.  Per CTA and k-block this cuts the L2->SM traffic from 48 KB to
+//   32 KB and frees room for a 6-deep ring (ncu on the 1-CTA kernel: tensor pipe 75 % active with
+//   the XBAR at 15.6 TB/s and only ~1.3 us of TMA lookahead).
+template <bool kPair>
+struct TcCfg {
+  static constexpr int kStages = kPair ? 6 : TC_STAGES;
+  static constexpr int kBBytes = kPair ? TC_B_BYTES / 2 : TC_B_BYTES;
+  static constexpr int kStageBytes = TC_A_BYTES + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xFFF) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+// 2-CTA TMA loads: data lands in THIS CTA's smem, bytes are credited to the LEADER's mbarrier
+// (peer bit 24 of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool kPair>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  using Cfg = TcCfg<kPair>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t bar_base = base + kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  // work decomposition: a "unit" is one tile (1-CTA) or two vertically adjacent M tiles (pair)
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 2);      // A producer + B producer (of the leader CTA)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), kPair ? 16 : 8);   // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int total_kb = p.taps * p.kchunks;
-  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.block_n * TC_BLOCK_K * 2;
+  const int b_rows = kPair ? (p.block_n >> 1) : p.block_n;        // weight rows this CTA loads
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 10) {
+    // ===================== TMA producers (both CTAs of a pair) =====================
+    // warp 0 streams the activation (A) boxes, warp 10 the weight (B) boxes: two independent
+    // single-thread issue loops (one loop issuing both was the limiter: it was never blocked on a
+    // free stage, i.e. it could not issue fast enough to stay ahead of the tensor core)
     if (lane == 0) {
+      const bool is_a = warp == 0;
+      const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) *
+                             (kPair ? 2u : 1u);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        const int n_tile = unit % p.n_tiles_n;
+        const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
         const int n0 = (m_tile / p.tiles_y) * p.BN_img;
-        const int y0 = (m_tile % p.tiles_y) * p.BH;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
-          const int ky = tap / p.KS, kx = tap - ky * p.KS;
-          const int off = p.pad;
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), stage_tx);
-          const uint32_t sa = base + stage * TC_STAGE_BYTES;
-          const uint32_t sb = sa + TC_A_BYTES;
-          if (cc < p.kchunks1)
-            tma_load_4d(sa, &tmA1, full_bar(stage), cc * TC_BLOCK_K, kx - off,
-                        y0 * p.stride + ky - off, n0);
-          else
-            tma_load_4d(sa, &tmA2, full_bar(stage), (cc - p.kchunks1) * TC_BLOCK_K, kx - off,
-                        y0 * p.stride + ky - off, n0);
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * TC_BLOCK_K, n_tile * p.block_n);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        const int y0 = (m_tile % p.tiles_y) * p.BH * p.stride - p.pad;
+        const int bn0 = n_tile * p.block_n + (kPair ? (int)rank * b_rows : 0);
+        int kb = 0;
+        for (int ky = 0; ky < p.KS; ++ky) {
+          for (int kx = 0; kx < p.KS; ++kx) {
+            for (int cc = 0; cc < p.kchunks; ++cc, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t sa = base + stage * Cfg::kStageBytes;
+              if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
+              if (is_a) {
+                const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
+                const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+                if (kPair) tma_load_4d_pair(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+                else tma_load_4d(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+              } else {
+                if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128 (256 for a pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+                             ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        if (kPair) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+        else mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * TC_STAGE_BYTES;
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+            if (kPair)
+              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));   // frees the smem stage when these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (kPair) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));       // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs)
+        if (kPair) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
     const int half = (warp - 2) >> 2;    // this warp takes the 32-column chunks with index % 2 == half
+    const uint32_t leader_tempty0 = kPair ? mapa_rank(tempty_bar(0), 0) : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n, m_tile = tile / p.n_tiles_n;
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int n_tile = unit % p.n_tiles_n;
+      const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
@@ -310,17 +435,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (kPair) mbar_arrive_remote(leader_tempty0 + 8u * (uint32_t)acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                 ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                   ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                   ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -402,6 +534,19 @@ int prepare_conv_tc(psld_op& op) {
   const int BN_img = 128 / (OW * BH);
   if (BN_img > 256) return unsupported("image too small");
 
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  // 2-CTA pairs whenever there are at least two M tiles (PSLD_TC_PAIR=0 forces the 1-CTA kernel)
+  const int64_t m_tiles_all = (int64_t)((N + BN_img - 1) / BN_img) * (OH / BH);
+  static const int pair_env = [] {
+    const char* e = getenv("PSLD_TC_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  const bool pair = pair_env != 0 && m_tiles_all >= 2 && sms >= 2;
   ConvTcState* st = new (std::nothrow) ConvTcState();
   if (!st) { set_error("conv_tc: out of host memory"); return PSLD_ECUDA; }
   int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
@@ -409,7 +554,7 @@ int prepare_conv_tc(psld_op& op) {
     rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, OW, BH, BN_img, stride)
                 : encode_act_map(&st->a2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   const int K = KS * KS * (C1 + C2);
-  if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, block_n);
+  if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, pair ? block_n / 2 : block_n);
   if (rc != PSLD_OK) { delete st; return rc; }
 
   ConvTcParams& p = st->p;
@@ -436,18 +581,23 @@ int prepare_conv_tc(psld_op& op) {
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * OH * OW;
   const int64_t m_tiles = (int64_t)((N + BN_img - 1) / BN_img) * p.tiles_y;
-  p.num_tiles = (int)(m_tiles * p.n_tiles_n);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    cudaGetLastError();
-    sms = 148;
+  const int64_t m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
+  p.num_tiles = (int)(m_units * p.n_tiles_n);          // work units (tiles, or tile pairs)
+  st->pair = pair;
+  if (pair) {
+    const int pairs = sms / 2;
+    st->grid = 2 * (p.num_tiles < pairs ? p.num_tiles : pairs);
+  } else {
+    st->grid = p.num_tiles < sms ? p.num_tiles : sms;
   }
-  st->grid = p.num_tiles < sms ? p.num_tiles : sms;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<false>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               TcCfg<true>::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -470,7 +620,24 @@ int release_conv_tc(psld_op& op) {
 int run_conv_tc(const psld_op& op, cudaStream_t s) {
   const ConvTcState* st = (const ConvTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_tc: op not prepared (call psld_op_prepare)");
-  conv_tc_kernel<<<st->grid, TC_THREADS, TC_SMEM_BYTES, s>>>(st->a1, st->a2, st->b, st->p);
+  if (st->pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)st->grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<true>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, st->a1, st->a2, st->b, st->p));
+  } else {
+    conv_tc_kernel<false><<<st->grid, TC_THREADS, TcCfg<false>::kSmemBytes, s>>>(st->a1, st->a2,
+                                                                                 st->b, st->p);
+  }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
