@@ -248,6 +248,7 @@ def main_b200(args):
 
     # ---- per-kernel roofline from CUDA-event timing of every op
     prof = profile_plan(plan, iters=max(1, args.profile_ops)) if args.profile_ops > 0 else {}
+    conv_classes = prof.pop("_conv_classes", {})
     roof = None
     if "conv_tc" in prof:
         c = prof["conv_tc"]
@@ -319,6 +320,8 @@ def main_b200(args):
             "tensor_frac_of_step": (FLOP_PER_SAMPLE_NFE * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
             "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
             "engines": plan.engine_count, "finite": finite,
+            "conv_classes": {k: {"n": v["n"], "ms": round(v["ms"], 4), "tflops": round(v["tflops"], 1)}
+                             for k, v in sorted(conv_classes.items(), key=lambda kv: -kv[1]["ms"])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -90,7 +90,8 @@ struct TcCfg {
   static constexpr int kStages = kPair ? 6 : TC_STAGES;
   static constexpr int kBBytes = kPair ? TC_B_BYTES / 2 : TC_B_BYTES;
   static constexpr int kStageBytes = TC_A_BYTES + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStagingBytes = 8 * 4096;   // epilogue transpose buffers, 4 KB per warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -175,7 +176,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + kStages * Cfg::kStageBytes;
+  const uint32_t stg_base = base + kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -321,6 +323,129 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
       const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
       const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
+      if (p.y != nullptr && (p.block_n & 63) == 0) {
+        // ---- staged path: 64-column groups go through a per-warp 32 x 128 B shared-memory tile
+        // (16-byte chunks XOR-swizzled by row) so that BOTH the residual loads and the output
+        // stores hit global memory as full 128-byte lines (4 rows per instruction) instead of 32
+        // scattered 16-byte pieces; thread <-> TMEM row only touches its own row of the tile.
+        const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+        const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
+        const int sub_row = lane >> 3, chunk = lane & 7;
+        const int ncg = p.block_n >> 6;
+        const uint32_t my_row = stg + (uint32_t)lane * 128u;
+        uint4 rq[8];
+        auto load_res = [&](int cg) {
+          const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t mr = m_base + 4 * it + sub_row;
+            if (mr < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + mr * p.Cout);
+          }
+        };
+        if (p.res && half < ncg) load_res(half);
+        for (int cg = half; cg < ncg; cg += 2) {
+          const int co_base = n_tile * p.block_n + cg * 64;
+          if (p.res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = 4 * it + sub_row;
+              const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(a), "r"(rq[it].x), "r"(rq[it].y), "r"(rq[it].z), "r"(rq[it].w) : "memory");
+            }
+            __syncwarp();
+            if (cg + 2 < ncg) load_res(cg + 2);
+          }
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                   (uint32_t)acc * 256u + (uint32_t)(cg * 64 + sub * 32);
+            tmem_ld32(taddr, r);
+            tmem_ld_wait();
+            const int co0 = co_base + sub * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+            if (valid) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+              if (temb) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(temb + co0 + j));
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t a = my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4);
+              if (p.res) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
+                const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+                  if (valid) { v[q * 8 + 2 * t] += f.x; v[q * 8 + 2 * t + 1] += f.y; }
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[q * 8 + 2 * t] *= p.scale;
+                v[q * 8 + 2 * t + 1] *= p.scale;
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+                o[t] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+            if (stats) {
+              float a[16];
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
+                a[2 * g] = (x0 + x1) + (x2 + x3);
+                a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+              }
+#pragma unroll
+              for (int w = 8; w >= 1; w >>= 1) {
+                const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                  const float send = hi ? a[j] : a[j + w];
+                  const float keep = hi ? a[j + w] : a[j];
+                  a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                }
+              }
+              a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+              if ((lane & 1) == 0)
+                p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1)] = a[0];
+            }
+          }
+          __syncwarp();
+          __nv_bfloat16* yp = p.y + co_base + chunk * 8;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = 4 * it + sub_row;
+            const int64_t mr = m_base + row;
+            const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+            if (mr < p.M) *reinterpret_cast<uint4*>(yp + mr * p.Cout) = q;
+          }
+          __syncwarp();
+        }
+      } else {
       const bool has_res = valid && p.res != nullptr;
       uint4 rq[4];                                       // residual of the chunk being processed
       if (has_res && half * 32 < p.block_n) {
@@ -433,6 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
       }
+      }  // legacy (non-staged) path
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

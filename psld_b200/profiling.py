@@ -66,8 +66,17 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
                 acc[k] += evs[k].elapsed_time(evs[k + 1])
     out = {}
     elt = 2 if plan.bf16 else 4
+    classes = {}
     for k in range(n):
         op = plan.op_array[k]
+        if op.kind == L.OP_CONV:
+            i = op.i
+            key = f"{op_name(op)} {i[L.CONV_OH]}x{i[L.CONV_OW]} {i[L.CONV_C1] + i[L.CONV_C2]}->" \
+                  f"{i[L.CONV_COUT]} k{i[L.CONV_KS]}s{i[L.CONV_STRIDE]}"
+            c = classes.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
+            c["ms"] += acc[k] / iters
+            c["n"] += 1
+            c["flops"] += op_flops(op)
         d = out.setdefault(op_name(op), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += acc[k] / iters
         d["n"] += 1
@@ -75,4 +84,7 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
         d["bytes"] += op_bytes(op, elt)
     for d in out.values():
         d["launch_ms"] = d["ms"] / max(d["n"], 1)
+    for c in classes.values():
+        c["tflops"] = c["flops"] / (c["ms"] * 1e-3) / 1e12 if c["ms"] > 0 else 0.0
+    out["_conv_classes"] = classes
     return out

@@ -19,5 +19,7 @@ print('ms/step', d['ms_per_step'], 'samples/s', d['value'], 'finite', d['finite'
 print('per_kernel_ms', d['per_kernel_ms'])
 print('roofline', d['roofline'] and {k: d['roofline'][k] for k in ('achieved','frac','share_of_step')})
 print('update', d['roofline_update'].get('frac'), d['roofline_update'].get('large'))
+print('clocks', d['clocks'])
+for k, v in d.get('conv_classes', {}).items(): print('  ', k, v)
 "
 fi
