@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--profile-ops", type=int, default=2, help="per-op event timing iterations")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -77,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -210,11 +212,18 @@ def main_b200(args):
     state = sde.prior_sampling_device((B, 3, 32, 32), seed=1 + rank, device=dev).to(state_dtype)
     plan.x_in.copy_(state)
 
+    side = torch.cuda.Stream(dev)          # CUDA-graph capture needs a non-default stream
+
     def run_steps(first, count):
         tabs = StepTables(sde, ts[first:first + count + 1], count, "sscs_sde", False, 1e-3,
                           merge_noise=True)
         table = tabs.time_table.to(dev)
+        raw = torch.frombuffer(bytearray(C.string_at(C.addressof(tabs.sscs), C.sizeof(tabs.sscs))),
+                               dtype=torch.uint8).to(dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
         d = L.SamplerDesc()
+        if args.graph:
+            d.sscs_dev, d.step_counter = raw.data_ptr(), counter.data_ptr()
         d.sampler, d.n_steps, d.denoise = 0, count, 0
         d.state_dtype = L.dtype_code(state_dtype)
         d.fuse_halves, d.temb_op = 2, plan.temb_op     # one fused pass, one merged draw per step
@@ -222,19 +231,23 @@ def main_b200(args):
         d.state, d.net_in, d.eps = state.data_ptr(), plan.x_in.data_ptr(), plan.eps.data_ptr()
         d.time_table = table.data_ptr()
         d.sscs = C.cast(tabs.sscs, C.POINTER(L.SscsCoeffs))
-        L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d), stream), "sampler_run")
-        return table, tabs
+        L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d),
+                                     C.c_void_p(side.cuda_stream)), "sampler_run")
+        return table, tabs, raw, counter
 
-    keep = run_steps(0, max(args.warmup, 3))
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(side):
+        keep = run_steps(0, max(args.warmup, 3))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
-    e0.record()
-    keep2 = run_steps(args.warmup, args.steps)
-    e1.record()
+    with torch.cuda.stream(side):
+        e0.record()                     # events on the stream the kernels are launched on
+        keep2 = run_steps(args.warmup, args.steps)
+        e1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -243,7 +256,7 @@ def main_b200(args):
     ms_per_step = ms_total / args.steps
     value = B * world / (NFE * ms_per_step * 1e-3)
     # first-half-step launch + per step (program + fused update)
-    launches = 1 + args.steps * (plan.launches + 1)
+    launches = 1 + args.steps * (plan.launches + 1 + (1 if args.graph else 0))
     finite = bool(torch.isfinite(state).all().item())
 
     # ---- per-kernel roofline from CUDA-event timing of every op
@@ -253,9 +266,17 @@ def main_b200(args):
     if "conv_tc" in prof:
         c = prof["conv_tc"]
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        traffic, tsrc = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp) and B == 256:
+            tj = json.load(open(tp))
+            traffic = tj["kernels"].get("conv_tc_kernel", {}).get("traffic_bytes_per_launch")
+            tsrc = tj["source"]
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, bf16)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + ", sustained",
+                "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                "traffic_source": tsrc, "algorithmic_flop_per_launch": c["flops"] / c["n"],
+                "peak_source": pk["src"] + ", sustained",
                 "launches_per_step": c["n"], "avg_launch_ms": c["launch_ms"],
                 "share_of_step": c["ms"] / sum(v["ms"] for v in prof.values())}
     elif "conv_simt" in prof:
@@ -312,6 +333,7 @@ def main_b200(args):
                 "batch_per_gpu": B, "batch_total": B * world, "nfe_per_sample": NFE,
                 "state_dtype": args.state, "noise": "in-kernel Philox4x32-10",
                 "step": "one SSCS predictor step = 1 score_fn call + 1 fused update",
+                "cuda_graph": bool(args.graph),
                 "l2": "activations per step (GBs at B=256) exceed the 126 MB L2; no flush needed",
                 "parallelism": f"batch-sharded x{world}, no per-step communication",
             },

@@ -176,6 +176,8 @@ enum { PSLD_LAYOUT_N = 0, PSLD_LAYOUT_C, PSLD_LAYOUT_HW, PSLD_LAYOUT_DIR, PSLD_L
  *   in[6],in[7] = concatenated Dense_0 W [totalC, 4nf], b [totalC]
  *   out[0] = proj [nt, totalC] f32 (Dense_0(SiLU(temb)) of every resblock)
  *   out[1] = scratch f32 [nt, E + 8nf]
+ *   out[2] = optional device int32 step counter: the time row used is in[0][*out[2] + r]
+ *            (lets a captured CUDA graph of one sampler step be replayed for every step)
  *   i: NT, NF, EMB (0 fourier, 1 positional), TOTALC, LOGGED                           */
 enum { PSLD_TEMB_NT = 0, PSLD_TEMB_NF, PSLD_TEMB_EMB, PSLD_TEMB_TOTALC, PSLD_TEMB_LOGGED };
 
@@ -262,6 +264,13 @@ typedef struct {
   const psld_score_step* em;    /* host [n_steps]  (sampler 1)                          */
   const psld_score_step* den;   /* host, denoise step coefficients                      */
   void* record;         /* optional: state after every step [n_steps, B,2C,H,W] or NULL */
+  /* CUDA-graph replay (optional; all three non-NULL enables it, Philox noise only, no record):
+   * ONE predictor step (program + fused update + counter increment) is stream-captured and the
+   * instantiated graph is launched n_steps times; per-step scalars are read on the device from
+   * these tables at row *step_counter.  `stream` must not be the legacy default stream.        */
+  const psld_sscs_coeffs* sscs_dev; /* device copy of sscs[n_steps]                            */
+  const psld_score_step* em_dev;    /* device copy of em[n_steps]                              */
+  int32_t* step_counter;            /* device int32, zeroed by the caller                      */
 } psld_sampler_desc;
 
 PSLD_API int psld_sampler_run(const psld_op* ops, int n_ops, const psld_sampler_desc* d,

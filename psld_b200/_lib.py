@@ -66,7 +66,8 @@ class SamplerDesc(C.Structure):
                 ("state", C.c_void_p), ("net_in", C.c_void_p), ("eps", C.c_void_p),
                 ("time_table", C.c_void_p), ("noise", C.c_void_p),
                 ("sscs", C.POINTER(SscsCoeffs)), ("em", C.POINTER(ScoreStep)),
-                ("den", C.POINTER(ScoreStep)), ("record", C.c_void_p)]
+                ("den", C.POINTER(ScoreStep)), ("record", C.c_void_p),
+                ("sscs_dev", C.c_void_p), ("em_dev", C.c_void_p), ("step_counter", C.c_void_p)]
 
 
 EXPORTS = {

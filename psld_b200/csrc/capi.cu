@@ -111,12 +111,13 @@ extern "C" int psld_program_launches(const psld_op* ops, int n_ops) {
 }
 
 static int run_net(const psld_op* ops, int n_ops, int temb_op, const float* time_ptr,
-                   cudaStream_t s) {
+                   cudaStream_t s, int* step_counter = nullptr) {
   for (int i = 0; i < n_ops; ++i) {
     int rc;
     if (i == temb_op) {
       psld_op t = ops[i];
       t.in[0] = time_ptr;      // this call's (log) time, identical for the whole batch
+      t.out[2] = step_counter; // graph replay: row index read on the device
       rc = dispatch(t, s);
     } else {
       rc = dispatch(ops[i], s);
@@ -145,7 +146,62 @@ extern "C" int psld_sampler_run(const psld_op* ops, int n_ops, const psld_sample
   const int n = d->n_steps;
   int rc = PSLD_OK;
 
-  if (d->sampler == 0) {
+  const bool graph = d->step_counter != nullptr && d->noise == nullptr && d->record == nullptr &&
+                     n > 1 && (d->sampler == 0 ? d->sscs_dev != nullptr : d->em_dev != nullptr);
+  if (graph) {
+    // -------- CUDA-graph replay: capture ONE predictor step, launch it for every step.
+    PSLD_CHECK_ARG(s != nullptr, "psld_sampler_run: graph replay needs a non-default stream");
+    const int fuse = d->sampler == 0 ? d->fuse_halves : 0;
+    if (d->sampler == 0 && fuse && n > 0) {
+      rc = psld_sscs_update(d->state, d->state, d->state_dtype, d->net_in, nullptr, nullptr, nullptr,
+                            nullptr, &d->sscs[0], PSLD_STAGE_HALF_A, d->seed, 0, d->B, d->chw, s);
+      if (rc) return rc;
+    }
+    // with fuse_halves == 1 the last step has no HALF_C stage: it runs outside the graph
+    const int n_graph = (d->sampler == 0 && fuse == 1) ? n - 1 : n;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    PSLD_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = PSLD_OK;
+    if (d->sampler == 0) {
+      if (!fuse)
+        rc = launch_sscs_table(d->state, d->state_dtype, d->net_in, nullptr, d->sscs_dev,
+                               d->step_counter, PSLD_STAGE_HALF_A, d->seed, d->B, d->chw, s);
+      if (!rc) rc = run_net(ops, n_ops, d->temb_op, d->time_table, s, d->step_counter);
+      int stages = PSLD_STAGE_SCORE | PSLD_STAGE_HALF_B;
+      if (fuse == 1) stages |= PSLD_STAGE_HALF_C;
+      if (!rc)
+        rc = launch_sscs_table(d->state, d->state_dtype, d->net_in, d->eps, d->sscs_dev,
+                               d->step_counter, stages, d->seed, d->B, d->chw, s);
+    } else {
+      rc = run_net(ops, n_ops, d->temb_op, d->time_table, s, d->step_counter);
+      if (!rc)
+        rc = launch_em_table(d->state, d->state_dtype, d->net_in, d->eps, d->em_dev,
+                             d->step_counter, d->seed, d->B, d->chw, s);
+    }
+    if (!rc) rc = launch_step_inc(d->step_counter, s);
+    cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); return PSLD_ECUDA; }
+    ce = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return PSLD_ECUDA; }
+    for (int i = 0; i < n_graph && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(ge, s);
+    if (ce == cudaSuccess && n_graph < n) {
+      const int i = n - 1;
+      rc = run_net(ops, n_ops, d->temb_op, d->time_table + i, s);
+      if (!rc)
+        rc = psld_sscs_update(d->state, d->state, d->state_dtype, d->net_in, d->eps, nullptr, nullptr,
+                              nullptr, &d->sscs[i], PSLD_STAGE_SCORE | PSLD_STAGE_HALF_B, d->seed, i,
+                              d->B, d->chw, s);
+    }
+    // the executable graph must outlive its launches: drain the stream before destroying it
+    cudaError_t se = cudaStreamSynchronize(s);
+    cudaGraphExecDestroy(ge);
+    if (ce != cudaSuccess) { set_error("cudaGraphLaunch: %s", cudaGetErrorString(ce)); return PSLD_ECUDA; }
+    if (se != cudaSuccess) { set_error("graph replay failed: %s", cudaGetErrorString(se)); return PSLD_ECUDA; }
+    if (rc) return rc;
+  } else if (d->sampler == 0) {
     // -------- SSCS: half step -> score step -> half step (sde.py:331-336)
     if (d->fuse_halves && n > 0) {
       rc = psld_sscs_update(d->state, d->state, d->state_dtype, d->net_in, nullptr, z(0), nullptr,

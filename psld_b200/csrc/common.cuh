@@ -102,4 +102,12 @@ int prepare_attn_tc(psld_op& op);
 int release_attn_tc(psld_op& op);
 int run_attn_tc(const psld_op& op, cudaStream_t s);
 
+int launch_step_inc(int* step_ptr, cudaStream_t s);
+int launch_sscs_table(void* u, int state_dtype, float* net_in, const float* eps,
+                      const psld_sscs_coeffs* table, const int* step_ptr, int stages, uint64_t seed,
+                      int64_t B, int64_t chw, cudaStream_t s);
+int launch_em_table(void* u, int state_dtype, float* net_in, const float* eps,
+                    const psld_score_step* table, const int* step_ptr, uint64_t seed, int64_t B,
+                    int64_t chw, cudaStream_t s);
+
 }  // namespace psld

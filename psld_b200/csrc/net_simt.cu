@@ -85,7 +85,8 @@ int run_layout(const psld_op& op, cudaStream_t s) {
 // multiplication order is kept: re-associating moves the embedding by 1e-4)
 __global__ void temb_embed_kernel(const float* __restrict__ t, const float* __restrict__ W,
                                   float* __restrict__ emb, int nt, int nf, int emb_type,
-                                  int logged) {
+                                  int logged, const int* __restrict__ step_ptr) {
+  if (step_ptr) t += *step_ptr;      // graph replay: t is a per-call table, the step lives on device
   const int E = emb_type == 0 ? 2 * nf : nf;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nt * E) return;
@@ -140,7 +141,7 @@ int run_temb(const psld_op& op, cudaStream_t s) {
   float* h0 = emb + (int64_t)nt * E;
   float* h1 = h0 + (int64_t)nt * D;
   temb_embed_kernel<<<(int)ceil_div((int64_t)nt * E, 128), 128, 0, s>>>(
-      (const float*)op.in[0], (const float*)op.in[1], emb, nt, nf, et, logged);
+      (const float*)op.in[0], (const float*)op.in[1], emb, nt, nf, et, logged, (const int*)op.out[2]);
   PSLD_CHECK_LAUNCH();
   linear_rows_kernel<false><<<(int)ceil_div((int64_t)nt * D * 32, 256), 256, 0, s>>>(
       emb, (const float*)op.in[2], (const float*)op.in[3], h0, nt, E, D);

@@ -15,6 +15,8 @@
 // Memory-bound: 4 pairs per thread, 128-bit loads/stores, grid sized to cover the data
 // (one wave is >> 148 SMs at the BASELINE batch sizes).
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace psld {
@@ -143,6 +145,8 @@ __device__ __forceinline__ void get_noise(const float* z, uint64_t seed, uint64_
 
 struct SscsParams {
   psld_sscs_coeffs c;
+  const psld_sscs_coeffs* table;   // optional device table indexed by *step_ptr (CUDA-graph replay)
+  const int* step_ptr;
   const float* eps;
   const float* z_a;
   const float* z_b;
@@ -154,8 +158,8 @@ struct SscsParams {
 };
 
 template <typename S>
-__global__ void __launch_bounds__(256)
-sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams p) {
+__device__ __forceinline__ void sscs_update_body(S* __restrict__ u_out, const S* __restrict__ u_in,
+                                                 const SscsParams& p) {
   const int64_t nvec = p.B * (p.chw >> 2);
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (int64_t)gridDim.x * blockDim.x) {
@@ -202,8 +206,36 @@ sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const Sscs
   }
 }
 
+
+// coefficients as a by-value kernel parameter (constant bank)
+template <typename S>
+__global__ void __launch_bounds__(256)
+sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams p) {
+  sscs_update_body<S>(u_out, u_in, p);
+}
+
+// CUDA-graph replay: coefficients = row *step_ptr of a device table, staged in shared memory
+template <typename S>
+__global__ void __launch_bounds__(256)
+sscs_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams pp) {
+  __shared__ SscsParams p;
+  const int step = *pp.step_ptr;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.table + step);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&p.c);
+  for (int i = threadIdx.x; i < (int)(sizeof(psld_sscs_coeffs) / 4); i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x == 0) {
+    p.eps = pp.eps; p.z_a = pp.z_a; p.z_b = pp.z_b; p.z_c = pp.z_c; p.net_in = pp.net_in;
+    p.seed = pp.seed; p.step = (uint64_t)step;
+    p.B = pp.B; p.chw = pp.chw; p.stages = pp.stages;
+  }
+  __syncthreads();
+  sscs_update_body<S>(u_out, u_in, p);
+}
+
 struct EmParams {
   psld_score_step c;
+  const psld_score_step* table;
+  const int* step_ptr;
   const float* eps;
   const float* z;
   float* net_in;
@@ -213,8 +245,8 @@ struct EmParams {
 };
 
 template <typename S>
-__global__ void __launch_bounds__(256)
-em_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams p) {
+__device__ __forceinline__ void em_update_body(S* __restrict__ u_out, const S* __restrict__ u_in,
+                                               const EmParams& p) {
   const int64_t nvec = p.B * (p.chw >> 2);
   const S hb = (S)p.c.half_beta, mi = (S)p.c.m_inv, ga = (S)p.c.gamma, nu = (S)p.c.nu;
   const S g2x = (S)p.c.g2_x, g2m = (S)p.c.g2_m, dt = (S)p.c.dt;
@@ -259,6 +291,29 @@ em_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmPara
   }
 }
 
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+em_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams p) {
+  em_update_body<S>(u_out, u_in, p);
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+em_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams pp) {
+  __shared__ EmParams p;
+  const int step = *pp.step_ptr;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.table + step);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&p.c);
+  for (int i = threadIdx.x; i < (int)(sizeof(psld_score_step) / 4); i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x == 0) {
+    p.eps = pp.eps; p.z = pp.z; p.net_in = pp.net_in; p.seed = pp.seed; p.step = (uint64_t)step;
+    p.B = pp.B; p.chw = pp.chw; p.use_philox = pp.use_philox;
+  }
+  __syncthreads();
+  em_update_body<S>(u_out, u_in, p);
+}
+
 __global__ void __launch_bounds__(256)
 prior_kernel(float* __restrict__ u, float m_std, uint64_t seed, int64_t B, int64_t chw) {
   const int64_t nvec = B * (chw >> 2);
@@ -286,6 +341,49 @@ static inline int grid_for(int64_t nvec) {
 
 using namespace psld;
 
+namespace psld {
+__global__ void step_inc_kernel(int* p) { *p += 1; }
+
+int launch_step_inc(int* step_ptr, cudaStream_t s) {
+  step_inc_kernel<<<1, 1, 0, s>>>(step_ptr);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+// graph-replay variants: coefficients come from row *step_ptr of a device table
+int launch_sscs_table(void* u, int state_dtype, float* net_in, const float* eps,
+                      const psld_sscs_coeffs* table, const int* step_ptr, int stages, uint64_t seed,
+                      int64_t B, int64_t chw, cudaStream_t s) {
+  SscsParams p;
+  memset(&p, 0, sizeof(p));
+  p.table = table; p.step_ptr = step_ptr;
+  p.eps = eps; p.net_in = net_in; p.seed = seed; p.B = B; p.chw = chw; p.stages = stages;
+  const int grid = grid_for(B * (chw / 4));
+  if (state_dtype == PSLD_F64)
+    sscs_update_table_kernel<double><<<grid, 256, 0, s>>>((double*)u, (const double*)u, p);
+  else
+    sscs_update_table_kernel<float><<<grid, 256, 0, s>>>((float*)u, (const float*)u, p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+int launch_em_table(void* u, int state_dtype, float* net_in, const float* eps,
+                    const psld_score_step* table, const int* step_ptr, uint64_t seed, int64_t B,
+                    int64_t chw, cudaStream_t s) {
+  EmParams p;
+  memset(&p, 0, sizeof(p));
+  p.table = table; p.step_ptr = step_ptr;
+  p.eps = eps; p.net_in = net_in; p.seed = seed; p.B = B; p.chw = chw; p.use_philox = 1;
+  const int grid = grid_for(B * (chw / 4));
+  if (state_dtype == PSLD_F64)
+    em_update_table_kernel<double><<<grid, 256, 0, s>>>((double*)u, (const double*)u, p);
+  else
+    em_update_table_kernel<float><<<grid, 256, 0, s>>>((float*)u, (const float*)u, p);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+}  // namespace psld
+
 extern "C" int psld_sscs_update(void* u_out, const void* u_in, int state_dtype, float* net_in,
                                 const float* eps, const float* z_a, const float* z_b,
                                 const float* z_c, const psld_sscs_coeffs* coeffs, int stages,
@@ -299,6 +397,7 @@ extern "C" int psld_sscs_update(void* u_out, const void* u_in, int state_dtype, 
                  "psld_sscs_update: state dtype must be f64 or f32");
   SscsParams p;
   p.c = *coeffs;
+  p.table = nullptr; p.step_ptr = nullptr;
   p.eps = eps; p.z_a = z_a; p.z_b = z_b; p.z_c = z_c; p.net_in = net_in;
   p.seed = seed; p.step = step; p.B = B; p.chw = chw; p.stages = stages;
   const int grid = grid_for(B * (chw / 4));
@@ -321,6 +420,7 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
                  "psld_em_update: state dtype must be f64 or f32");
   EmParams p;
   p.c = *coeffs;
+  p.table = nullptr; p.step_ptr = nullptr;
   p.eps = eps; p.z = z; p.net_in = net_in; p.seed = seed; p.step = step;
   p.B = B; p.chw = chw; p.use_philox = use_philox;
   const int grid = grid_for(B * (chw / 4));

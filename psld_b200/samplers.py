@@ -79,6 +79,7 @@ class _FusedSampler(Sampler):
         self.state_dtype = torch.float64 if sd in ("float64", "f64", "fp64") else torch.float32
         self.fuse_halves = bool(_opt(config, "fuse_halves", True))
         self.merge_noise = bool(_opt(config, "merge_noise", True))   # Philox mode only
+        self.use_graph = bool(_opt(config, "cuda_graph", True))       # replay one captured step
         self.seed = int(getattr(config.evaluation, "seed", 0)) + int(os.environ.get("RANK", "0"))
         self.noise = None          # optional pre-drawn noise bank (parity mode)
         self.record = None         # optional [n, B,2C,H,W] buffer filled with per-step states
@@ -158,9 +159,31 @@ class _FusedSampler(Sampler):
         if tabs.den is not None:
             d.den = C.pointer(tabs.den)
         d.record = record.data_ptr() if record is not None else None
-        L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d), stream),
-                "psld_sampler_run")
-        self._keep = (table, noise, tabs, plan)       # keep alive until the stream drains
+        extra = None
+        if self.use_graph and noise is None and record is None and n > 1:
+            # CUDA-graph replay of one predictor step: per-step scalars live in device tables
+            # indexed by a device-side step counter; needs a capturable (non-default) stream
+            tab = tabs.sscs if tabs.sscs is not None else tabs.em
+            raw = torch.frombuffer(bytearray(C.string_at(C.addressof(tab), C.sizeof(tab))),
+                                   dtype=torch.uint8).to(dev)
+            counter = torch.zeros(1, dtype=torch.int32, device=dev)
+            if tabs.sscs is not None:
+                d.sscs_dev = raw.data_ptr()
+            else:
+                d.em_dev = raw.data_ptr()
+            d.step_counter = counter.data_ptr()
+            extra = (raw, counter)
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d),
+                                             C.c_void_p(side.cuda_stream)), "psld_sampler_run")
+            cur.wait_stream(side)
+        else:
+            L.check(lib.psld_sampler_run(plan.op_array, plan.n_ops, C.byref(d), stream),
+                    "psld_sampler_run")
+        self._keep = (table, noise, tabs, plan, extra)   # keep alive until the stream drains
 
     # ------------------------------------------------------------------ generic score_fn
     def _run_generic(self, lib, state, tabs, n, denoise, B, chw, noise, record, sdt, stream, dev,

@@ -38,9 +38,11 @@ def _golden_cfg(tag):
     return cfg
 
 
-def _run(cfg, score_fn, u0, nb, state_dtype=torch.float64, fuse=False, record=True, merge=False):
+def _run(cfg, score_fn, u0, nb, state_dtype=torch.float64, fuse=False, record=True, merge=False,
+         graph=False):
     kind = cfg.evaluation.sampler.name
     S = SAMPLERS[kind](cfg, PSLD(cfg), score_fn)
+    S.use_graph = graph
     S.state_dtype = state_dtype
     S.fuse_halves = fuse
     S.merge_noise = merge
@@ -168,3 +170,17 @@ def test_merged_noise_is_exact_in_law():
     n = B * 3 * 64 * 64
     for a, b in zip(outs[False], outs[True]):
         assert abs(a - b) <= 6 * max(abs(a), 1e-3) / np.sqrt(n) * 2 + 1e-6, (outs)
+
+
+@pytest.mark.parametrize("kind", ["sscs_sde", "em_sde"])
+@pytest.mark.parametrize("fuse,merge", [(False, False), (True, False), (True, True)])
+def test_cuda_graph_replay_equals_host_loop(kind, fuse, merge):
+    """One captured predictor step replayed n times (device-side step counter + coefficient table)
+    gives bit-identical states to launching every kernel from the host."""
+    cfg = tiny_config(sampler=kind, n_discrete_steps=9)
+    net, _ = make_net(cfg, "bf16")
+    u0, _ = sampler_inputs(cfg, 3, 8, kind)
+    for sd in (torch.float32, torch.float64):
+        a, _, _ = _run(cfg, net, u0, None, state_dtype=sd, fuse=fuse, record=False, merge=merge, graph=False)
+        b, _, _ = _run(cfg, net, u0, None, state_dtype=sd, fuse=fuse, record=False, merge=merge, graph=True)
+        assert torch.isfinite(a).all() and torch.equal(a, b)
