@@ -673,6 +673,17 @@ int prepare_conv_tc(psld_op& op) {
     return e ? atoi(e) : 1;
   }();
   const bool pair = pair_env != 0 && m_tiles_all >= 2 && sms >= 2;
+  // N tile = the widest that divides Cout.  (Measured: narrowing to N=128 to fix the wave
+  // quantisation of the 16x16 layers - 7 half rounds instead of 4 - is a net loss, 2.0 -> 2.8 ms:
+  // k-blocks then retire every 256 cycles and the TMA issue loops cannot keep up.)
+  // PSLD_TC_BLOCK_N overrides for experiments.
+  {
+    static const int bn_env = [] {
+      const char* e = getenv("PSLD_TC_BLOCK_N");
+      return e ? atoi(e) : 0;
+    }();
+    if (bn_env > 0 && bn_env <= block_n && Cout % bn_env == 0 && bn_env % 32 == 0) block_n = bn_env;
+  }
   ConvTcState* st = new (std::nothrow) ConvTcState();
   if (!st) { set_error("conv_tc: out of host memory"); return PSLD_ECUDA; }
   int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
