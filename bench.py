@@ -30,9 +30,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NFE = 1000
-FLOP_PER_SAMPLE_NFE = 76.43e9          # BASELINE.md §2 (CIFAR-10 NCSN++), 2*MAC
 METRIC = "PSLD CIFAR-10 samples/sec (SSCS sampler)"
 UNIT = "samples/sec"
+
+
+WORKLOADS = {
+    # name: (config factory, GFLOP/sample/NFE from BASELINE.md §2, default per-GPU batch, description)
+    "cifar10": ("cifar10_config", 76.43e9, 256,
+                "PSLD CIFAR-10 NCSN++ (nf=128, ch_mult=[2,2,2], 8 res blocks, attn@16, fir, fourier), "
+                "SSCS sampler, 1000 NFE, random-init weights (BASELINE configs[1])"),
+    "celeba64": ("celeba64_config", 84.06e9, 64,
+                 "PSLD CelebA-64 NCSN++ (nf=128, ch_mult=[1,2,2,2], 4 res blocks, attn@16, fir, fourier), "
+                 "SSCS sampler, 1000 NFE, random-init weights (BASELINE configs[3])"),
+}
 
 
 def parse():
@@ -41,7 +51,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = workload default")
+    ap.add_argument("--workload", default="cifar10", choices=["cifar10", "celeba64"],
+                    help="cifar10 = BASELINE configs[1] (headline); celeba64 = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--state", default="float32", choices=["float32", "float64"])
     ap.add_argument("--e2e-nfe", type=int, default=NFE, help="0 disables the end-to-end run")
@@ -146,7 +158,7 @@ def run_cpu_port(cfg, batch, steps, warmup, threads=None):
     dt = go(steps)
     per_step = dt / steps
     return {"value": batch / (NFE * per_step), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle port of SSCSSampler.sample, CIFAR-10 NCSN++ fp32, batch {batch}, "
+            "sample": f"oracle port of SSCSSampler.sample, {cfg.data.image_size}x{cfg.data.image_size} NCSN++ fp32, batch {batch}, "
                       f"{steps} of {NFE} NFE timed after {warmup} warm-up, extrapolated linearly",
             "ms_per_step": per_step * 1e3, "sample_nfe_per_sec": batch / per_step}
 
@@ -155,21 +167,21 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from psld_b200 import cifar10_config
-    cfg = cifar10_config()
+    import psld_b200
+    cfg_name, _, _, workload_desc = WORKLOADS[args.workload]
+    cfg = getattr(psld_b200, cfg_name)()
     batch = args.cpu_batch
     # bound the run: (steps+warmup) CPU steps of ~0.17 s/sample each must end within minutes
     per_sample_est = 0.2
     while batch > 1 and (args.steps + args.warmup) * batch * per_sample_est > 240:
         batch //= 2
     r = run_cpu_port(cfg, batch, args.steps, args.warmup)
-    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+    line = {"metric": METRIC if args.workload == "cifar10" else METRIC.replace("CIFAR-10", "CelebA-64"),
+            "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "PSLD CIFAR-10 NCSN++ (nf=128, ch_mult=[2,2,2], 8 res blocks, "
-                                   "attn@16, fir, fourier), SSCS sampler, 1000 NFE, random-init weights",
-                       "cpu_batch": batch},
+            "config": {"workload": workload_desc, "cpu_batch": batch},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -180,7 +192,7 @@ def main_reference(args):
 def main_b200(args):
     import torch
     import torch.distributed as dist
-    from psld_b200 import NCSNpp, PSLD, SSCSSampler, cifar10_config, time_grid
+    from psld_b200 import NCSNpp, PSLD, SSCSSampler, time_grid
     from psld_b200 import _lib as L
     from psld_b200.distributed import env_rank, gather_samples, max_over_ranks
     from psld_b200.profiling import profile_plan
@@ -194,14 +206,20 @@ def main_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
-    cfg = cifar10_config(batch_size=args.batch, n_samples=args.batch * world)
+    import psld_b200
+    cfg_name, flop_per_sample_nfe, default_batch, workload_desc = WORKLOADS[args.workload]
+    make_cfg = getattr(psld_b200, cfg_name)
+    if args.batch <= 0:
+        args.batch = default_batch
+    cfg = make_cfg(batch_size=args.batch, n_samples=args.batch * world)
     cfg.evaluation.sampler["state_dtype"] = args.state
     torch.manual_seed(1234)
     net = NCSNpp(cfg).eval().set_precision(args.precision).to(dev)   # random-init weights
     sde = PSLD(cfg)
     S = SSCSSampler(cfg, sde, net)
     B = args.batch
-    chw = 3 * 32 * 32
+    H = cfg.data.image_size
+    chw = 3 * H * H
     ts, n = time_grid(cfg)
     plan = net.plan(B, 1, True)
     lib = L.lib()
@@ -209,7 +227,7 @@ def main_b200(args):
 
     # ---- device-resident loop pieces: K predictor steps of the real 1000-step schedule
     state_dtype = torch.float32 if args.state == "float32" else torch.float64
-    state = sde.prior_sampling_device((B, 3, 32, 32), seed=1 + rank, device=dev).to(state_dtype)
+    state = sde.prior_sampling_device((B, 3, H, H), seed=1 + rank, device=dev).to(state_dtype)
     plan.x_in.copy_(state)
 
     side = torch.cuda.Stream(dev)          # CUDA-graph capture needs a non-default stream
@@ -268,7 +286,7 @@ def main_b200(args):
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
         traffic, tsrc = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and B == 256:
+        if os.path.exists(tp) and B == 256 and args.workload == "cifar10":
             tj = json.load(open(tp))
             traffic = tj["kernels"].get("conv_tc_kernel", {}).get("traffic_bytes_per_launch")
             tsrc = tj["source"]
@@ -295,11 +313,11 @@ def main_b200(args):
     # ---- end to end through the public API: pinned host prior -> HOST samples
     e2e = None
     if args.e2e_nfe > 0:
-        cfg_e = cifar10_config(batch_size=B, n_samples=B * world, n_discrete_steps=args.e2e_nfe)
+        cfg_e = make_cfg(batch_size=B, n_samples=B * world, n_discrete_steps=args.e2e_nfe)
         cfg_e.evaluation.sampler["state_dtype"] = args.state
         Se = SSCSSampler(cfg_e, sde, net)
         ts_e, n_e = time_grid(cfg_e)
-        host_prior = sde.prior_sampling([B, 3, 32, 32]).pin_memory()
+        host_prior = sde.prior_sampling([B, 3, H, H]).pin_memory()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -318,18 +336,18 @@ def main_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_port(cifar10_config(), args.cpu_batch, args.cpu_steps, 1)
+        r = run_cpu_port(make_cfg(), args.cpu_batch, args.cpu_steps, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.workload == "cifar10" else METRIC.replace("CIFAR-10", "CelebA-64"),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {
-                "workload": "PSLD CIFAR-10 NCSN++ (nf=128, ch_mult=[2,2,2], 8 res blocks, attn@16, fir, "
-                            "fourier), SSCS sampler, 1000 NFE, random-init weights (BASELINE configs[1])",
+                "workload": workload_desc,
                 "batch_per_gpu": B, "batch_total": B * world, "nfe_per_sample": NFE,
                 "state_dtype": args.state, "noise": "in-kernel Philox4x32-10",
                 "step": "one SSCS predictor step = 1 score_fn call + 1 fused update",
@@ -339,7 +357,7 @@ def main_b200(args):
             },
             "clocks": clk, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "roofline_update": upd, "cpu_baseline": cpu,
-            "tensor_frac_of_step": (FLOP_PER_SAMPLE_NFE * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
+            "tensor_frac_of_step": (flop_per_sample_nfe * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
             "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
             "engines": plan.engine_count, "finite": finite,
             "conv_classes": {k: {"n": v["n"], "ms": round(v["ms"], 4), "tflops": round(v["tflops"], 1)}

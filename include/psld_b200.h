@@ -132,6 +132,12 @@ PSLD_API int psld_em_update(void* u_out, const void* u_in, int state_dtype, floa
 PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                       psld_stream_t stream);
 
+/* Caller-side epilogue of sampling, fused (SimpleImageWriter.write_on_batch_end,
+ * main/callbacks.py:103-107 + save_as_images, main/util.py:147-158): drop the momentum half,
+ * x*0.5+0.5, *255, clip, truncate to uint8; state NCHW [B,2C,H,W] -> images NHWC [B,H,W,C]. */
+PSLD_API int psld_quantize_images(const void* state, int state_dtype, uint8_t* out_nhwc, int64_t B,
+                                  int C, int HW, psld_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * 2. NCSN++ score network ops.  Activations are NHWC inside the network, element type
  *    PSLD_F32 (reference-faithful path) or PSLD_BF16 (tensor-core path).

@@ -431,3 +431,14 @@ class OracleScoreFn:
     def __call__(self, u, t):
         with torch.no_grad():
             return ncsnpp_forward(self.config, self.sd, u, t)
+
+
+# --------------------------------------------------------------------------------------
+# 5. Caller-side image quantisation (callbacks.py:103-107, util.py:147-158)
+# --------------------------------------------------------------------------------------
+def images_uint8(state: torch.Tensor) -> np.ndarray:
+    """[B,2C,H,W] -> uint8 [B,H,W,C]: drop momentum, x*0.5+0.5, *255, clip, astype(uint8)."""
+    x, _ = torch.chunk(state.cpu(), 2, dim=1)
+    obj = x * 0.5 + 0.5
+    arr = obj.permute(0, 2, 3, 1).contiguous().numpy()
+    return (arr * 255).clip(0, 255).astype(np.uint8)

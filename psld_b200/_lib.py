@@ -83,6 +83,8 @@ EXPORTS = {
                                  C.c_int64, C.c_int64, C.c_void_p]),
     "psld_prior_sample": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_int64, C.c_int64,
                                     C.c_void_p]),
+    "psld_quantize_images": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                       C.c_void_p]),
     "psld_op_prepare": (C.c_int, [C.POINTER(Op)]),
     "psld_op_release": (C.c_int, [C.POINTER(Op)]),
     "psld_op_run": (C.c_int, [C.POINTER(Op), C.c_void_p]),

@@ -330,6 +330,26 @@ prior_kernel(float* __restrict__ u, float m_std, uint64_t seed, int64_t B, int64
   }
 }
 
+// SimpleImageWriter + save_as_images of the reference (main/callbacks.py:103-107,
+// main/util.py:147-158) as one pass: keep the position half, x*0.5+0.5, *255, clip to [0,255],
+// truncate to uint8, NCHW -> NHWC.  Arithmetic in the state's own type, like the reference.
+template <typename S>
+__global__ void __launch_bounds__(256)
+quantize_kernel(const S* __restrict__ u, uint8_t* __restrict__ out, int64_t B, int C, int HW) {
+  const int64_t total = B * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int p = (int)(r % HW);
+    const int64_t b = r / HW;
+    S v = u[(b * 2 * C + c) * HW + p] * (S)0.5 + (S)0.5;
+    v = v * (S)255;
+    v = v < (S)0 ? (S)0 : (v > (S)255 ? (S)255 : v);
+    out[i] = (uint8_t)v;
+  }
+}
+
 static inline int grid_for(int64_t nvec) {
   // enough CTAs for >= 8 resident per SM on 148 SMs, capped so small problems stay 1 wave
   int64_t g = ceil_div(nvec, 256);
@@ -438,6 +458,21 @@ extern "C" int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t 
   PSLD_CHECK_ARG(u && B > 0 && chw > 0 && chw % 4 == 0, "psld_prior_sample: bad arguments");
   prior_kernel<<<grid_for(B * (chw / 4)), 256, 0, (cudaStream_t)stream>>>(u, (float)m_std, seed,
                                                                          B, chw);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_quantize_images(const void* state, int state_dtype, uint8_t* out_nhwc, int64_t B,
+                                    int C, int HW, psld_stream_t stream) {
+  PSLD_CHECK_ARG(state && out_nhwc && B > 0 && C > 0 && HW > 0, "psld_quantize_images: bad arguments");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
+                 "psld_quantize_images: state dtype must be f64 or f32");
+  const int grid = grid_for(B * HW * C);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    quantize_kernel<double><<<grid, 256, 0, s>>>((const double*)state, out_nhwc, B, C, HW);
+  else
+    quantize_kernel<float><<<grid, 256, 0, s>>>((const float*)state, out_nhwc, B, C, HW);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

@@ -184,3 +184,17 @@ def test_cuda_graph_replay_equals_host_loop(kind, fuse, merge):
         a, _, _ = _run(cfg, net, u0, None, state_dtype=sd, fuse=fuse, record=False, merge=merge, graph=False)
         b, _, _ = _run(cfg, net, u0, None, state_dtype=sd, fuse=fuse, record=False, merge=merge, graph=True)
         assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_image_quantisation_bit_exact(dtype):
+    """Fused writer arithmetic (drop momentum, x*0.5+0.5, *255, clip, truncate) == the reference's
+    numpy sequence, bit for bit (integer output)."""
+    from psld_b200 import samples_to_uint8
+    g = torch.Generator().manual_seed(5)
+    st = (torch.randn(7, 6, 32, 32, generator=g, dtype=torch.float64) * 1.3).to(dtype)
+    st[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.999999], dtype=dtype)   # edges of the range
+    got = samples_to_uint8(st.cuda()).cpu().numpy()
+    ref = O.images_uint8(st)
+    assert got.shape == ref.shape == (7, 32, 32, 3) and got.dtype == ref.dtype
+    assert (got == ref).all()

@@ -124,3 +124,22 @@ def test_no_cpu_fallback():
         net(torch.zeros(1, 6, 32, 32), torch.ones(1))
     with pytest.raises(RuntimeError, match="no CPU path"):
         build_plan(net, 1, 1, False)
+
+
+def test_checkpoint_loader(tmp_path):
+    """Lightning-style checkpoint (prefixes score_fn./ema_score_fn.) -> NCSNpp, strict."""
+    from psld_b200 import load_checkpoint, select_score_fn_state
+    cfg = tiny_config()
+    src = NCSNpp(cfg)
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in src.state_dict().items()}, 4)
+    ema = {k: v + 1.0 for k, v in sd.items()}
+    ck = {"state_dict": {**{"score_fn." + k: v for k, v in sd.items()},
+                         **{"ema_score_fn." + k: v for k, v in ema.items()}}, "epoch": 3}
+    path = tmp_path / "psld.ckpt"
+    torch.save(ck, path)
+    a = load_checkpoint(NCSNpp(cfg), str(path), sample_from="target")
+    b = load_checkpoint(NCSNpp(cfg), str(path), sample_from="source")
+    k0 = "all_modules.3.weight"
+    assert torch.equal(a.state_dict()[k0], ema[k0]) and torch.equal(b.state_dict()[k0], sd[k0])
+    with pytest.raises(KeyError):
+        select_score_fn_state({"foo.x": torch.zeros(1)}, "target")
