@@ -155,6 +155,9 @@ PSLD_API int psld_quantize_images(const void* state, int state_dtype, uint8_t* o
 #define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0;
                               stride 1 'same' padding, or 3x3 stride 2 without padding)     */
 
+#define PSLD_ENGINE_TC_GN 2 /* PSLD_OP_CONV only: tensor-core 3x3 conv with GroupNorm(+SiLU) applied
+                              to the input inside the kernel (in[6] = per-(n,channel) affine)  */
+
 #define PSLD_OP_NI 28
 #define PSLD_OP_NF 24
 #define PSLD_OP_NP 8
@@ -195,9 +198,11 @@ enum { PSLD_TEMB_NT = 0, PSLD_TEMB_NF, PSLD_TEMB_EMB, PSLD_TEMB_TOTALC, PSLD_TEM
  *   (sum, sum of squares) per 32 pixels x 4 channels, written by the PSLD_OP_CONV that produced
  *   the tensor (its out[1]).  When every source has them the full-tensor statistics pass is
  *   replaced by a fold over these micro-groups.
- *   i: N, HW, C1, C2, G, SILU, IN_DTYPE, OUT_DTYPE, NCHUNK ; f[0] = eps                 */
+ *   i: N, HW, C1, C2, G, SILU, IN_DTYPE, OUT_DTYPE, NCHUNK, AFFINE_ONLY ; f[0] = eps
+ *   AFFINE_ONLY = 1: no apply pass; out[0] receives fp32 [N, C, 2] = (rstd*gamma,
+ *   beta - mean*rstd*gamma) for a PSLD_ENGINE_TC_GN convolution to apply on load.            */
 enum { PSLD_GN_N = 0, PSLD_GN_HW, PSLD_GN_C1, PSLD_GN_C2, PSLD_GN_G, PSLD_GN_SILU,
-       PSLD_GN_IN_DTYPE, PSLD_GN_OUT_DTYPE, PSLD_GN_NCHUNK };
+       PSLD_GN_IN_DTYPE, PSLD_GN_OUT_DTYPE, PSLD_GN_NCHUNK, PSLD_GN_AFFINE_ONLY };
 
 /* --- PSLD_OP_FIR (upfirdn2d, op/upfirdn2d.py:159-200; callers up_or_down_sampling.py:195-257):
  *   in[0] = x [N,H,W,C] ; out[0] = y [N,OH,OW,C]
@@ -210,6 +215,9 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
  *   up_or_down_sampling.py:178; epilogue terms layerspp.py:262-274,88-91, ncsnpp.py:353-356)
  *   in[0] = x1, in[1] = x2 or NULL, in[2] = residual [N,OH,OW,Cout] or NULL,
  *   in[3] = temb proj (f32) or NULL, in[4] = weight, in[5] = bias f32 [Cout] or NULL
+ *   in[6] = (engine PSLD_ENGINE_TC_GN) fp32 [N, Cin, 2] (scale, shift) produced by a PSLD_OP_GN
+ *           in affine-only mode: the conv input is silu?(x * scale + shift), applied in-kernel
+ *           (i[GN_SILU] selects the SiLU); x1/x2 are then the RAW, un-normalised tensors
  *   out[0] = y
  *   out[1] = optional fp32 [N*OH*OW/32, Cout/4, 2] micro-group statistics of y for the GroupNorm
  *            that consumes it (TC engine, bf16 NHWC output, OH*OW % 32 == 0), or NULL
@@ -219,7 +227,7 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
 enum { PSLD_CONV_N = 0, PSLD_CONV_H, PSLD_CONV_W, PSLD_CONV_C1, PSLD_CONV_C2, PSLD_CONV_COUT,
        PSLD_CONV_KS, PSLD_CONV_STRIDE, PSLD_CONV_PAD, PSLD_CONV_OH, PSLD_CONV_OW,
        PSLD_CONV_IN_LAYOUT, PSLD_CONV_OUT_LAYOUT, PSLD_CONV_IN_DTYPE, PSLD_CONV_OUT_DTYPE,
-       PSLD_CONV_RES_DTYPE, PSLD_CONV_TEMB_OFF, PSLD_CONV_TEMB_BSTRIDE };
+       PSLD_CONV_RES_DTYPE, PSLD_CONV_TEMB_OFF, PSLD_CONV_TEMB_BSTRIDE, PSLD_CONV_GN_SILU };
 
 /* --- PSLD_OP_ATTN (AttnBlockpp core, layerspp.py:82-86): single head over HW tokens.
  *   in[0] = qkv [N, HW, 3C] (q | k | v along the last axis) ; out[0] = o [N, HW, C]

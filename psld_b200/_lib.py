@@ -19,17 +19,18 @@ F32, BF16, F64 = 0, 1, 2
 NHWC, NCHW = 0, 1
 STAGE_HALF_A, STAGE_SCORE, STAGE_HALF_B, STAGE_HALF_C = 1, 2, 4, 8
 OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN = 1, 2, 3, 4, 5, 6
-ENGINE_SIMT, ENGINE_TC = 0, 1
+ENGINE_SIMT, ENGINE_TC, ENGINE_TC_GN = 0, 1, 2
 OP_NI, OP_NF, OP_NP = 28, 24, 8
 
 # slot indices
 (LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE, LAYOUT_CPAD) = range(6)
 (TEMB_NT, TEMB_NF, TEMB_EMB, TEMB_TOTALC, TEMB_LOGGED) = range(5)
-(GN_N, GN_HW, GN_C1, GN_C2, GN_G, GN_SILU, GN_IN_DTYPE, GN_OUT_DTYPE, GN_NCHUNK) = range(9)
+(GN_N, GN_HW, GN_C1, GN_C2, GN_G, GN_SILU, GN_IN_DTYPE, GN_OUT_DTYPE, GN_NCHUNK,
+ GN_AFFINE_ONLY) = range(10)
 (FIR_N, FIR_H, FIR_W, FIR_C, FIR_UP, FIR_DOWN, FIR_PAD0, FIR_PAD1, FIR_KH, FIR_DTYPE) = range(10)
 (CONV_N, CONV_H, CONV_W, CONV_C1, CONV_C2, CONV_COUT, CONV_KS, CONV_STRIDE, CONV_PAD, CONV_OH,
  CONV_OW, CONV_IN_LAYOUT, CONV_OUT_LAYOUT, CONV_IN_DTYPE, CONV_OUT_DTYPE, CONV_RES_DTYPE,
- CONV_TEMB_OFF, CONV_TEMB_BSTRIDE) = range(18)
+ CONV_TEMB_OFF, CONV_TEMB_BSTRIDE, CONV_GN_SILU) = range(19)
 (ATTN_N, ATTN_HW, ATTN_C, ATTN_DTYPE) = range(4)
 
 

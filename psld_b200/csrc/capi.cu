@@ -26,7 +26,7 @@ static int op_launch_count(const psld_op& op) {
   switch (op.kind) {
     case PSLD_OP_LAYOUT: return 1;
     case PSLD_OP_TEMB: return 4;
-    case PSLD_OP_GN: return 2;
+    case PSLD_OP_GN: return 2;   // statistics (or fold of producer statistics) + apply / affine
     case PSLD_OP_FIR: return 1;
     case PSLD_OP_CONV: return 1;
     case PSLD_OP_ATTN: return 1;
@@ -41,6 +41,7 @@ static int dispatch(const psld_op& op, cudaStream_t s) {
     case PSLD_OP_GN: return run_gn(op, s);
     case PSLD_OP_FIR: return run_fir(op, s);
     case PSLD_OP_CONV:
+      if (op.engine == PSLD_ENGINE_TC_GN) return run_conv_gn_tc(op, s);
       return op.engine == PSLD_ENGINE_TC ? run_conv_tc(op, s) : run_conv_simt(op, s);
     case PSLD_OP_ATTN:
       return op.engine == PSLD_ENGINE_TC ? run_attn_tc(op, s) : run_attn_simt(op, s);
@@ -72,6 +73,7 @@ extern "C" int psld_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 extern "C" int psld_op_prepare(psld_op* op) {
   PSLD_CHECK_ARG(op != nullptr, "psld_op_prepare: null op");
   if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC) return prepare_conv_tc(*op);
+  if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC_GN) return prepare_conv_gn_tc(*op);
   if (op->kind == PSLD_OP_ATTN && op->engine == PSLD_ENGINE_TC) return prepare_attn_tc(*op);
   return PSLD_OK;
 }
@@ -79,6 +81,7 @@ extern "C" int psld_op_prepare(psld_op* op) {
 extern "C" int psld_op_release(psld_op* op) {
   PSLD_CHECK_ARG(op != nullptr, "psld_op_release: null op");
   if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC) return release_conv_tc(*op);
+  if (op->kind == PSLD_OP_CONV && op->engine == PSLD_ENGINE_TC_GN) return release_conv_gn_tc(*op);
   if (op->kind == PSLD_OP_ATTN && op->engine == PSLD_ENGINE_TC) return release_attn_tc(*op);
   return PSLD_OK;
 }

@@ -98,6 +98,9 @@ int run_attn_simt(const psld_op& op, cudaStream_t s);
 int prepare_conv_tc(psld_op& op);
 int release_conv_tc(psld_op& op);
 int run_conv_tc(const psld_op& op, cudaStream_t s);
+int prepare_conv_gn_tc(psld_op& op);
+int release_conv_gn_tc(psld_op& op);
+int run_conv_gn_tc(const psld_op& op, cudaStream_t s);
 int prepare_attn_tc(psld_op& op);
 int release_attn_tc(psld_op& op);
 int run_attn_tc(const psld_op& op, cudaStream_t s);

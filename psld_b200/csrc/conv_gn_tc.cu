@@ -1,0 +1,449 @@
+// GroupNorm+SiLU-on-load 3x3 convolution: tcgen05 (cta_group::2) implicit GEMM whose A operand is
+// normalised INSIDE the kernel, so the separate GroupNorm "apply" pass over HBM (read x, write
+// silu(gn(x)), 20 % of the sampler step) disappears for the layers this kernel takes.
+//
+//   y = scale * ( conv3x3( silu( x * sc[n,c] + sh[n,c] ) ) + bias + temb + residual )
+//
+// with (sc, sh) the per-(sample, channel) affine form of GroupNorm (gn_affine_kernel) — i.e.
+// ResnetBlockBigGANpp's  act(GroupNorm_k(.)) -> Conv_k  pairs (reference layerspp.py:243,259,266).
+//
+// How the normalisation is applied once per element although a 3x3 conv reads every pixel 9 times:
+// per (tile, 64-channel chunk) the RAW tile plus its vertical halo ((BH+2) x W pixels, out-of-image
+// rows zero-filled by TMA) is loaded ONCE; four "transform" warps normalise it in shared memory and
+// write three operand tiles: centre, shifted left and shifted right by one pixel (image-edge
+// columns zeroed = the conv's horizontal padding).  The 9 taps are then plain descriptor offsets:
+// kx selects the variant, ky adds ky*W rows (a multiple of the 1024-byte swizzle atom for
+// W = 16, 32), so no tap needs its own load.  L2->SM traffic for A drops from 9 x 16 KB to 24 KB
+// per chunk; weights stream per tap through a 3-stage ring (half tile per CTA, as in conv_tc).
+//
+// Warps (480 threads): 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator,
+// 2..9 = epilogue (shared with conv_tc), 10 = weight TMA, 11..14 = transform.
+
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "conv_tc_common.cuh"
+
+namespace psld {
+
+constexpr int GN_THREADS = 480;
+constexpr int GN_B_STAGES = 3;
+constexpr int GN_B_BYTES = 128 * 128;            // half weight tile per CTA (<= 128 rows x 128 B)
+constexpr int GN_MAX_ROWS = 192;                 // (BH+2)*W: 6x32 or 10x16
+constexpr int GN_VAR_BYTES = GN_MAX_ROWS * 128;  // one operand variant (24 KB)
+constexpr int GN_ABUF_BYTES = 3 * GN_VAR_BYTES;  // left | centre | right
+constexpr int GN_STAGING_BYTES = 8 * 4096;
+constexpr int GN_SMEM_BYTES = 2 * GN_ABUF_BYTES + GN_B_STAGES * GN_B_BYTES + GN_STAGING_BYTES + 1024 + 256;
+
+struct ConvGnParams {
+  ConvTcParams c;
+  const float* affine;     // [N, Cin, 2] (scale, shift) of the GroupNorm feeding this conv
+  int cin;                 // C1 + C2
+  int silu;
+  int rows_in;             // (BH + 2) * W
+  int w_shift;             // log2(W)
+  int n_images;
+};
+
+struct ConvGnState {
+  CUtensorMap a1, a2, b;
+  ConvGnParams p;
+  int grid;
+};
+
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+__global__ void __launch_bounds__(GN_THREADS, 1)
+conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const ConvGnParams gp) {
+  const ConvTcParams& p = gp.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto abuf = [&](int b) { return base + (uint32_t)b * GN_ABUF_BYTES; };
+  const uint32_t bring = base + 2 * GN_ABUF_BYTES;
+  const uint32_t stg_base = bring + GN_B_STAGES * GN_B_BYTES;
+  const uint32_t bar_base = stg_base + GN_STAGING_BYTES;
+  auto raw_full = [&](int b) { return bar_base + 8u * b; };
+  auto a_ready = [&](int b) { return bar_base + 8u * (2 + b); };
+  auto a_empty = [&](int b) { return bar_base + 8u * (4 + b); };
+  auto b_full = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (9 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (14 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 16;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(raw_full(b), 1);
+      mbar_init(a_ready(b), 2);       // one elected arrive per CTA of the pair
+      mbar_init(a_empty(b), 1);
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 16);
+    }
+    for (int s = 0; s < GN_B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int b_rows = p.block_n >> 1;
+  const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
+
+  if (warp == 0) {
+    // ===================== raw activation tile producer =====================
+    if (lane == 0) {
+      int buf = 0;
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+        const int n0 = m_tile / p.tiles_y;
+        const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(a_empty(buf), ph ^ 1);
+          mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
+          const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
+          const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+          tma_load_4d(abuf(buf) + GN_VAR_BYTES, tmA, raw_full(buf), c0, 0, y0, n0);  // centre slot
+          if (++buf == 2) { buf = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== weight producer (half tile per CTA, credited to the leader) ======
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)b_rows * 128u * 2u;
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        const int n_tile = unit % p.n_tiles_n;
+        const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_empty(stage), ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
+            tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, &tmB, b_full(stage),
+                             (tap * p.kchunks + cc) * TC_BLOCK_K, bn0);
+            if (++stage == GN_B_STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int buf = 0, stage = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      const uint32_t row_step = (uint32_t)p.W * 128u;       // ky * W rows
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait_cluster(a_ready(buf), aph);
+          tc_fence_after();
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            mbar_wait(b_full(stage), bph);
+            tc_fence_after();
+            // variant kx: 0 = shifted so that row (y,x) holds t(y,x-1), 1 = centre, 2 = t(y,x+1)
+            const uint64_t adesc = make_sw128_desc(abuf(buf) + (uint32_t)kx * GN_VAR_BYTES +
+                                                   (uint32_t)ky * row_step);
+            const uint64_t bdesc = make_sw128_desc(bring + (uint32_t)stage * GN_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                               (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            tc_commit_pair(b_empty(stage));
+            if (++stage == GN_B_STAGES) { stage = 0; bph ^= 1; }
+          }
+          tc_commit_pair(a_empty(buf));
+          if (++buf == 2) { buf = 0; aph ^= 1; }
+        }
+        tc_commit_pair(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 11) {
+    // ===================== transform warps: GroupNorm + SiLU, three shifted operand tiles =====
+    const int tt = (int)threadIdx.x - 11 * 32;      // 0..127
+    const int j = tt & 7;                           // 16-byte chunk = channels 8j .. 8j+7
+    const int r0 = tt >> 3;                         // rows r0, r0+16, ...
+    const uint32_t leader_ready0 = mapa_rank(a_ready(0), 0);
+    const int Wm = p.W - 1;
+    int buf = 0;
+    uint32_t ph = 0;
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+      const int n0 = m_tile / p.tiles_y;
+      const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
+      const bool img_ok = n0 < gp.n_images;
+      for (int cc = 0; cc < p.kchunks; ++cc) {
+        float sc[8], sh[8];
+        if (img_ok) {
+          const float4* ap = reinterpret_cast<const float4*>(
+              gp.affine + ((int64_t)n0 * gp.cin + cc * TC_BLOCK_K + j * 8) * 2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(ap + q);
+            sc[2 * q] = v.x; sh[2 * q] = v.y; sc[2 * q + 1] = v.z; sh[2 * q + 1] = v.w;
+          }
+        }
+        mbar_wait(raw_full(buf), ph);
+        const uint32_t L = abuf(buf), Cc = L + GN_VAR_BYTES, R = Cc + GN_VAR_BYTES;
+        for (int r = r0; r < gp.rows_in; r += 16) {
+          const int x = r & Wm;
+          const int gy = y0 + (r >> gp.w_shift);
+          const bool valid = img_ok && gy >= 0 && gy < p.H;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          if (valid) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(Cc + off) : "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+              float a = fmaf(f.x, sc[2 * q], sh[2 * q]);
+              float b = fmaf(f.y, sc[2 * q + 1], sh[2 * q + 1]);
+              if (gp.silu) { a = silu_fast(a); b = silu_fast(b); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              w[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          // centre: t(y, x)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(Cc + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          // left variant: row (y, x+1) <- t(y, x);  column 0 <- 0
+          if (x < Wm) {
+            const int rn = r + 1;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(L + (uint32_t)rn * 128u + (uint32_t)((j ^ (rn & 7)) << 4)), "r"(w[0]),
+                           "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+          if (x == 0)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(L + off), "r"(0u) : "memory");
+          // right variant: row (y, x-1) <- t(y, x);  column W-1 <- 0
+          if (x > 0) {
+            const int rp = r - 1;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(R + (uint32_t)rp * 128u + (uint32_t)((j ^ (rp & 7)) << 4)), "r"(w[0]),
+                           "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+          if (x == Wm)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(R + off), "r"(0u) : "memory");
+        }
+        // generic-proxy writes -> visible to the tensor core (async proxy), then tell the leader
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tt == 0) mbar_arrive_remote(leader_ready0 + 8u * (uint32_t)buf);
+        if (++buf == 2) { buf = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9), shared with conv_tc =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int n_tile = unit % p.n_tiles_n;
+      const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      tc_epilogue_tile(p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+                       stg_base + (uint32_t)(warp - 2) * 4096u);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_tempty0 + 8u * (uint32_t)acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int encode_raw_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int rows_y) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)W, (cuuint32_t)rows_y, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(raw tile) failed: %d", (int)r); return PSLD_ECUDA; }
+  return PSLD_OK;
+}
+
+static int encode_w_half_map(CUtensorMap* tm, const void* ptr, int Cout, int K, int rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PSLD_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight) failed: %d", (int)r); return PSLD_ECUDA; }
+  return PSLD_OK;
+}
+
+// Returns PSLD_EUNSUPPORTED when the shape must take the unfused route (GroupNorm apply + conv_tc).
+int prepare_conv_gn_tc(psld_op& op) {
+  const int N = op.i[PSLD_CONV_N], H = op.i[PSLD_CONV_H], W = op.i[PSLD_CONV_W];
+  const int C1 = op.i[PSLD_CONV_C1], C2 = op.i[PSLD_CONV_C2], Cout = op.i[PSLD_CONV_COUT];
+  const int KS = op.i[PSLD_CONV_KS];
+  auto unsupported = [&](const char* why) {
+    set_error("conv_gn_tc: not eligible (%s): N=%d H=%d W=%d C1=%d C2=%d Cout=%d KS=%d", why, N, H,
+              W, C1, C2, Cout, KS);
+    return PSLD_EUNSUPPORTED;
+  };
+  static const int env = [] { const char* e = getenv("PSLD_TC_FUSE_GN"); return e ? atoi(e) : 1; }();
+  if (!env) return unsupported("disabled by PSLD_TC_FUSE_GN=0");
+  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16 || op.i[PSLD_CONV_OUT_DTYPE] != PSLD_BF16)
+    return unsupported("bf16 in/out only");
+  if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC || op.i[PSLD_CONV_OUT_LAYOUT] != PSLD_NHWC)
+    return unsupported("NHWC only");
+  if (KS != 3 || op.i[PSLD_CONV_STRIDE] != 1 || op.i[PSLD_CONV_PAD] != 1) return unsupported("3x3 s1 p1 only");
+  if (C1 % TC_BLOCK_K || C2 % TC_BLOCK_K) return unsupported("Cin %% 64 != 0");
+  if (Cout % 64 || Cout > 256 && Cout % 256) return unsupported("Cout");
+  if (!((W == 32 && H >= 4) || (W == 16 && H >= 8)) || (H & (H - 1))) return unsupported("map must be 16x16+ / 32x32+ wide tiles");
+  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != PSLD_BF16) return unsupported("residual dtype");
+  if (!op.in[0] || !op.in[4] || !op.in[6] || !op.out[0] || (C2 > 0 && !op.in[1])) {
+    set_error("conv_gn_tc: null pointer");
+    return PSLD_EINVAL;
+  }
+  int block_n = 0;
+  for (int cand : {256, 128, 64})
+    if (Cout % cand == 0) { block_n = cand; break; }
+  const int BH = 128 / W;
+  const int rows_in = (BH + 2) * W;
+  if (rows_in > GN_MAX_ROWS) return unsupported("tile rows");
+  const int64_t m_tiles = (int64_t)N * (H / BH);
+  if (m_tiles < 2) return unsupported("single tile");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  ConvGnState* st = new (std::nothrow) ConvGnState();
+  if (!st) { set_error("conv_gn_tc: out of host memory"); return PSLD_ECUDA; }
+  int rc = encode_raw_map(&st->a1, op.in[0], N, H, W, C1, BH + 2);
+  if (rc == PSLD_OK)
+    rc = C2 > 0 ? encode_raw_map(&st->a2, op.in[1], N, H, W, C2, BH + 2)
+                : encode_raw_map(&st->a2, op.in[0], N, H, W, C1, BH + 2);
+  const int K = 9 * (C1 + C2);
+  if (rc == PSLD_OK) rc = encode_w_half_map(&st->b, op.in[4], Cout, K, block_n / 2);
+  if (rc != PSLD_OK) { delete st; return rc; }
+  ConvGnParams& g = st->p;
+  ConvTcParams& p = g.c;
+  p.bias = (const float*)op.in[5];
+  p.temb = (const float*)op.in[3];
+  p.res = (const __nv_bfloat16*)op.in[2];
+  p.y = (__nv_bfloat16*)op.out[0];
+  p.y_nchw = nullptr;
+  p.cout_valid = Cout;
+  p.mg_stats = (float*)op.out[1];
+  p.scale = op.f[0];
+  p.temb_off = op.i[PSLD_CONV_TEMB_OFF];
+  p.temb_bstride = op.i[PSLD_CONV_TEMB_BSTRIDE];
+  p.H = H; p.W = W; p.HW = H * W; p.Cout = Cout;
+  p.stride = 1; p.pad = 1;
+  p.BH = BH; p.BN_img = 1; p.tiles_y = H / BH;
+  p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
+  p.taps = 9; p.KS = 3;
+  p.block_n = block_n; p.n_tiles_n = Cout / block_n;
+  p.M = (int64_t)N * H * W;
+  p.num_tiles = (int)(((m_tiles + 1) / 2) * p.n_tiles_n);
+  g.affine = (const float*)op.in[6];
+  g.cin = C1 + C2;
+  g.silu = op.i[PSLD_CONV_GN_SILU];
+  g.rows_in = rows_in;
+  g.w_shift = W == 32 ? 5 : 4;
+  g.n_images = N;
+  const int pairs = sms / 2;
+  st->grid = 2 * (p.num_tiles < pairs ? p.num_tiles : pairs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GN_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_gn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      delete st;
+      return PSLD_ECUDA;
+    }
+    attr_set = true;
+  }
+  op.aux = st;
+  return PSLD_OK;
+}
+
+int release_conv_gn_tc(psld_op& op) {
+  if (op.aux) {
+    delete (ConvGnState*)op.aux;
+    op.aux = nullptr;
+  }
+  return PSLD_OK;
+}
+
+int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
+  const ConvGnState* st = (const ConvGnState*)op.aux;
+  PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)st->grid);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = GN_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gn_tc_kernel, st->a1, st->a2, st->b, st->p));
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+}  // namespace psld

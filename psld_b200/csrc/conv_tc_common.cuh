@@ -1,0 +1,384 @@
+// Shared pieces of the tcgen05 convolution kernels: parameters, 2-CTA (cta_group::2) PTX wrappers
+// and the epilogue (TMEM -> registers -> bias/temb/residual/scale -> bf16 through a swizzled
+// shared-memory tile -> coalesced global stores, plus GroupNorm micro-group statistics).
+#pragma once
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace psld {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;        // bf16 elements = one 128-byte swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+constexpr int TC_B_BYTES = 256 * TC_BLOCK_K * 2;          // 32 KB (max BLOCK_N = 256)
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 352;        // A-TMA warp + MMA warp + 8 epilogue warps + B-TMA warp
+constexpr int TC_TMEM_COLS = 512;
+
+struct ConvTcParams {
+  const float* bias;
+  const float* temb;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  float* y_nchw;             // when non-null: fp32 NCHW output, first cout_valid channels only
+  float* mg_stats;           // optional [M/32, Cout/4, 2] micro-group (sum, sumsq) of the output
+  int cout_valid;
+  float scale;
+  int temb_off, temb_bstride;
+  int H, W, HW, Cout;        // OUTPUT map size (== input size for the stride-1 'same' case)
+  int stride, pad;           // 1/KS/2, or 2/0 (3x3 stride-2 conv on a pre-padded input)
+  int BH, BN_img;            // output rows / images per tile: W*BH*BN_img == 128; the TMA box is
+                             // {64, W*stride, BH*stride, BN_img} traversed with element stride
+  int tiles_y;               // H / BH
+  int kchunks1, kchunks;     // 64-channel chunks in source 1 / in total (C1+C2)/64
+  int taps, KS;
+  int block_n, n_tiles_n;
+  int num_tiles;
+  int64_t M;                 // N*H*W
+};
+
+
+// ---------------------------------------------------------------- the kernel
+// kPair = false: one CTA per tile (tcgen05 cta_group::1, M = 128).
+// kPair = true : a cluster of two CTAs (one TPC) works on two vertically adjacent M tiles with ONE
+//   tcgen05.mma.cta_group::2 stream (M = 256) issued by the leader CTA.  Each CTA loads its own
+//   A tile and only HALF of the weight tile (block_n/2 rows); the tensor core reads the B halves
+//   from both CTAs' shared memory.  Per CTA and k-block this cuts the L2->SM traffic from 48 KB to
+//   32 KB and frees room for a 6-deep ring (ncu on the 1-CTA kernel: tensor pipe 75 % active with
+//   the XBAR at 15.6 TB/s and only ~1.3 us of TMA lookahead).
+template <bool kPair>
+struct TcCfg {
+  static constexpr int kStages = kPair ? 6 : TC_STAGES;
+  static constexpr int kBBytes = kPair ? TC_B_BYTES / 2 : TC_B_BYTES;
+  static constexpr int kStageBytes = TC_A_BYTES + kBBytes;
+  static constexpr int kStagingBytes = 8 * 4096;   // epilogue transpose buffers, 4 KB per warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xFFF) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+// 2-CTA TMA loads: data lands in THIS CTA's smem, bytes are credited to the LEADER's mbarrier
+// (peer bit 24 of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// One output tile: TMEM accumulator -> (+bias +temb +residual) * scale -> bf16 NHWC (or the fp32
+// NCHW network head) + GroupNorm micro-group statistics.  Called by the 8 epilogue warps;
+// `quarter` = TMEM lane quarter (warp id % 4), `half` selects alternate column groups, `stg` =
+// this warp's 4 KB staging tile in shared memory.
+__device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
+                                                 int m_tile, int n_tile, int quarter, int half,
+                                                 int lane, uint32_t stg) {
+  const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
+  const bool valid = m < p.M;
+  const int img = valid ? (int)(m / p.HW) : 0;
+  const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
+  const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
+  const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
+  if (p.y != nullptr && (p.block_n & 63) == 0) {
+    // ---- staged path: 64-column groups go through a per-warp 32 x 128 B shared-memory tile
+    // (16-byte chunks XOR-swizzled by row) so that BOTH the residual loads and the output
+    // stores hit global memory as full 128-byte lines (4 rows per instruction) instead of 32
+    // scattered 16-byte pieces; thread <-> TMEM row only touches its own row of the tile.
+        const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
+    const int sub_row = lane >> 3, chunk = lane & 7;
+    const int ncg = p.block_n >> 6;
+    const uint32_t my_row = stg + (uint32_t)lane * 128u;
+    uint4 rq[8];
+    auto load_res = [&](int cg) {
+      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t mr = m_base + 4 * it + sub_row;
+        if (mr < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + mr * p.Cout);
+      }
+    };
+    if (p.res && half < ncg) load_res(half);
+    for (int cg = half; cg < ncg; cg += 2) {
+      const int co_base = n_tile * p.block_n + cg * 64;
+      if (p.res) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = 4 * it + sub_row;
+          const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(a), "r"(rq[it].x), "r"(rq[it].y), "r"(rq[it].z), "r"(rq[it].w) : "memory");
+        }
+        __syncwarp();
+        if (cg + 2 < ncg) load_res(cg + 2);
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)acc * 256u + (uint32_t)(cg * 64 + sub * 32);
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        const int co0 = co_base + sub * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+        if (valid) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (temb) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(temb + co0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t a = my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4);
+          if (p.res) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+              if (valid) { v[q * 8 + 2 * t] += f.x; v[q * 8 + 2 * t + 1] += f.y; }
+            }
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            v[q * 8 + 2 * t] *= p.scale;
+            v[q * 8 + 2 * t + 1] *= p.scale;
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+            o[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+        if (stats) {
+          float a[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
+            a[2 * g] = (x0 + x1) + (x2 + x3);
+            a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+          }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send = hi ? a[j] : a[j + w];
+              const float keep = hi ? a[j + w] : a[j];
+              a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+            }
+          }
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+          if ((lane & 1) == 0)
+            p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1)] = a[0];
+        }
+      }
+      __syncwarp();
+      __nv_bfloat16* yp = p.y + co_base + chunk * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = 4 * it + sub_row;
+        const int64_t mr = m_base + row;
+        const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        uint4 q;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+        if (mr < p.M) *reinterpret_cast<uint4*>(yp + mr * p.Cout) = q;
+      }
+      __syncwarp();
+    }
+  } else {
+  const bool has_res = valid && p.res != nullptr;
+  uint4 rq[4];                                       // residual of the chunk being processed
+  if (has_res && half * 32 < p.block_n) {
+    const __nv_bfloat16* rp = p.res + m * p.Cout + n_tile * p.block_n + half * 32;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) rq[t] = *reinterpret_cast<const uint4*>(rp + 8 * t);
+  }
+  for (int ch = half * 32; ch < p.block_n; ch += 64) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                           (uint32_t)acc * 256u + (uint32_t)ch;
+    tmem_ld32(taddr, r);
+    const int co0 = n_tile * p.block_n + ch;
+    uint4 rn[4];                                     // prefetch the next chunk's residual
+    const bool more = ch + 64 < p.block_n;
+    if (has_res && more) {
+      const __nv_bfloat16* rp = p.res + m * p.Cout + co0 + 64;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) rn[t] = *reinterpret_cast<const uint4*>(rp + 8 * t);
+    }
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+    if (valid) {
+      const int64_t o = m * p.Cout + co0;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+      if (temb) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(temb + co0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+      if (p.res) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 q = rq[j >> 3];
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+            const float2 f = __bfloat1622float2(h);
+            v[j + 2 * t] += f.x;
+            v[j + 2 * t + 1] += f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+      if (p.y_nchw) {
+        // network output head (ncsnpp.py:430): fp32 NCHW, lanes = consecutive pixels
+        const int64_t pix = m - (int64_t)img * p.HW;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = co0 + j;
+          if (co < p.cout_valid)
+            p.y_nchw[((int64_t)img * p.cout_valid + co) * p.HW + pix] = v[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+            w[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(p.y + o + j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (has_res && more) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) rq[t] = rn[t];
+    }
+    __syncwarp();
+    if (stats) {
+      // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
+      // granularity: (sum, sum of squares) over this warp's 32 pixels.  16 values per lane are
+      // transposed-and-reduced across the warp with 16 shuffles (halving butterfly); the
+      // consumer GroupNorm combines micro-groups into its groups (gn_finalize_kernel).
+      float a[16];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
+        a[2 * g] = (x0 + x1) + (x2 + x3);
+        a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+      }
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1) {
+        const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+          const float send = hi ? a[j] : a[j + w];
+          const float keep = hi ? a[j + w] : a[j];
+          a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+        }
+      }
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+      if ((lane & 1) == 0) {
+        const int idx = lane >> 1;     // = bit4*8 + bit3*4 + bit2*2 + bit1
+        p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + idx] = a[0];
+      }
+    }
+  }
+  }  // legacy (non-staged) path
+}
+
+}  // namespace psld

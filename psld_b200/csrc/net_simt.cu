@@ -397,6 +397,38 @@ gn_finalize_kernel(const float* __restrict__ mg1, const float* __restrict__ mg2,
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
 }
 
+// Affine-only epilogue of the statistics pass: per (sample, channel) scale = rstd*gamma and
+// shift = beta - mean*scale, consumed by the GroupNorm-on-load convolution (conv_gn_tc.cu).
+__global__ void __launch_bounds__(256)
+gn_affine_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ affine, int HW, int C, int G,
+                 int nchunk, float eps) {
+  extern __shared__ float shf[];  // mean[G], rstd[G]
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double su = 0, sq = 0;
+    for (int k = 0; k < nchunk; ++k) {
+      const double* src = part + ((int64_t)n * nchunk + k) * 2 * G;
+      su += src[2 * g];
+      sq += src[2 * g + 1];
+    }
+    const double cntd = (double)HW * cpg;
+    const double mean = su / cntd;
+    double var = sq / cntd - mean * mean;
+    if (var < 0) var = 0;
+    shf[g] = (float)mean;
+    shf[G + g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = shf[G + g] * gamma[c];
+    affine[((int64_t)n * C + c) * 2] = sc;
+    affine[((int64_t)n * C + c) * 2 + 1] = beta[c] - sc * shf[g];
+  }
+}
+
 int run_gn(const psld_op& op, cudaStream_t s) {
   const int N = op.i[PSLD_GN_N], HW = op.i[PSLD_GN_HW], C1 = op.i[PSLD_GN_C1];
   const int C2 = op.i[PSLD_GN_C2], G = op.i[PSLD_GN_G], silu = op.i[PSLD_GN_SILU];
@@ -431,6 +463,14 @@ int run_gn(const psld_op& op, cudaStream_t s) {
 #undef GN_STATS
   }
   PSLD_CHECK_LAUNCH();
+  const float* ga0 = (const float*)op.in[2];
+  const float* be0 = (const float*)op.in[3];
+  if (op.i[PSLD_GN_AFFINE_ONLY]) {
+    gn_affine_kernel<<<N, 256, sh2, s>>>(part, ga0, be0, (float*)op.out[0], HW, C, G, nchunk_eff,
+                                        op.f[0]);
+    PSLD_CHECK_LAUNCH();
+    return PSLD_OK;
+  }
   // apply pass: pure streaming, ~16 KB of input per CTA
   const int vw = v8 ? 8 : 4;
   int nca = (int)ceil_div((int64_t)HW * (C / vw), 256 * 2 * GN_UNROLL);

@@ -13,7 +13,7 @@ KIND_NAMES = {L.OP_LAYOUT: "layout", L.OP_TEMB: "temb", L.OP_GN: "groupnorm", L.
 
 def op_name(op):
     if op.kind == L.OP_CONV:
-        return "conv_tc" if op.engine == L.ENGINE_TC else "conv_simt"
+        return {L.ENGINE_TC: "conv_tc", L.ENGINE_TC_GN: "conv_tc_gn"}.get(op.engine, "conv_simt")
     if op.kind == L.OP_ATTN:
         return "attn_tc" if op.engine == L.ENGINE_TC else "attn_simt"
     return KIND_NAMES.get(op.kind, "?")
@@ -37,7 +37,9 @@ def op_bytes(op, elt: int) -> float:
     i = op.i
     if op.kind == L.OP_GN:      # stats pass reads x, apply pass reads x and writes y
         n = i[L.GN_N] * i[L.GN_HW] * (i[L.GN_C1] + i[L.GN_C2])
-        return 3.0 * n * elt
+        if i[L.GN_AFFINE_ONLY]:
+            return (0.0 if op.inp[4] else 1.0) * n * elt
+        return (2.0 if op.inp[4] else 3.0) * n * elt
     if op.kind == L.OP_FIR:
         KH, up, down = i[L.FIR_KH], i[L.FIR_UP], i[L.FIR_DOWN]
         OH = (i[L.FIR_H] * up + i[L.FIR_PAD0] + i[L.FIR_PAD1] - KH) // down + 1

@@ -55,6 +55,7 @@ class Plan:
         self.engine_count = {"tc": 0, "simt": 0}
         self.mg = {}            # data_ptr of an activation -> its micro-group statistics tensor
         self.fused_stats = True
+        self.fuse_gn = True
         self.temb_op = -1
         self._build()
         self.n_ops = len(self.ops)
@@ -73,6 +74,23 @@ class Plan:
         if lst:
             return lst.pop()
         return self._new(*shape)
+
+    def _release_affine(self, t):
+        self.pool.setdefault(("aff",) + tuple(t.shape), []).append(t)
+
+    def _gn_fusable(self, x1, x2, cout):
+        """Host mirror of prepare_conv_gn_tc (csrc/conv_gn_tc.cu): can act(GroupNorm(x)) -> conv3x3
+        run as ONE kernel that normalises its input tile in shared memory?"""
+        import os
+        if not self.bf16 or not self.fuse_gn or os.environ.get("PSLD_TC_FUSE_GN", "1") == "0":
+            return False
+        N, H, W, C1 = x1.shape
+        C2 = x2.shape[-1] if x2 is not None else 0
+        if C1 % 64 or C2 % 64 or cout % 64 or (cout > 256 and cout % 256):
+            return False
+        if not ((W == 32 and H >= 4) or (W == 16 and H >= 8)) or (H & (H - 1)):
+            return False
+        return N * (H // (128 // W)) >= 2
 
     def _release(self, t):
         self.pool.setdefault(tuple(t.shape), []).append(t)
@@ -108,14 +126,21 @@ class Plan:
         op.inp[0], op.out[0] = src.data_ptr(), dst.data_ptr()
         self._push(op)
 
-    def op_gn(self, x1, x2, gn_mod, silu, HW):
-        """GroupNorm(+SiLU) over cat(x1, x2) -> new [B, HW.., C1+C2] buffer."""
+    def op_gn(self, x1, x2, gn_mod, silu, HW, affine_only=False):
+        """GroupNorm(+SiLU) over cat(x1, x2) -> new [B, HW.., C1+C2] buffer; with ``affine_only``
+        only the per-(sample, channel) (scale, shift) pair [B, C, 2] fp32 is produced, for a
+        convolution that normalises its input on load (PSLD_ENGINE_TC_GN)."""
         C1 = x1.shape[-1]
         C2 = x2.shape[-1] if x2 is not None else 0
         Cc = C1 + C2
         G = gn_mod.num_groups
         assert gn_mod.num_channels == Cc, (gn_mod.num_channels, Cc)
-        y = self._acquire(*x1.shape[:-1], Cc)
+        if affine_only:
+            key = ("aff", self.B, Cc, 2)
+            lst = self.pool.setdefault(key, [])
+            y = lst.pop() if lst else self._new(self.B, Cc, 2, dtype=torch.float32)
+        else:
+            y = self._acquire(*x1.shape[:-1], Cc)
         # stats pass: ~64 KB of input per CTA, but enough CTAs to fill 148 SMs at small batch
         per_img = HW * Cc * (2 if self.bf16 else 4)
         nchunk = max(-(-per_img // 65536), -(-592 // self.B))
@@ -124,6 +149,7 @@ class Plan:
         i = op.i
         i[L.GN_N], i[L.GN_HW], i[L.GN_C1], i[L.GN_C2], i[L.GN_G] = self.B, HW, C1, C2, G
         i[L.GN_SILU], i[L.GN_IN_DTYPE], i[L.GN_OUT_DTYPE], i[L.GN_NCHUNK] = int(silu), self.acode, self.acode, nchunk
+        i[L.GN_AFFINE_ONLY] = int(affine_only)
         op.f[0] = float(gn_mod.eps)
         op.inp[0] = x1.data_ptr()
         op.inp[1] = x2.data_ptr() if x2 is not None else None
@@ -165,7 +191,7 @@ class Plan:
 
     def op_conv(self, x1, x2, w_oihw, bias, *, ks, stride=1, pad=None, residual=None,
                 temb_off=-1, scale=1.0, out=None, in_nchw=False, out_nchw_f32=False,
-                hw=None, allow_tc=True, want_stats=True):
+                hw=None, allow_tc=True, want_stats=True, affine=None, gn_silu=True):
         """y = scale * (conv(cat(x1,x2), w) + bias + temb + residual); w is [Cout, Cin, ks, ks]."""
         pad = ks // 2 if pad is None else pad
         if in_nchw:
@@ -206,7 +232,24 @@ class Plan:
         op.out[0] = out.data_ptr()
         w = w_oihw.detach().to(self.dev, torch.float32)
         done = False
-        if self.bf16 and allow_tc and not in_nchw:
+        if affine is not None:
+            # GroupNorm(+SiLU) applied on load inside the tensor-core kernel
+            op.engine = L.ENGINE_TC_GN
+            op.inp[6] = affine.data_ptr()
+            i[L.CONV_GN_SILU] = int(gn_silu)
+            wt = self._w(w.permute(0, 2, 3, 1).reshape(Cout, -1), torch.bfloat16)
+            op.inp[4] = wt.data_ptr()
+            mg = None
+            if self.fused_stats and want_stats and (OH * OW) % 32 == 0:
+                mg = self._mg_buffer(N * OH * OW, Cout)
+                op.out[1] = mg.data_ptr()
+            if not self.dry:
+                L.check(self.lib.psld_op_prepare(C.byref(op)), "psld_op_prepare(conv_gn)")
+            if mg is not None:
+                self.mg[out.data_ptr()] = mg
+            self.engine_count["tc_gn"] = self.engine_count.get("tc_gn", 0) + 1
+            done = True
+        elif self.bf16 and allow_tc and not in_nchw:
             op.engine = L.ENGINE_TC
             cout_pad = Cout
             if out_nchw_f32 and Cout % 32:
@@ -288,6 +331,26 @@ class Plan:
         """ResnetBlockBigGANpp.forward (reference layerspp.py:242-274)."""
         net = self.net
         N, H, W, _ = x1.shape
+        scale = _SQRT1_2 if net.skip_rescale else 1.0
+        if not (m.up or m.down) and self._gn_fusable(x1, x2, m.out_ch):
+            # both act(GroupNorm_k(.)) -> Conv_k pairs run as GroupNorm-on-load convolutions:
+            # the statistics pass only emits a per-(sample, channel) affine, no apply pass
+            aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
+            h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
+            self._release_affine(aff0)
+            aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
+            if hasattr(m, "Conv_2"):
+                sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
+            else:
+                assert x2 is None
+                sc = x1
+            out = self.op_conv(h, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
+                               out=self._new(N, H, W, m.out_ch), affine=aff1)
+            self._release_affine(aff1)
+            self._release(h)
+            if hasattr(m, "Conv_2"):
+                self._release(sc)
+            return out
         a = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W)
         xs1, xs2 = x1, x2
         fir_tmp = []
@@ -317,7 +380,6 @@ class Plan:
         else:
             assert xs2 is None
             sc = xs1
-        scale = _SQRT1_2 if net.skip_rescale else 1.0
         out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
                            out=self._new(*b.shape[:-1], m.out_ch))
         self._release(b)

@@ -27,7 +27,7 @@ def run_op(op, prepare=False):
 
 def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=None, temb_off=0,
             temb_bstride=0, scale=1.0, engine=L.ENGINE_SIMT, out_nchw_f32=False, out=None,
-            mg_stats=False):
+            mg_stats=False, affine=None, gn_silu=True):
     """x*: NHWC tensors on cuda.  Returns (op, out, keepalive)."""
     N, H, W, C1 = x1.shape
     C2 = x2.shape[-1] if x2 is not None else 0
@@ -54,7 +54,7 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
     cout_k = Cout
     w = w_oihw.to(dev, torch.float32)
     b = bias.to(dev, torch.float32).contiguous() if bias is not None else None
-    if engine == L.ENGINE_TC:
+    if engine in (L.ENGINE_TC, L.ENGINE_TC_GN):
         if out_nchw_f32 and Cout % 32:
             cout_k = -(-Cout // 32) * 32
         wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
@@ -80,6 +80,10 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
     op.inp[4] = wp.data_ptr()
     op.inp[5] = b.data_ptr() if b is not None else None
     op.out[0] = out.data_ptr()
+    if affine is not None:
+        op.inp[6] = affine.data_ptr()
+        i[L.CONV_GN_SILU] = int(gn_silu)
+        keep.append(affine)
     if mg_stats:
         mg = torch.full((N * OH * OW // 32, Cout // 4, 2), float("nan"), dtype=torch.float32, device=dev)
         op.out[1] = mg.data_ptr()

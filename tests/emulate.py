@@ -68,6 +68,18 @@ def run_plan(plan, x, t):
                     assert st is not None and tuple(st.shape) == tuple(ref.shape), (st.shape, ref.shape)
                     # bf16 plans: the producer summed unrounded fp32 values, tolerate the rounding
                     assert float((st - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
+            if i[L.GN_AFFINE_ONLY]:
+                xn = xx.permute(0, 3, 1, 2)
+                Bn, Cn = xn.shape[:2]
+                G = i[L.GN_G]
+                v = xn.reshape(Bn, G, -1).double()
+                mean, var = v.mean(-1), v.var(-1, unbiased=False)
+                rstd = 1.0 / torch.sqrt(var + f[0])
+                cpg = Cn // G
+                sc = rstd.repeat_interleave(cpg, 1) * g(op.inp[2]).double()[None]
+                sh = g(op.inp[3]).double()[None] - mean.repeat_interleave(cpg, 1) * sc
+                g(op.out[0]).copy_(torch.stack([sc, sh], -1).float())
+                continue
             if i[L.GN_SILU]:
                 y = F.silu(y)
             g(op.out[0]).copy_(y.permute(0, 2, 3, 1))
@@ -84,8 +96,14 @@ def run_plan(plan, x, t):
             assert i[L.CONV_IN_LAYOUT] == L.NHWC
             xx = _f(x1) if x2 is None else torch.cat([_f(x1), _f(x2)], -1)
             assert xx.shape[-1] == Cin
+            if op.engine == L.ENGINE_TC_GN:      # GroupNorm(+SiLU) applied on load, bf16-rounded
+                aff = g(op.inp[6])
+                xx = xx * aff[:, None, None, :, 0] + aff[:, None, None, :, 1]
+                if i[L.CONV_GN_SILU]:
+                    xx = F.silu(xx)
+                xx = xx.to(torch.bfloat16).float()
             w = _f(g(op.inp[4]))
-            if op.engine == L.ENGINE_TC:
+            if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN):
                 w = w.reshape(cout, ks, ks, Cin).permute(0, 3, 1, 2)
             else:
                 w = w.reshape(ks, ks, Cin, cout).permute(3, 2, 0, 1)

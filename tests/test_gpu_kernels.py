@@ -330,6 +330,38 @@ def test_conv_tc_stride2(case):
     assert err <= 4e-3, err
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 0, 64), (3, 32, 32, 256, 0, 256), (2, 16, 16, 128, 128, 256),
+                                  (5, 16, 16, 256, 0, 128), (1, 32, 32, 256, 128, 256)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_conv_gn_fused(case, silu):
+    """GroupNorm(+SiLU)-on-load 3x3 conv (PSLD_ENGINE_TC_GN): per-(sample, channel) affine + SiLU
+    applied to the raw tile in shared memory, three shifted operand variants, 2-CTA MMA."""
+    N, H, W, C1, C2, Cout = case
+    r = _rng(sum(case) + 5)
+    x1 = _t(r.standard_normal((N, H, W, C1)) * 1.7 + 0.3, torch.bfloat16)
+    x2 = _t(r.standard_normal((N, H, W, C2)) * 0.6 - 0.2, torch.bfloat16) if C2 else None
+    Cin = C1 + C2
+    w = _t(r.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9))
+    b = _t(0.1 * r.standard_normal(Cout))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cin)), 0.2 * r.standard_normal((N, Cin))], -1))
+    res = _t(r.standard_normal((N, H, W, Cout)), torch.bfloat16)
+    temb = _t(r.standard_normal((N, Cout)))
+    kw = dict(residual=res, temb=temb, temb_off=0, temb_bstride=Cout, scale=0.7071)
+    op, out, keep = conv_op(x1, x2, w, b, engine=L.ENGINE_TC_GN, mg_stats=True, affine=aff, gn_silu=silu, **kw)
+    run_op(op, prepare=True)
+    xx = x1.float().cpu() if x2 is None else torch.cat([x1.float().cpu(), x2.float().cpu()], -1)
+    a = xx * aff.cpu()[:, None, None, :, 0] + aff.cpu()[:, None, None, :, 1]
+    if silu:
+        a = F.silu(a)
+    a = a.to(torch.bfloat16)
+    ref = conv_ref(a, None, w.to(torch.bfloat16), b, **kw)
+    err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
+    assert err <= 6e-3, err       # bf16 output rounding + tanh-form SiLU before the bf16 rounding of A
+    mg = keep[-1]
+    mref = mg_ref(ref.permute(0, 2, 3, 1))
+    assert float((mg.double().cpu() - mref).abs().max()) <= 5e-3 * float(mref.abs().max())
+
+
 def test_conv_tc_output_head():
     """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
     r = _rng(77)
