@@ -16,8 +16,8 @@
 // W = 16, 32), so no tap needs its own load.  L2->SM traffic for A drops from 9 x 16 KB to 24 KB
 // per chunk; weights stream per tap through a 3-stage ring (half tile per CTA, as in conv_tc).
 //
-// Warps (480 threads): 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator,
-// 2..9 = epilogue (shared with conv_tc), 10 = weight TMA, 11..14 = transform.
+// Warps (640 threads): 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator,
+// 2 = weight TMA, 3 idle, 4..11 = epilogue (shared with conv_tc), 12..19 = transform.
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -30,7 +30,8 @@
 
 namespace psld {
 
-constexpr int GN_THREADS = 480;
+constexpr int GN_TRANSFORM_WARPS = 8;
+constexpr int GN_THREADS = (12 + GN_TRANSFORM_WARPS) * 32;   // 640 = 5 warpgroups
 constexpr int GN_B_STAGES = 3;
 constexpr int GN_B_BYTES = 128 * 128;            // half weight tile per CTA (<= 128 rows x 128 B)
 constexpr int GN_MAX_ROWS = 192;                 // (BH+2)*W: 6x32 or 10x16
@@ -114,6 +115,9 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // (setmaxnreg re-balancing between the warpgroups was tried: ptxas lowers the budget of the
+  // .dec branches but does not raise the epilogue's above the launch-bound value, so it only
+  // added spills; all warps keep the launch allocation.)
   const int b_rows = p.block_n >> 1;
   const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
 
@@ -136,7 +140,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2) {
     // ===================== weight producer (half tile per CTA, credited to the leader) ======
     if (lane == 0) {
       int stage = 0;
@@ -193,13 +197,18 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 11) {
+  } else if (warp >= 12) {
     // ===================== transform warps: GroupNorm + SiLU, three shifted operand tiles =====
-    const int tt = (int)threadIdx.x - 11 * 32;      // 0..127
+    constexpr int TT = GN_TRANSFORM_WARPS * 32;     // transform threads
+    constexpr int RSTEP = TT / 8;                   // rows covered per pass
+    constexpr int ITEMS = (GN_MAX_ROWS + RSTEP - 1) / RSTEP;
+    const int tt = (int)threadIdx.x - 12 * 32;      // 0..TT-1
     const int j = tt & 7;                           // 16-byte chunk = channels 8j .. 8j+7
-    const int r0 = tt >> 3;                         // rows r0, r0+16, ...
+    const int r0 = tt >> 3;                         // rows r0, r0+RSTEP, ...
     const uint32_t leader_ready0 = mapa_rank(a_ready(0), 0);
     const int Wm = p.W - 1;
+    const uint32_t sm0 = smem_u32(smem_raw);
+    auto sptr = [&](uint32_t a) { return reinterpret_cast<uint4*>(smem_raw + (a - sm0)); };
     int buf = 0;
     uint32_t ph = 0;
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
@@ -209,6 +218,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const bool img_ok = n0 < gp.n_images;
       for (int cc = 0; cc < p.kchunks; ++cc) {
         float sc[8], sh[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sc[q] = 0.f; sh[q] = 0.f; }
         if (img_ok) {
           const float4* ap = reinterpret_cast<const float4*>(
               gp.affine + ((int64_t)n0 * gp.cin + cc * TC_BLOCK_K + j * 8) * 2);
@@ -220,58 +231,62 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
         mbar_wait(raw_full(buf), ph);
         const uint32_t L = abuf(buf), Cc = L + GN_VAR_BYTES, R = Cc + GN_VAR_BYTES;
-        for (int r = r0; r < gp.rows_in; r += 16) {
-          const int x = r & Wm;
+        // all of this thread's rows at once: independent load -> normalise -> store chains
+        uint4 t[ITEMS];
+        bool inb[ITEMS], valid[ITEMS];
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+          const int r = r0 + RSTEP * u;
+          inb[u] = r < gp.rows_in;
           const int gy = y0 + (r >> gp.w_shift);
-          const bool valid = img_ok && gy >= 0 && gy < p.H;
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
-          if (valid) {
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(Cc + off) : "memory");
+          valid[u] = inb[u] && img_ok && gy >= 0 && gy < p.H;
+          t[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (valid[u]) t[u] = *sptr(Cc + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+          if (valid[u]) {
+            uint32_t* ww = reinterpret_cast<uint32_t*>(&t[u]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[q]));
               float a = fmaf(f.x, sc[2 * q], sh[2 * q]);
               float b = fmaf(f.y, sc[2 * q + 1], sh[2 * q + 1]);
               if (gp.silu) { a = silu_fast(a); b = silu_fast(b); }
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              w[q] = *reinterpret_cast<uint32_t*>(&h);
+              ww[q] = *reinterpret_cast<uint32_t*>(&h);
             }
           }
-          // centre: t(y, x)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(Cc + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-          // left variant: row (y, x+1) <- t(y, x);  column 0 <- 0
-          if (x < Wm) {
+        }
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+          if (!inb[u]) continue;
+          const int r = r0 + RSTEP * u;
+          const int x = r & Wm;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          *sptr(Cc + off) = t[u];                                    // centre: t(y, x)
+          if (x < Wm) {                                              // left variant: (y, x+1) <- t(y, x)
             const int rn = r + 1;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(L + (uint32_t)rn * 128u + (uint32_t)((j ^ (rn & 7)) << 4)), "r"(w[0]),
-                           "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            *sptr(L + (uint32_t)rn * 128u + (uint32_t)((j ^ (rn & 7)) << 4)) = t[u];
           }
-          if (x == 0)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(L + off), "r"(0u) : "memory");
-          // right variant: row (y, x-1) <- t(y, x);  column W-1 <- 0
-          if (x > 0) {
+          if (x == 0) *sptr(L + off) = make_uint4(0u, 0u, 0u, 0u);    // left image edge
+          if (x > 0) {                                               // right variant: (y, x-1) <- t(y, x)
             const int rp = r - 1;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(R + (uint32_t)rp * 128u + (uint32_t)((j ^ (rp & 7)) << 4)), "r"(w[0]),
-                           "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            *sptr(R + (uint32_t)rp * 128u + (uint32_t)((j ^ (rp & 7)) << 4)) = t[u];
           }
-          if (x == Wm)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(R + off), "r"(0u) : "memory");
+          if (x == Wm) *sptr(R + off) = make_uint4(0u, 0u, 0u, 0u);   // right image edge
         }
         // generic-proxy writes -> visible to the tensor core (async proxy), then tell the leader
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(GN_TRANSFORM_WARPS * 32) : "memory");
         if (tt == 0) mbar_arrive_remote(leader_ready0 + 8u * (uint32_t)buf);
         if (++buf == 2) { buf = 0; ph ^= 1; }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9), shared with conv_tc =====================
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..11), shared with conv_tc =====================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 4) >> 2;
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -280,8 +295,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      tc_epilogue_tile(p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
-                       stg_base + (uint32_t)(warp - 2) * 4096u);
+      tc_epilogue_tile<true>(p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+                       stg_base + (uint32_t)(warp - 4) * 4096u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tempty0 + 8u * (uint32_t)acc);

@@ -135,6 +135,9 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc
 // NCHW network head) + GroupNorm micro-group statistics.  Called by the 8 epilogue warps;
 // `quarter` = TMEM lane quarter (warp id % 4), `half` selects alternate column groups, `stg` =
 // this warp's 4 KB staging tile in shared memory.
+// kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
+// processed (32 registers; off for kernels that are short of registers).
+template <bool kPrefetchRes = true>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
                                                  int lane, uint32_t stg) {
@@ -162,9 +165,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         if (mr < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + mr * p.Cout);
       }
     };
-    if (p.res && half < ncg) load_res(half);
+    if (kPrefetchRes && p.res && half < ncg) load_res(half);
     for (int cg = half; cg < ncg; cg += 2) {
       const int co_base = n_tile * p.block_n + cg * 64;
+      if (!kPrefetchRes && p.res) load_res(cg);
       if (p.res) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -174,7 +178,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
                        ::"r"(a), "r"(rq[it].x), "r"(rq[it].y), "r"(rq[it].z), "r"(rq[it].w) : "memory");
         }
         __syncwarp();
-        if (cg + 2 < ncg) load_res(cg + 2);
+        if (kPrefetchRes && cg + 2 < ncg) load_res(cg + 2);
       }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {

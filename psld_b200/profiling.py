@@ -74,7 +74,8 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
         if op.kind == L.OP_CONV:
             i = op.i
             key = f"{op_name(op)} {i[L.CONV_OH]}x{i[L.CONV_OW]} {i[L.CONV_C1] + i[L.CONV_C2]}->" \
-                  f"{i[L.CONV_COUT]} k{i[L.CONV_KS]}s{i[L.CONV_STRIDE]}"
+                  f"{i[L.CONV_COUT]} k{i[L.CONV_KS]}s{i[L.CONV_STRIDE]}" \
+                  f"{'+res' if op.inp[2] else ''}{'+temb' if op.inp[3] else ''}"
             c = classes.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
             c["ms"] += acc[k] / iters
             c["n"] += 1

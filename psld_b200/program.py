@@ -56,6 +56,7 @@ class Plan:
         self.mg = {}            # data_ptr of an activation -> its micro-group statistics tensor
         self.fused_stats = True
         self.fuse_gn = True
+        self.fuse_gn_residual = False   # also fuse GroupNorm_1 into Conv_1 (residual epilogue)
         self.temb_op = -1
         self._build()
         self.n_ops = len(self.ops)
@@ -333,21 +334,30 @@ class Plan:
         N, H, W, _ = x1.shape
         scale = _SQRT1_2 if net.skip_rescale else 1.0
         if not (m.up or m.down) and self._gn_fusable(x1, x2, m.out_ch):
-            # both act(GroupNorm_k(.)) -> Conv_k pairs run as GroupNorm-on-load convolutions:
-            # the statistics pass only emits a per-(sample, channel) affine, no apply pass
+            # act(GroupNorm_0(.)) -> Conv_0 runs as ONE GroupNorm-on-load convolution: the
+            # statistics pass only emits a per-(sample, channel) affine, there is no apply pass.
+            # (Conv_1 keeps the separate apply: measured, the fused kernel loses more on its
+            # residual epilogue - 96 registers per thread with 640 threads - than the apply costs.)
             aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
-            aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
+            if self.fuse_gn_residual and self._gn_fusable(h, None, m.out_ch):
+                aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
+                b, b_aff = h, aff1
+            else:
+                b = self.op_gn(h, None, m.GroupNorm_1, True, H * W)
+                self._release(h)
+                b_aff = None
             if hasattr(m, "Conv_2"):
                 sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
             else:
                 assert x2 is None
                 sc = x1
-            out = self.op_conv(h, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
-                               out=self._new(N, H, W, m.out_ch), affine=aff1)
-            self._release_affine(aff1)
-            self._release(h)
+            out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
+                               out=self._new(N, H, W, m.out_ch), affine=b_aff)
+            if b_aff is not None:
+                self._release_affine(b_aff)
+            self._release(b)
             if hasattr(m, "Conv_2"):
                 self._release(sc)
             return out
