@@ -281,22 +281,33 @@ def main_b200(args):
     prof = profile_plan(plan, iters=max(1, args.profile_ops)) if args.profile_ops > 0 else {}
     conv_classes = prof.pop("_conv_classes", {})
     roof = None
-    if "conv_tc" in prof:
-        c = prof["conv_tc"]
+    tc_names = [k for k in ("conv_tc", "conv_tc_gn") if k in prof]
+    if tc_names:
+        # the tcgen05 implicit-GEMM convolution family (plain + GroupNorm-on-load variant)
+        c = {"flops": sum(prof[k]["flops"] for k in tc_names), "ms": sum(prof[k]["ms"] for k in tc_names),
+             "n": sum(prof[k]["n"] for k in tc_names)}
+        c["launch_ms"] = c["ms"] / c["n"]
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
         traffic, tsrc = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and B == 256 and args.workload == "cifar10":
             tj = json.load(open(tp))
-            traffic = tj["kernels"].get("conv_tc_kernel", {}).get("traffic_bytes_per_launch")
-            tsrc = tj["source"]
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, bf16)",
+            ks = [tj["kernels"][k] for k in ("conv_tc_kernel", "conv_gn_tc_kernel") if k in tj["kernels"]]
+            if ks:
+                traffic = sum(k["traffic_bytes_per_launch"] * k["launches"] for k in ks) / sum(k["launches"] for k in ks)
+                tsrc = tj["source"]
+        roof = {"bound": "tensor",
+                "kernel": "conv_tc_kernel + conv_gn_tc_kernel (tcgen05 implicit-GEMM convolutions, bf16)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                "frac": ach / pk["tf_sustained"], "traffic": traffic,
+                "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
                 "traffic_source": tsrc, "algorithmic_flop_per_launch": c["flops"] / c["n"],
                 "peak_source": pk["src"] + ", sustained",
                 "launches_per_step": c["n"], "avg_launch_ms": c["launch_ms"],
-                "share_of_step": c["ms"] / sum(v["ms"] for v in prof.values())}
+                "share_of_step": c["ms"] / sum(v["ms"] for v in prof.values()),
+                "per_kernel": {k: {"ms": round(prof[k]["ms"], 3), "launches": prof[k]["n"],
+                                   "tflops": round(prof[k]["flops"] / (prof[k]["ms"] * 1e-3) / 1e12, 1)}
+                               for k in tc_names}}
     elif "conv_simt" in prof:
         c = prof["conv_simt"]
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12

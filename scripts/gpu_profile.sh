@@ -3,7 +3,7 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0"
+B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0 --no-graph"
 # warm-up = 1 + 3*(launches+1) launches; capture the single timed step after it
 SKIP=${SKIP:-1342}
 CNT=${CNT:-450}

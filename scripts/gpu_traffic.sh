@@ -3,7 +3,7 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0"
+B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0 --no-graph"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -s ${SKIP:-1342} -c ${CNT:-450} --csv --log-file gpurun_out/traffic.csv $B > gpurun_out/ncu_traffic.log 2>&1
 echo "traffic rc=$?"

@@ -82,3 +82,31 @@ def test_module_contract():
     assert torch.equal(net(x, t), twin(x, t))
     with pytest.raises(RuntimeError):
         net(x.cpu(), t.cpu())
+
+
+@pytest.mark.parametrize("sf,B,precision,tol", [
+    (dict(nf=48, ch_mult=[1, 2], num_res_blocks=1), 3, "bf16", 3e-2),     # channels 48/96: SIMT fallbacks in a bf16 plan
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 5, "bf16", 3e-2),  # 8x8 level, 2 images per tile, odd batch
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 1, "bf16", 3e-2),  # single sample (single-tile layers)
+    (dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, fir=False, progressive_input="none",
+          embedding_type="positional"), 2, "fp32", 2e-5),                 # ablation-script architecture flags
+    (dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, fir=False, progressive_input="none",
+          embedding_type="positional"), 2, "bf16", 3e-2),
+    (dict(nf=32, ch_mult=[1, 2], num_res_blocks=1, out_ch=3), 2, "fp32", 2e-5),   # score_m nets (out_ch = C)
+])
+def test_forward_odd_configs_vs_oracle(sf, B, precision, tol):
+    """Shapes outside the tensor-core sweet spot, odd batches and the non-default architecture
+    switches go through the same program (with CUDA-core fallbacks) and match the oracle."""
+    from psld_b200 import make_config
+    sf = dict(sf, init_scale=1.0)
+    cfg = make_config(score_fn=sf)
+    net, sd = make_net(cfg, precision)
+    r = np.random.default_rng(B)
+    x = torch.from_numpy(r.standard_normal((B, 6, 32, 32)).astype(np.float32))
+    t = torch.from_numpy(r.uniform(0.01, 1.0, B).astype(np.float32))
+    y = net(x.cuda(), t.cuda())
+    torch.cuda.synchronize()
+    ref = O.ncsnpp_forward(cfg, sd, x, t)
+    err = rel_l2(y, ref)
+    print(f"odd config {sf} B={B} {precision}: rel-L2 {err:.3e} engines {net.plan(B, B, False).engine_count}")
+    assert err <= tol, err
