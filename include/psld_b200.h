@@ -215,6 +215,10 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
  *   up_or_down_sampling.py:178; epilogue terms layerspp.py:262-274,88-91, ncsnpp.py:353-356)
  *   in[0] = x1, in[1] = x2 or NULL, in[2] = residual [N,OH,OW,Cout] or NULL,
  *   in[3] = temb proj (f32) or NULL, in[4] = weight, in[5] = bias f32 [Cout] or NULL
+ *   in[6], in[7] = (engine PSLD_ENGINE_TC, i[EXT_C1] > 0) a second input cat(e1, e2) [N,OH,OW,EXT_C1+EXT_C2]
+ *           whose 1x1 convolution is accumulated into the same output tile: y = scale*(conv(x,W) +
+ *           conv1x1(e, We) + bias + ...); the weight is then [Cout, K + EXT_C1 + EXT_C2] with the
+ *           1x1 part appended along K (ResnetBlockBigGANpp's Conv_2 shortcut, layerspp.py:269-274)
  *   in[6] = (engine PSLD_ENGINE_TC_GN) fp32 [N, Cin, 2] (scale, shift) produced by a PSLD_OP_GN
  *           in affine-only mode: the conv input is silu?(x * scale + shift), applied in-kernel
  *           (i[GN_SILU] selects the SiLU); x1/x2 are then the RAW, un-normalised tensors
@@ -227,7 +231,8 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
 enum { PSLD_CONV_N = 0, PSLD_CONV_H, PSLD_CONV_W, PSLD_CONV_C1, PSLD_CONV_C2, PSLD_CONV_COUT,
        PSLD_CONV_KS, PSLD_CONV_STRIDE, PSLD_CONV_PAD, PSLD_CONV_OH, PSLD_CONV_OW,
        PSLD_CONV_IN_LAYOUT, PSLD_CONV_OUT_LAYOUT, PSLD_CONV_IN_DTYPE, PSLD_CONV_OUT_DTYPE,
-       PSLD_CONV_RES_DTYPE, PSLD_CONV_TEMB_OFF, PSLD_CONV_TEMB_BSTRIDE, PSLD_CONV_GN_SILU };
+       PSLD_CONV_RES_DTYPE, PSLD_CONV_TEMB_OFF, PSLD_CONV_TEMB_BSTRIDE, PSLD_CONV_GN_SILU,
+       PSLD_CONV_EXT_C1, PSLD_CONV_EXT_C2 };
 
 /* --- PSLD_OP_ATTN (AttnBlockpp core, layerspp.py:82-86): single head over HW tokens.
  *   in[0] = qkv [N, HW, 3C] (q | k | v along the last axis) ; out[0] = o [N, HW, C]

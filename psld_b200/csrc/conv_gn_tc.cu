@@ -407,6 +407,7 @@ int prepare_conv_gn_tc(psld_op& op) {
   p.BH = BH; p.BN_img = 1; p.tiles_y = H / BH;
   p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
   p.taps = 9; p.KS = 3;
+  p.ext_kchunks1 = 0; p.ext_kchunks = 0;
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * H * W;
   p.num_tiles = (int)(((m_tiles + 1) / 2) * p.n_tiles_n);

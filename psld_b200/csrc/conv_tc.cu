@@ -40,7 +40,7 @@
 namespace psld {
 
 struct ConvTcState {
-  CUtensorMap a1, a2, b;
+  CUtensorMap a1, a2, b, e1, e2;
   ConvTcParams p;
   int grid;
   bool pair;      // 2-CTA (cta_group::2) variant
@@ -49,7 +49,8 @@ struct ConvTcState {
 template <bool kPair>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmE1,
+               const __grid_constant__ CUtensorMap tmE2, const ConvTcParams p) {
   using Cfg = TcCfg<kPair>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -101,7 +102,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_kb = p.taps * p.kchunks;
+  // K = taps x input channels, optionally followed by a 1x1 "extension" over a second input
+  // (the residual block's Conv_2 shortcut accumulated into the same tile, layerspp.py:269-274)
+  const int total_kb = p.taps * p.kchunks + p.ext_kchunks;
   const int b_rows = kPair ? (p.block_n >> 1) : p.block_n;        // weight rows this CTA loads
 
   if (warp == 0 || warp == 10) {
@@ -140,6 +143,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
+        }
+        for (int cc = 0; cc < p.ext_kchunks; ++cc, ++kb) {    // shortcut input, centre tap only
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
+          if (is_a) {
+            const CUtensorMap* tmE = cc < p.ext_kchunks1 ? &tmE1 : &tmE2;
+            const int c0 = (cc < p.ext_kchunks1 ? cc : cc - p.ext_kchunks1) * TC_BLOCK_K;
+            if (kPair) tma_load_4d_pair(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+            else tma_load_4d(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+          } else {
+            if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+            else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -329,7 +347,19 @@ int prepare_conv_tc(psld_op& op) {
   if (rc == PSLD_OK)
     rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, OW, BH, BN_img, stride)
                 : encode_act_map(&st->a2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
-  const int K = KS * KS * (C1 + C2);
+  const int E1 = op.i[PSLD_CONV_EXT_C1], E2 = op.i[PSLD_CONV_EXT_C2];
+  const bool ext = op.in[6] != nullptr && E1 > 0;
+  if (ext && (stride != 1 || E1 % TC_BLOCK_K || E2 % TC_BLOCK_K || (E2 > 0 && !op.in[7]))) {
+    delete st;
+    return unsupported("1x1 extension needs stride 1 and channel counts %% 64 == 0");
+  }
+  if (rc == PSLD_OK)
+    rc = ext ? encode_act_map(&st->e1, op.in[6], N, OH, OW, E1, OW, BH, BN_img, 1)
+             : encode_act_map(&st->e1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+  if (rc == PSLD_OK)
+    rc = (ext && E2 > 0) ? encode_act_map(&st->e2, op.in[7], N, OH, OW, E2, OW, BH, BN_img, 1)
+                         : encode_act_map(&st->e2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+  const int K = KS * KS * (C1 + C2) + (ext ? E1 + E2 : 0);
   if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, pair ? block_n / 2 : block_n);
   if (rc != PSLD_OK) { delete st; return rc; }
 
@@ -354,6 +384,8 @@ int prepare_conv_tc(psld_op& op) {
   p.BH = BH; p.BN_img = BN_img; p.tiles_y = OH / BH;
   p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
   p.taps = KS * KS; p.KS = KS;
+  p.ext_kchunks1 = ext ? E1 / TC_BLOCK_K : 0;
+  p.ext_kchunks = ext ? (E1 + E2) / TC_BLOCK_K : 0;
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * OH * OW;
   const int64_t m_tiles = (int64_t)((N + BN_img - 1) / BN_img) * p.tiles_y;
@@ -409,10 +441,11 @@ int run_conv_tc(const psld_op& op, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, st->a1, st->a2, st->b, st->p));
+    PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, st->a1, st->a2, st->b, st->e1,
+                                       st->e2, st->p));
   } else {
-    conv_tc_kernel<false><<<st->grid, TC_THREADS, TcCfg<false>::kSmemBytes, s>>>(st->a1, st->a2,
-                                                                                 st->b, st->p);
+    conv_tc_kernel<false><<<st->grid, TC_THREADS, TcCfg<false>::kSmemBytes, s>>>(
+        st->a1, st->a2, st->b, st->e1, st->e2, st->p);
   }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;

@@ -35,6 +35,7 @@ struct ConvTcParams {
   int tiles_y;               // H / BH
   int kchunks1, kchunks;     // 64-channel chunks in source 1 / in total (C1+C2)/64
   int taps, KS;
+  int ext_kchunks1, ext_kchunks;   // 64-channel chunks of the fused 1x1 shortcut input (0 = none)
   int block_n, n_tiles_n;
   int num_tiles;
   int64_t M;                 // N*H*W

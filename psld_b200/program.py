@@ -57,6 +57,7 @@ class Plan:
         self.fused_stats = True
         self.fuse_gn = True
         self.fuse_gn_residual = False   # also fuse GroupNorm_1 into Conv_1 (residual epilogue)
+        self.fuse_shortcut = True       # Conv_2 (1x1 shortcut) as extra K-blocks of Conv_1
         self.temb_op = -1
         self._build()
         self.n_ops = len(self.ops)
@@ -92,6 +93,17 @@ class Plan:
         if not ((W == 32 and H >= 4) or (W == 16 and H >= 8)) or (H & (H - 1)):
             return False
         return N * (H // (128 // W)) >= 2
+
+    def _ext_fusable(self, b, e1, e2, cout):
+        """Can Conv_2 (1x1 shortcut over e = cat(e1, e2)) ride along Conv_1's MMA stream?"""
+        if not self.bf16 or not self.fuse_shortcut:
+            return False
+        N, H, W, Cb = b.shape
+        E1 = e1.shape[-1]
+        E2 = e2.shape[-1] if e2 is not None else 0
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        return (Cb % 64 == 0 and E1 % 64 == 0 and E2 % 64 == 0 and cout % 32 == 0 and pow2(W)
+                and pow2(H) and 4 <= W <= 128 and tuple(e1.shape[:3]) == (N, H, W))
 
     def _release(self, t):
         self.pool.setdefault(tuple(t.shape), []).append(t)
@@ -192,7 +204,7 @@ class Plan:
 
     def op_conv(self, x1, x2, w_oihw, bias, *, ks, stride=1, pad=None, residual=None,
                 temb_off=-1, scale=1.0, out=None, in_nchw=False, out_nchw_f32=False,
-                hw=None, allow_tc=True, want_stats=True, affine=None, gn_silu=True):
+                hw=None, allow_tc=True, want_stats=True, affine=None, gn_silu=True, ext=None):
         """y = scale * (conv(cat(x1,x2), w) + bias + temb + residual); w is [Cout, Cin, ks, ks]."""
         pad = ks // 2 if pad is None else pad
         if in_nchw:
@@ -256,6 +268,19 @@ class Plan:
             if out_nchw_f32 and Cout % 32:
                 cout_pad = -(-Cout // 32) * 32       # zero rows; the epilogue writes Cout planes
             wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+            if ext is not None:
+                # fused 1x1 shortcut: its weight is appended along K, its input becomes a second
+                # A source (centre tap), its bias joins the conv bias
+                e1, e2, we, be = ext
+                wt = torch.cat([wt, we.detach().to(self.dev, torch.float32).reshape(Cout, -1)], 1)
+                op.inp[6] = e1.data_ptr()
+                op.inp[7] = e2.data_ptr() if e2 is not None else None
+                i[L.CONV_EXT_C1] = e1.shape[-1]
+                i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
+                if be is not None:
+                    b32 = self._w((bias.detach().to(self.dev, torch.float32) if bias is not None else 0) +
+                                  be.detach().to(self.dev, torch.float32))
+                    op.inp[5] = b32.data_ptr()
             if cout_pad != Cout:
                 wt = torch.cat([wt, wt.new_zeros(cout_pad - Cout, wt.shape[1])], 0)
                 if b32 is not None:
@@ -282,6 +307,10 @@ class Plan:
             elif rc != L.EUNSUPPORTED:
                 L.check(rc, "psld_op_prepare(conv)")
             else:
+                if ext is not None:
+                    raise RuntimeError("psld_b200: fused 1x1 shortcut requested for a conv the "
+                                       "tensor-core engine rejected: " +
+                                       self.lib.psld_last_error().decode(errors="replace"))
                 i[L.CONV_COUT] = Cout
                 if bias is not None:
                     op.inp[5] = self._w(bias).data_ptr()
@@ -348,17 +377,21 @@ class Plan:
                 b = self.op_gn(h, None, m.GroupNorm_1, True, H * W)
                 self._release(h)
                 b_aff = None
+            ext, sc = None, None
             if hasattr(m, "Conv_2"):
-                sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
+                if b_aff is None and self._ext_fusable(b, x1, x2, m.out_ch):
+                    ext = (x1, x2, m.Conv_2.weight, m.Conv_2.bias)
+                else:
+                    sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
             else:
                 assert x2 is None
                 sc = x1
             out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
-                               out=self._new(N, H, W, m.out_ch), affine=b_aff)
+                               out=self._new(N, H, W, m.out_ch), affine=b_aff, ext=ext)
             if b_aff is not None:
                 self._release_affine(b_aff)
             self._release(b)
-            if hasattr(m, "Conv_2"):
+            if hasattr(m, "Conv_2") and sc is not None:
                 self._release(sc)
             return out
         a = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W)
@@ -385,15 +418,19 @@ class Plan:
         self._release(a)
         b = self.op_gn(h, None, m.GroupNorm_1, True, h.shape[1] * h.shape[2])
         self._release(h)
+        ext, sc = None, None
         if hasattr(m, "Conv_2"):
-            sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
+            if self._ext_fusable(b, xs1, xs2, m.out_ch):
+                ext = (xs1, xs2, m.Conv_2.weight, m.Conv_2.bias)
+            else:
+                sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
         else:
             assert xs2 is None
             sc = xs1
         out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
-                           out=self._new(*b.shape[:-1], m.out_ch))
+                           out=self._new(*b.shape[:-1], m.out_ch), ext=ext)
         self._release(b)
-        if hasattr(m, "Conv_2"):
+        if hasattr(m, "Conv_2") and sc is not None:
             self._release(sc)
         for t in fir_tmp:
             self._release(t)

@@ -27,7 +27,7 @@ def run_op(op, prepare=False):
 
 def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=None, temb_off=0,
             temb_bstride=0, scale=1.0, engine=L.ENGINE_SIMT, out_nchw_f32=False, out=None,
-            mg_stats=False, affine=None, gn_silu=True):
+            mg_stats=False, affine=None, gn_silu=True, ext=None):
     """x*: NHWC tensors on cuda.  Returns (op, out, keepalive)."""
     N, H, W, C1 = x1.shape
     C2 = x2.shape[-1] if x2 is not None else 0
@@ -62,6 +62,14 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
             wt = torch.cat([wt, wt.new_zeros(cout_k - Cout, wt.shape[1])], 0)
             if b is not None:
                 b = torch.cat([b, b.new_zeros(cout_k - Cout)])
+        if ext is not None:      # (e1, e2, w_ext [Cout, E, 1, 1]): fused 1x1 shortcut
+            e1, e2, we = ext
+            wt = torch.cat([wt, we.to(dev, torch.float32).reshape(Cout, -1)], 1)
+            op.inp[6] = e1.data_ptr()
+            op.inp[7] = e2.data_ptr() if e2 is not None else None
+            i[L.CONV_EXT_C1] = e1.shape[-1]
+            i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
+            keep += [e1, e2]
         wp = wt.to(torch.bfloat16).contiguous()
         i[L.CONV_COUT] = cout_k
         op.f[1] = float(Cout)

@@ -103,6 +103,14 @@ def run_plan(plan, x, t):
                     xx = F.silu(xx)
                 xx = xx.to(torch.bfloat16).float()
             w = _f(g(op.inp[4]))
+            w_ext, x_ext = None, None
+            if op.engine == L.ENGINE_TC and i[L.CONV_EXT_C1] > 0:    # fused 1x1 shortcut (K-extension)
+                ne = i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]
+                w_ext = w[:, ks * ks * Cin:].reshape(cout, ne, 1, 1)
+                w = w[:, : ks * ks * Cin]
+                e1, e2 = g(op.inp[6]), g(op.inp[7])
+                x_ext = _f(e1) if e2 is None else torch.cat([_f(e1), _f(e2)], -1)
+                assert x_ext.shape[-1] == ne
             if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN):
                 w = w.reshape(cout, ks, ks, Cin).permute(0, 3, 1, 2)
             else:
@@ -110,6 +118,8 @@ def run_plan(plan, x, t):
             bias = g(op.inp[5])
             y = F.conv2d(xx.permute(0, 3, 1, 2), w, bias, stride=i[L.CONV_STRIDE], padding=i[L.CONV_PAD])
             assert y.shape[2] == i[L.CONV_OH] and y.shape[3] == i[L.CONV_OW]
+            if w_ext is not None:
+                y = y + F.conv2d(x_ext.permute(0, 3, 1, 2), w_ext)
             if op.inp[3]:
                 tp = g(op.inp[3])
                 off = i[L.CONV_TEMB_OFF]

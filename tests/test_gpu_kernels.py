@@ -362,6 +362,28 @@ def test_conv_gn_fused(case, silu):
     assert float((mg.double().cpu() - mref).abs().max()) <= 5e-3 * float(mref.abs().max())
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 256, 256, 256, 256), (3, 16, 16, 256, 256, 0, 256),
+                                  (3, 8, 8, 128, 64, 64, 128), (2, 32, 32, 64, 128, 0, 64)])
+def test_conv_tc_fused_shortcut(case):
+    """Conv_1 (3x3) with the Conv_2 1x1 shortcut over cat(e1, e2) accumulated into the same
+    accumulator as extra K-blocks (layerspp.py:266-274)."""
+    N, H, W, Cb, E1, E2, Cout = case
+    r = _rng(sum(case) + 9)
+    b_in = _t(r.standard_normal((N, H, W, Cb)), torch.bfloat16)
+    e1 = _t(r.standard_normal((N, H, W, E1)), torch.bfloat16)
+    e2 = _t(r.standard_normal((N, H, W, E2)), torch.bfloat16) if E2 else None
+    w = _t(r.standard_normal((Cout, Cb, 3, 3)) / np.sqrt(Cb * 9))
+    we = _t(r.standard_normal((Cout, E1 + E2, 1, 1)) / np.sqrt(E1 + E2))
+    bias = _t(0.1 * r.standard_normal(Cout))
+    op, out, keep = conv_op(b_in, None, w, bias, engine=L.ENGINE_TC, scale=0.7071, ext=(e1, e2, we),
+                            mg_stats=(H * W) % 32 == 0)
+    run_op(op, prepare=True)
+    ref = conv_ref(b_in, None, w.to(torch.bfloat16), bias) + conv_ref(e1, e2, we.to(torch.bfloat16), None)
+    ref = ref * 0.7071
+    err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
+    assert err <= 4e-3, err
+
+
 def test_conv_tc_output_head():
     """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
     r = _rng(77)
