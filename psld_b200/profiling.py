@@ -25,6 +25,8 @@ def op_flops(op) -> float:
     if op.kind == L.OP_CONV:
         M = i[L.CONV_N] * i[L.CONV_OH] * i[L.CONV_OW]
         K = i[L.CONV_KS] ** 2 * (i[L.CONV_C1] + i[L.CONV_C2])
+        if op.engine == L.ENGINE_TC:
+            K += i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]      # fused 1x1 shortcut
         cout = int(op.f[1]) if (op.engine == L.ENGINE_TC and op.f[1] >= 1) else i[L.CONV_COUT]
         return 2.0 * M * K * cout
     if op.kind == L.OP_ATTN:
@@ -75,7 +77,8 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
             i = op.i
             key = f"{op_name(op)} {i[L.CONV_OH]}x{i[L.CONV_OW]} {i[L.CONV_C1] + i[L.CONV_C2]}->" \
                   f"{i[L.CONV_COUT]} k{i[L.CONV_KS]}s{i[L.CONV_STRIDE]}" \
-                  f"{'+res' if op.inp[2] else ''}{'+temb' if op.inp[3] else ''}"
+                  f"{'+res' if op.inp[2] else ''}{'+temb' if op.inp[3] else ''}" \
+                  f"{'+sc' + str(i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]) if (op.engine == L.ENGINE_TC and i[L.CONV_EXT_C1]) else ''}"
             c = classes.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
             c["ms"] += acc[k] / iters
             c["n"] += 1
