@@ -5,8 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0 --no-graph"
 # warm-up = 1 + 3*(launches+1) launches; capture the single timed step after it
-SKIP=${SKIP:-1342}
-CNT=${CNT:-450}
+read SKIP CNT < <(python scripts/launch_window.py 2>/dev/null)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $CNT --csv \
     --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
