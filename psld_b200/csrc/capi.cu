@@ -26,7 +26,8 @@ static int op_launch_count(const psld_op& op) {
   switch (op.kind) {
     case PSLD_OP_LAYOUT: return 1;
     case PSLD_OP_TEMB: return 4;
-    case PSLD_OP_GN: return 2;   // statistics (or fold of producer statistics) + apply / affine
+    case PSLD_OP_GN:             // statistics (or fold of producer statistics) + apply / affine;
+      return (op.i[PSLD_GN_AFFINE_ONLY] && op.in[4] && (op.i[PSLD_GN_C2] == 0 || op.in[5])) ? 1 : 2;
     case PSLD_OP_FIR: return 1;
     case PSLD_OP_CONV: return 1;
     case PSLD_OP_ATTN: return 1;

@@ -368,33 +368,78 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
 // Pass 1 alternative: the producer convolutions already wrote (sum, sumsq) per 32 pixels x 4
 // channels (conv_tc epilogue); fold those "micro-groups" into this GroupNorm's groups.  Reads
 // ~3% of the tensor instead of all of it.  Output format = one chunk of gn_stats_kernel.
+// All 256 threads stream the (slot, micro-group) items with 8 independent loads in flight (the
+// first version walked the slots serially per thread: ~32 dependent L2 round trips, 8 us).
+// kAffine: write the per-(sample, channel) (scale, shift) pairs for a GroupNorm-on-load
+// convolution directly (no separate gn_affine launch); otherwise write the (sum, sumsq) partials
+// in the format of one gn_stats_kernel chunk for gn_apply_kernel.
+template <bool kAffine>
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ mg1, const float* __restrict__ mg2,
-                   double* __restrict__ part, int HW, int C1, int C2, int G) {
-  extern __shared__ double sh[];  // [2*G]
+                   double* __restrict__ part, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ affine, int HW, int C1, int C2,
+                   int G, float eps) {
+  extern __shared__ double sh[];  // [2*G] (+ mean/rstd floats behind it when kAffine)
   const int n = blockIdx.x;
   const int C = C1 + C2, cpg = C / G;
-  const int nmg1 = C1 >> 2, nmg = C >> 2, slots = HW >> 5;
+  const int nmg1 = C1 >> 2, nmg = C >> 2, nmg2 = nmg - nmg1, slots = HW >> 5;
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
   __syncthreads();
-  for (int m = threadIdx.x; m < nmg; m += blockDim.x) {
-    const bool first = m < nmg1;
-    const float* src = first ? mg1 + ((int64_t)n * slots * nmg1 + m) * 2
-                             : mg2 + ((int64_t)n * slots * (nmg - nmg1) + (m - nmg1)) * 2;
-    const int64_t stride = (int64_t)(first ? nmg1 : nmg - nmg1) * 2;
-    double su = 0.0, sq = 0.0;
-    for (int k = 0; k < slots; ++k) {
-      const float2 v = *reinterpret_cast<const float2*>(src + k * stride);
-      su += v.x;
-      sq += v.y;
+  const float2* p1 = reinterpret_cast<const float2*>(mg1) + (int64_t)n * slots * nmg1;
+  const float2* p2 = reinterpret_cast<const float2*>(mg2) + (int64_t)n * slots * nmg2;
+  const int total = slots * nmg;
+  int gcur = -1;
+  double su = 0.0, sq = 0.0;
+  auto flush = [&]() {
+    if (gcur >= 0) { atomicAdd(&sh[2 * gcur], su); atomicAdd(&sh[2 * gcur + 1], sq); }
+    su = 0.0; sq = 0.0;
+  };
+  constexpr int U = 8;
+  for (int i0 = threadIdx.x; i0 < total; i0 += U * 256) {
+    float2 v[U];
+    int g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = make_float2(0.f, 0.f);
+      g[u] = -1;
+      if (i < total) {
+        const int k = i / nmg, m = i - k * nmg;
+        v[u] = m < nmg1 ? __ldg(p1 + (int64_t)k * nmg1 + m) : __ldg(p2 + (int64_t)k * nmg2 + (m - nmg1));
+        g[u] = (m * 4) / cpg;
+      }
     }
-    const int g = (m * 4) / cpg;
-    atomicAdd(&sh[2 * g], su);
-    atomicAdd(&sh[2 * g + 1], sq);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g[u] < 0) continue;
+      if (g[u] != gcur) { flush(); gcur = g[u]; }
+      su += v[u].x;
+      sq += v[u].y;
+    }
   }
+  flush();
   __syncthreads();
-  double* dst = part + (int64_t)n * 2 * G;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
+  if (!kAffine) {
+    double* dst = part + (int64_t)n * 2 * G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
+  } else {
+    float* mr = reinterpret_cast<float*>(sh + 2 * G);   // mean[G], rstd[G]
+    for (int gq = threadIdx.x; gq < G; gq += blockDim.x) {
+      const double cntd = (double)HW * cpg;
+      const double mean = sh[2 * gq] / cntd;
+      double var = sh[2 * gq + 1] / cntd - mean * mean;
+      if (var < 0) var = 0;
+      mr[gq] = (float)mean;
+      mr[G + gq] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int gq = c / cpg;
+      const float sc = mr[G + gq] * gamma[c];
+      affine[((int64_t)n * C + c) * 2] = sc;
+      affine[((int64_t)n * C + c) * 2 + 1] = beta[c] - sc * mr[gq];
+    }
+  }
 }
 
 // Affine-only epilogue of the statistics pass: per (sample, channel) scale = rstd*gamma and
@@ -450,8 +495,15 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   if (fused) {
     PSLD_CHECK_ARG(HW % 32 == 0 && (C / G) % 4 == 0,
                    "gn: fused statistics need HW %% 32 == 0 and (C/G) %% 4 == 0");
-    gn_finalize_kernel<<<N, 256, sh1, s>>>((const float*)op.in[4], (const float*)op.in[5], part, HW,
-                                          C1, C2, G);
+    if (op.i[PSLD_GN_AFFINE_ONLY]) {     // fold + affine in one launch
+      gn_finalize_kernel<true><<<N, 256, sh1 + sh2, s>>>(
+          (const float*)op.in[4], (const float*)op.in[5], part, (const float*)op.in[2],
+          (const float*)op.in[3], (float*)op.out[0], HW, C1, C2, G, op.f[0]);
+      PSLD_CHECK_LAUNCH();
+      return PSLD_OK;
+    }
+    gn_finalize_kernel<false><<<N, 256, sh1, s>>>((const float*)op.in[4], (const float*)op.in[5], part,
+                                                 nullptr, nullptr, nullptr, HW, C1, C2, G, op.f[0]);
     nchunk_eff = 1;
   } else {
     dim3 grid(nchunk, N);
