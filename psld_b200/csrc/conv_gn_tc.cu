@@ -38,7 +38,9 @@ constexpr int GN_MAX_ROWS = 192;                 // (BH+2)*W: 6x32 or 10x16
 constexpr int GN_VAR_BYTES = GN_MAX_ROWS * 128;  // one operand variant (24 KB)
 constexpr int GN_ABUF_BYTES = 3 * GN_VAR_BYTES;  // left | centre | right
 constexpr int GN_STAGING_BYTES = 8 * 4096;
-constexpr int GN_SMEM_BYTES = 2 * GN_ABUF_BYTES + GN_B_STAGES * GN_B_BYTES + GN_STAGING_BYTES + 1024 + 256;
+constexpr int GN_ADDV_BYTES = 8 * 256;
+// 768 B of alignment slack (the kernel traps if that is not enough); total = the 227 KB maximum
+constexpr int GN_SMEM_BYTES = 2 * GN_ABUF_BYTES + GN_B_STAGES * GN_B_BYTES + GN_STAGING_BYTES + 256 + GN_ADDV_BYTES + 768;
 
 struct ConvGnParams {
   ConvTcParams c;
@@ -73,6 +75,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   const uint32_t bring = base + 2 * GN_ABUF_BYTES;
   const uint32_t stg_base = bring + GN_B_STAGES * GN_B_BYTES;
   const uint32_t bar_base = stg_base + GN_STAGING_BYTES;
+  const uint32_t addv_base = bar_base + 256u;
+  if (addv_base + GN_ADDV_BYTES > smem_u32(smem_raw) + GN_SMEM_BYTES) __trap();
   auto raw_full = [&](int b) { return bar_base + 8u * b; };
   auto a_ready = [&](int b) { return bar_base + 8u * (2 + b); };
   auto a_empty = [&](int b) { return bar_base + 8u * (4 + b); };
@@ -293,13 +297,18 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      tc_epilogue_tile<true>(p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
-                       stg_base + (uint32_t)(warp - 4) * 4096u);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(leader_tempty0 + 8u * (uint32_t)acc);
+      tc_epilogue_tile<true>(
+          p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+          stg_base + (uint32_t)(warp - 4) * 4096u, addv_base + (uint32_t)(warp - 4) * 256u,
+          [&]() {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+          },
+          [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_relaxed(leader_tempty0 + 8u * (uint32_t)acc);
+          });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -58,6 +58,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + kStages * Cfg::kStageBytes;
   const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
+  const uint32_t addv_base = bar_base + 256u;
+  if (addv_base + Cfg::kAddvBytes > smem_u32(smem_raw) + Cfg::kSmemBytes) __trap();   // see TcCfg
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -212,16 +214,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      tc_epilogue_tile(p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
-                       stg_base + (uint32_t)(warp - 2) * 4096u);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_remote(leader_tempty0 + 8u * (uint32_t)acc);
-        else mbar_arrive(tempty_bar(acc));
-      }
+      tc_epilogue_tile(
+          p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+          stg_base + (uint32_t)(warp - 2) * 4096u, addv_base + (uint32_t)(warp - 2) * 256u,
+          [&]() {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+          },
+          [&]() {
+            // the accumulator is in registers: hand it back before the stores are issued
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (kPair) mbar_arrive_remote_relaxed(leader_tempty0 + 8u * (uint32_t)acc);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

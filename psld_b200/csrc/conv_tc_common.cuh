@@ -56,7 +56,10 @@ struct TcCfg {
   static constexpr int kBBytes = kPair ? TC_B_BYTES / 2 : TC_B_BYTES;
   static constexpr int kStageBytes = TC_A_BYTES + kBBytes;
   static constexpr int kStagingBytes = 8 * 4096;   // epilogue transpose buffers, 4 KB per warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static constexpr int kAddvBytes = 8 * 256;       // (bias + temb) * scale, 64 columns per warp
+  // 768 B of alignment slack: the kernel traps if the dynamic window starts further than that
+  // from a 1024-byte boundary (it starts ON one in practice); total = the 227 KB maximum
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + kAddvBytes + 768;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -76,6 +79,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+// no memory ordering needed (the payload is "TMEM has been read", completed by tcgen05.wait::ld);
+// the .release form costs a MEMBAR that waits for every store in flight
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -132,54 +141,107 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc
       : "memory");
 }
 
+// packed fp32x2 FMA (Blackwell FFMA2): (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1,
+                                      float c0, float c1) {
+  uint64_t a, b, c, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 q;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+  return q;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+
 // One output tile: TMEM accumulator -> (+bias +temb +residual) * scale -> bf16 NHWC (or the fp32
 // NCHW network head) + GroupNorm micro-group statistics.  Called by the 8 epilogue warps;
 // `quarter` = TMEM lane quarter (warp id % 4), `half` selects alternate column groups, `stg` =
-// this warp's 4 KB staging tile in shared memory.
+// this warp's 4 KB staging tile and `addv` its 256 B additive-vector slot in shared memory.
+// `acquire()` is called once before the first TMEM access (it waits for the accumulator),
+// `release()` right after this warp's LAST TMEM read (it hands the accumulator back to the MMA
+// warp before the global stores are issued, so the release never waits on them).
 // kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
 // processed (32 registers; off for kernels that are short of registers).
-template <bool kPrefetchRes = true>
+template <bool kPrefetchRes = true, class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
-                                                 int lane, uint32_t stg) {
+                                                 int lane, uint32_t stg, uint32_t addv,
+                                                 Acquire acquire, Release release) {
   const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
   const bool valid = m < p.M;
-  const int img = valid ? (int)(m / p.HW) : 0;
-  const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
   const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
   const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
-  if (p.y != nullptr && (p.block_n & 63) == 0) {
+  if (p.y != nullptr && (p.block_n & 63) == 0 && (p.HW & 31) == 0) {
     // ---- staged path: 64-column groups go through a per-warp 32 x 128 B shared-memory tile
     // (16-byte chunks XOR-swizzled by row) so that BOTH the residual loads and the output
     // stores hit global memory as full 128-byte lines (4 rows per instruction) instead of 32
     // scattered 16-byte pieces; thread <-> TMEM row only touches its own row of the tile.
-        const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
+    // HW % 32 == 0: the warp's 32 pixels belong to ONE image, so (bias + temb) * scale is a
+    // warp-uniform vector: 16 lanes fetch it once per column group into `addv`, and every
+    // output is one FFMA2 lane (acc * scale + addv), two with a residual.
+    const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
+    const bool full = m_base + 32 <= p.M;             // warp-uniform: no per-row bounds checks
     const int sub_row = lane >> 3, chunk = lane & 7;
     const int ncg = p.block_n >> 6;
     const uint32_t my_row = stg + (uint32_t)lane * 128u;
+    const float scale = p.scale;
+    const float* tembw = nullptr;
+    if (p.temb) tembw = p.temb + (m_base < p.M ? m_base / p.HW : 0) * p.temb_bstride + p.temb_off;
     uint4 rq[8];
-    auto load_res = [&](int cg) {
-      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int64_t mr = m_base + 4 * it + sub_row;
-        if (mr < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + mr * p.Cout);
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_add = [&](int cg) {
+      if (lane < 16) {
+        const int c = n_tile * p.block_n + cg * 64 + 4 * lane;
+        av = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tembw) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(tembw + c));
+          av.x += t.x; av.y += t.y; av.z += t.z; av.w += t.w;
+        }
       }
     };
-    if (kPrefetchRes && p.res && half < ncg) load_res(half);
+    auto load_res = [&](int cg) {
+      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8 +
+                                (m_base + sub_row) * p.Cout;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (full || m_base + 4 * it + sub_row < p.M)
+          rq[it] = *reinterpret_cast<const uint4*>(rp + (int64_t)(4 * it) * p.Cout);
+      }
+    };
+    if (half < ncg) {
+      load_add(half);
+      if (p.res) load_res(half);
+    }
+    acquire();
+    if (half >= ncg) release();
     for (int cg = half; cg < ncg; cg += 2) {
       const int co_base = n_tile * p.block_n + cg * 64;
-      if (!kPrefetchRes && p.res) load_res(cg);
+      const bool more = cg + 2 < ncg;
+      if (lane < 16)
+        sts128(addv + (uint32_t)lane * 16u, __float_as_uint(av.x * scale), __float_as_uint(av.y * scale),
+               __float_as_uint(av.z * scale), __float_as_uint(av.w * scale));
       if (p.res) {
+        if (!kPrefetchRes && cg != half) load_res(cg);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = 4 * it + sub_row;
-          const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(a), "r"(rq[it].x), "r"(rq[it].y), "r"(rq[it].z), "r"(rq[it].w) : "memory");
+          sts128(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4),
+                 rq[it].x, rq[it].y, rq[it].z, rq[it].w);
         }
-        __syncwarp();
-        if (kPrefetchRes && cg + 2 < ncg) load_res(cg + 2);
+      }
+      __syncwarp();
+      if (more) {
+        load_add(cg + 2);
+        if (kPrefetchRes && p.res) load_res(cg + 2);
       }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
@@ -188,50 +250,41 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
                                (uint32_t)acc * 256u + (uint32_t)(cg * 64 + sub * 32);
         tmem_ld32(taddr, r);
         tmem_ld_wait();
+        if (!more && sub == 1) release();
         const int co0 = co_base + sub * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
-        if (valid) {
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (temb) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(temb + co0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-        }
-#pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const uint4 a0 = lds128(addv + (uint32_t)(sub * 32 + q * 8) * 4u);
+          const uint4 a1 = lds128(addv + (uint32_t)(sub * 32 + q * 8 + 4) * 4u);
+          const uint32_t ad[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], __uint_as_float(r[q * 8 + 2 * t]),
+                  __uint_as_float(r[q * 8 + 2 * t + 1]), scale, scale, __uint_as_float(ad[2 * t]),
+                  __uint_as_float(ad[2 * t + 1]));
           const uint32_t a = my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4);
           if (p.res) {
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
-            const uint32_t w[4] = {w0, w1, w2, w3};
+            const uint4 wq = lds128(a);
+            const uint32_t w[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
-              if (valid) { v[q * 8 + 2 * t] += f.x; v[q * 8 + 2 * t + 1] += f.y; }
+              ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], f.x, f.y, scale, scale,
+                    v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
             }
+          }
+          if (!full && !valid) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[q * 8 + t] = 0.f;
           }
           uint32_t o[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            v[q * 8 + 2 * t] *= p.scale;
-            v[q * 8 + 2 * t + 1] *= p.scale;
             __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
             o[t] = *reinterpret_cast<uint32_t*>(&h);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          sts128(a, o[0], o[1], o[2], o[3]);
         }
         if (stats) {
           float a[16];
@@ -257,20 +310,26 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         }
       }
       __syncwarp();
-      __nv_bfloat16* yp = p.y + co_base + chunk * 8;
+      {
+        __nv_bfloat16* yp = p.y + co_base + chunk * 8 + (m_base + sub_row) * p.Cout;
+        uint4 q[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = 4 * it + sub_row;
-        const int64_t mr = m_base + row;
-        const uint32_t a = stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        uint4 q;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
-        if (mr < p.M) *reinterpret_cast<uint4*>(yp + mr * p.Cout) = q;
+        for (int it = 0; it < 8; ++it) {
+          const int row = 4 * it + sub_row;
+          q[it] = lds128(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (full || m_base + 4 * it + sub_row < p.M)
+            *reinterpret_cast<uint4*>(yp + (int64_t)(4 * it) * p.Cout) = q[it];
+        }
       }
       __syncwarp();
     }
   } else {
+  acquire();
+  const int img = valid ? (int)(m / p.HW) : 0;
+  const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
   const bool has_res = valid && p.res != nullptr;
   uint4 rq[4];                                       // residual of the chunk being processed
   if (has_res && half * 32 < p.block_n) {
@@ -383,6 +442,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       }
     }
   }
+  release();
   }  // legacy (non-staged) path
 }
 
