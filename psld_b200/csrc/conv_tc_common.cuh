@@ -170,7 +170,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 // `release()` right after this warp's LAST TMEM read (it hands the accumulator back to the MMA
 // warp before the global stores are issued, so the release never waits on them).
 // kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
-// processed (32 registers; off for kernels that are short of registers).
+// processed and the second TMEM chunk in flight while the first is processed (64 registers; off
+// for kernels that are short of registers).
 template <bool kPrefetchRes = true, class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
@@ -208,13 +209,87 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         }
       }
     };
+    const int64_t row4 = (int64_t)4 * p.Cout;          // 4 rows (elements)
     auto load_res = [&](int cg) {
       const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8 +
                                 (m_base + sub_row) * p.Cout;
+      if (full) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        if (full || m_base + 4 * it + sub_row < p.M)
-          rq[it] = *reinterpret_cast<const uint4*>(rp + (int64_t)(4 * it) * p.Cout);
+        for (int it = 0; it < 8; ++it) rq[it] = *reinterpret_cast<const uint4*>(rp + it * row4);
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (m_base + 4 * it + sub_row < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + it * row4);
+      }
+    };
+    // one 32-column chunk: r = accumulator row fragment -> bf16 into this thread's row of the
+    // staging tile (+ micro-group statistics)
+    auto process = [&](uint32_t (&r)[32], int sub, int co0) {
+      uint4 ad[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ad[q] = lds128(addv + (uint32_t)(sub * 32 + q * 4) * 4u);
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ffma2(v[4 * q], v[4 * q + 1], __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), scale,
+              scale, __uint_as_float(ad[q].x), __uint_as_float(ad[q].y));
+        ffma2(v[4 * q + 2], v[4 * q + 3], __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]),
+              scale, scale, __uint_as_float(ad[q].z), __uint_as_float(ad[q].w));
+      }
+      if (p.res) {
+        uint4 wq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wq[q] = lds128(my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w[4] = {wq[q].x, wq[q].y, wq[q].z, wq[q].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+            ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], f.x, f.y, scale, scale, v[q * 8 + 2 * t],
+                  v[q * 8 + 2 * t + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+          o[t] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        sts128(my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+      }
+      if (stats) {
+        // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
+        // granularity: (sum, sum of squares) over this warp's 32 pixels.  16 values per lane are
+        // transposed-and-reduced across the warp with 16 shuffles (halving butterfly); the
+        // consumer GroupNorm combines micro-groups into its groups (gn_finalize_kernel).
+        if (!full && !valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        float a[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
+          a[2 * g] = (x0 + x1) + (x2 + x3);
+          a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const float send = hi ? a[j] : a[j + w];
+            const float keep = hi ? a[j + w] : a[j];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+          }
+        }
+        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+        if ((lane & 1) == 0)
+          p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1)] = a[0];
       }
     };
     if (half < ncg) {
@@ -243,70 +318,27 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         load_add(cg + 2);
         if (kPrefetchRes && p.res) load_res(cg + 2);
       }
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        uint32_t r[32];
+      {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)acc * 256u + (uint32_t)(cg * 64 + sub * 32);
-        tmem_ld32(taddr, r);
-        tmem_ld_wait();
-        if (!more && sub == 1) release();
-        const int co0 = co_base + sub * 32;
-        float v[32];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 a0 = lds128(addv + (uint32_t)(sub * 32 + q * 8) * 4u);
-          const uint4 a1 = lds128(addv + (uint32_t)(sub * 32 + q * 8 + 4) * 4u);
-          const uint32_t ad[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], __uint_as_float(r[q * 8 + 2 * t]),
-                  __uint_as_float(r[q * 8 + 2 * t + 1]), scale, scale, __uint_as_float(ad[2 * t]),
-                  __uint_as_float(ad[2 * t + 1]));
-          const uint32_t a = my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4);
-          if (p.res) {
-            const uint4 wq = lds128(a);
-            const uint32_t w[4] = {wq.x, wq.y, wq.z, wq.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
-              ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], f.x, f.y, scale, scale,
-                    v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
-            }
-          }
-          if (!full && !valid) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[q * 8 + t] = 0.f;
-          }
-          uint32_t o[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
-            o[t] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          sts128(a, o[0], o[1], o[2], o[3]);
-        }
-        if (stats) {
-          float a[16];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float x0 = v[4 * g], x1 = v[4 * g + 1], x2 = v[4 * g + 2], x3 = v[4 * g + 3];
-            a[2 * g] = (x0 + x1) + (x2 + x3);
-            a[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
-          }
-#pragma unroll
-          for (int w = 8; w >= 1; w >>= 1) {
-            const bool hi = (lane & (2 * w)) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float send = hi ? a[j] : a[j + w];
-              const float keep = hi ? a[j + w] : a[j];
-              a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
-            }
-          }
-          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-          if ((lane & 1) == 0)
-            p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1)] = a[0];
+                               (uint32_t)acc * 256u + (uint32_t)(cg * 64);
+        if (kPrefetchRes) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr, r0);
+          tmem_ld_wait();
+          tmem_ld32(taddr + 32u, r1);        // in flight while the first chunk is processed
+          process(r0, 0, co_base);
+          tmem_ld_wait();
+          if (!more) release();
+          process(r1, 1, co_base + 32);
+        } else {                             // register-lean order
+          uint32_t r[32];
+          tmem_ld32(taddr, r);
+          tmem_ld_wait();
+          process(r, 0, co_base);
+          tmem_ld32(taddr + 32u, r);
+          tmem_ld_wait();
+          if (!more) release();
+          process(r, 1, co_base + 32);
         }
       }
       __syncwarp();
@@ -318,10 +350,13 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
           const int row = 4 * it + sub_row;
           q[it] = lds128(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
         }
+        if (full) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (full || m_base + 4 * it + sub_row < p.M)
-            *reinterpret_cast<uint4*>(yp + (int64_t)(4 * it) * p.Cout) = q[it];
+          for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(yp + it * row4) = q[it];
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (m_base + 4 * it + sub_row < p.M) *reinterpret_cast<uint4*>(yp + it * row4) = q[it];
         }
       }
       __syncwarp();
