@@ -166,7 +166,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // whole warp converged, one elected lane issues (see conv_tc.cu)
+    if (rank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                              ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int buf = 0, stage = 0, acc = 0;
@@ -187,17 +188,21 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             const uint64_t adesc = make_sw128_desc(abuf(buf) + (uint32_t)kx * GN_VAR_BYTES +
                                                    (uint32_t)ky * row_step);
             const uint64_t bdesc = make_sw128_desc(bring + (uint32_t)stage * GN_B_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
-              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                               (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            tc_commit_pair(b_empty(stage));
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                 (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              tc_commit_pair(b_empty(stage));
+              if (tap == 8) tc_commit_pair(a_empty(buf));
+            }
+            __syncwarp();
             if (++stage == GN_B_STAGES) { stage = 0; bph ^= 1; }
           }
-          tc_commit_pair(a_empty(buf));
           if (++buf == 2) { buf = 0; aph ^= 1; }
         }
-        tc_commit_pair(tfull_bar(acc));
+        if (elect_one()) tc_commit_pair(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -165,7 +165,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop converged (every value warp-uniform) and one elected lane
+    // issues: with a divergent `lane == 0` branch around the loop ptxas wraps every tcgen05
+    // instruction in an ELECT / R2UR.BROADCAST sequence and the issue loop itself (about 120
+    // instructions per k-block, never waiting on a barrier) paces the tensor pipe.
+    if (rank == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128 (256 for a pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                              ((uint32_t)(p.block_n >> 3) << 17) |
@@ -185,22 +189,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            if (kPair)
-              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                               (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+              if (kPair)
+                tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs) when these MMAs retire
+            if (kPair) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
           }
-          // frees the smem stage (in both CTAs) when these MMAs retire
-          if (kPair) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator ready for the epilogue (of both CTAs)
-        if (kPair) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
+        if (elect_one()) {
+          if (kPair) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
