@@ -146,7 +146,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     }
   } else if (warp == 2) {
     // ===================== weight producer (half tile per CTA, credited to the leader) ======
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)b_rows * 128u * 2u;
@@ -156,9 +156,12 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         for (int cc = 0; cc < p.kchunks; ++cc) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(b_empty(stage), ph ^ 1);
-            if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
-            tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, &tmB, b_full(stage),
-                             (tap * p.kchunks + cc) * TC_BLOCK_K, bn0);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
+              tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, &tmB, b_full(stage),
+                               (tap * p.kchunks + cc) * TC_BLOCK_K, bn0);
+            }
+            __syncwarp();
             if (++stage == GN_B_STAGES) { stage = 0; ph ^= 1; }
           }
         }

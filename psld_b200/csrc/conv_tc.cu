@@ -113,8 +113,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // ===================== TMA producers (both CTAs of a pair) =====================
     // warp 0 streams the activation (A) boxes, warp 10 the weight (B) boxes: two independent
     // single-thread issue loops (one loop issuing both was the limiter: it was never blocked on a
-    // free stage, i.e. it could not issue fast enough to stay ahead of the tensor core)
-    if (lane == 0) {
+    // free stage, i.e. it could not issue fast enough to stay ahead of the tensor core).  The
+    // warp stays converged and one elected lane issues (uniform-datapath coordinates).
+    {
       const bool is_a = warp == 0;
       const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) *
                              (kPair ? 2u : 1u);
@@ -132,16 +133,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int cc = 0; cc < p.kchunks; ++cc, ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1);
               const uint32_t sa = base + stage * Cfg::kStageBytes;
-              if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
-              if (is_a) {
-                const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
-                const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
-                if (kPair) tma_load_4d_pair(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
-                else tma_load_4d(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
-              } else {
-                if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
-                else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              if (elect_one()) {
+                if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
+                if (is_a) {
+                  const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
+                  const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+                  if (kPair) tma_load_4d_pair(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+                  else tma_load_4d(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+                } else {
+                  if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                  else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                }
               }
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -149,16 +153,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int cc = 0; cc < p.ext_kchunks; ++cc, ++kb) {    // shortcut input, centre tap only
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
-          if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
-          if (is_a) {
-            const CUtensorMap* tmE = cc < p.ext_kchunks1 ? &tmE1 : &tmE2;
-            const int c0 = (cc < p.ext_kchunks1 ? cc : cc - p.ext_kchunks1) * TC_BLOCK_K;
-            if (kPair) tma_load_4d_pair(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
-            else tma_load_4d(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
-          } else {
-            if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
-            else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+          if (elect_one()) {
+            if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
+            if (is_a) {
+              const CUtensorMap* tmE = cc < p.ext_kchunks1 ? &tmE1 : &tmE2;
+              const int c0 = (cc < p.ext_kchunks1 ? cc : cc - p.ext_kchunks1) * TC_BLOCK_K;
+              if (kPair) tma_load_4d_pair(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+              else tma_load_4d(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+            } else {
+              if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
