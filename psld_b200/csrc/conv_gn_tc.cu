@@ -32,12 +32,12 @@ namespace psld {
 
 constexpr int GN_TRANSFORM_WARPS = 8;
 constexpr int GN_THREADS = (12 + GN_TRANSFORM_WARPS) * 32;   // 640 = 5 warpgroups
-constexpr int GN_B_STAGES = 3;
+constexpr int GN_B_STAGES = 4;
 constexpr int GN_B_BYTES = 128 * 128;            // half weight tile per CTA (<= 128 rows x 128 B)
 constexpr int GN_MAX_ROWS = 192;                 // (BH+2)*W: 6x32 or 10x16
 constexpr int GN_VAR_BYTES = GN_MAX_ROWS * 128;  // one operand variant (24 KB)
 constexpr int GN_ABUF_BYTES = 3 * GN_VAR_BYTES;  // left | centre | right
-constexpr int GN_STAGING_BYTES = 8 * 4096;
+constexpr int GN_STAGING_BYTES = 8 * 2048;     // 32-column staging groups (frees a 4th B stage)
 constexpr int GN_ADDV_BYTES = 8 * 256;
 // 768 B of alignment slack (the kernel traps if that is not enough); total = the 227 KB maximum
 constexpr int GN_SMEM_BYTES = 2 * GN_ABUF_BYTES + GN_B_STAGES * GN_B_BYTES + GN_STAGING_BYTES + 256 + GN_ADDV_BYTES + 768;
@@ -81,10 +81,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   auto a_ready = [&](int b) { return bar_base + 8u * (2 + b); };
   auto a_empty = [&](int b) { return bar_base + 8u * (4 + b); };
   auto b_full = [&](int s) { return bar_base + 8u * (6 + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (9 + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (14 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * 16;
+  auto b_empty = [&](int s) { return bar_base + 8u * (6 + GN_B_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (6 + 2 * GN_B_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (8 + 2 * GN_B_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (10 + 2 * GN_B_STAGES);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -305,9 +305,9 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
-      tc_epilogue_tile<false>(
+      tc_epilogue_tile<false, 32>(
           p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
-          stg_base + (uint32_t)(warp - 4) * 4096u, addv_base + (uint32_t)(warp - 4) * 256u,
+          stg_base + (uint32_t)(warp - 4) * 2048u, addv_base + (uint32_t)(warp - 4) * 256u,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();

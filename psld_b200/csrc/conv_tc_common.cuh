@@ -172,36 +172,45 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 // kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
 // processed and the second TMEM chunk in flight while the first is processed (64 registers; off
 // for kernels that are short of registers).
-template <bool kPrefetchRes = true, class Acquire, class Release>
+template <bool kPrefetchRes = true, int GC = 64, class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
                                                  int lane, uint32_t stg, uint32_t addv,
                                                  Acquire acquire, Release release) {
+  static_assert(GC == 64 || GC == 32, "staging group = 64 or 32 columns");
   const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
   const bool valid = m < p.M;
   const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
   const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
-  if (p.y != nullptr && (p.block_n & 63) == 0 && (p.HW & 31) == 0) {
-    // ---- staged path: 64-column groups go through a per-warp 32 x 128 B shared-memory tile
+  if (p.y != nullptr && (p.block_n & (GC - 1)) == 0 && (p.HW & 31) == 0) {
+    // ---- staged path: GC-column groups go through a per-warp 32 x (2*GC) B shared-memory tile
     // (16-byte chunks XOR-swizzled by row) so that BOTH the residual loads and the output
-    // stores hit global memory as full 128-byte lines (4 rows per instruction) instead of 32
-    // scattered 16-byte pieces; thread <-> TMEM row only touches its own row of the tile.
+    // stores hit global memory as full 128-byte (GC = 32: 64-byte) row segments, 4 (8) rows per
+    // instruction, instead of 32 scattered 16-byte pieces; thread <-> TMEM row only touches its
+    // own row of the tile.
     // HW % 32 == 0: the warp's 32 pixels belong to ONE image, so (bias + temb) * scale is a
-    // warp-uniform vector: 16 lanes fetch it once per column group into `addv`, and every
+    // warp-uniform vector: GC/4 lanes fetch it once per column group into `addv`, and every
     // output is one FFMA2 lane (acc * scale + addv), two with a residual.
+    constexpr int RB = GC * 2;                        // staging row bytes
+    constexpr int CPR = GC / 8;                       // 16-byte chunks per row
+    constexpr int RPI = 32 / CPR;                     // rows per coalesced instruction
+    constexpr int ITS = 32 / RPI;                     // coalesced instructions per group
+    constexpr int NSUB = GC / 32;
+    auto swz = [](int row) { return GC == 64 ? (row & 7) : ((row >> 1) & 3); };
     const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
     const bool full = m_base + 32 <= p.M;             // warp-uniform: no per-row bounds checks
-    const int sub_row = lane >> 3, chunk = lane & 7;
-    const int ncg = p.block_n >> 6;
-    const uint32_t my_row = stg + (uint32_t)lane * 128u;
+    const int sub_row = lane / CPR, chunk = lane % CPR;
+    const int ncg = p.block_n / GC;
+    const uint32_t my_row = stg + (uint32_t)lane * RB;
+    const int my_swz = swz(lane);
     const float scale = p.scale;
     const float* tembw = nullptr;
     if (p.temb) tembw = p.temb + (m_base < p.M ? m_base / p.HW : 0) * p.temb_bstride + p.temb_off;
-    uint4 rq[8];
+    uint4 rq[ITS];
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_add = [&](int cg) {
-      if (lane < 16) {
-        const int c = n_tile * p.block_n + cg * 64 + 4 * lane;
+      if (lane < GC / 4) {
+        const int c = n_tile * p.block_n + cg * GC + 4 * lane;
         av = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (tembw) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(tembw + c));
@@ -209,17 +218,18 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         }
       }
     };
-    const int64_t row4 = (int64_t)4 * p.Cout;          // 4 rows (elements)
+    const int64_t rowstep = (int64_t)RPI * p.Cout;    // RPI rows (elements)
     auto load_res = [&](int cg) {
-      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * 64 + chunk * 8 +
+      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * GC + chunk * 8 +
                                 (m_base + sub_row) * p.Cout;
       if (full) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) rq[it] = *reinterpret_cast<const uint4*>(rp + it * row4);
+        for (int it = 0; it < ITS; ++it) rq[it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
       } else {
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-          if (m_base + 4 * it + sub_row < p.M) rq[it] = *reinterpret_cast<const uint4*>(rp + it * row4);
+        for (int it = 0; it < ITS; ++it)
+          if (m_base + RPI * it + sub_row < p.M)
+            rq[it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
       }
     };
     // one 32-column chunk: r = accumulator row fragment -> bf16 into this thread's row of the
@@ -239,7 +249,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       if (p.res) {
         uint4 wq[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) wq[q] = lds128(my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4));
+        for (int q = 0; q < 4; ++q) wq[q] = lds128(my_row + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t w[4] = {wq[q].x, wq[q].y, wq[q].z, wq[q].w};
@@ -259,7 +269,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
           __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
           o[t] = *reinterpret_cast<uint32_t*>(&h);
         }
-        sts128(my_row + (uint32_t)(((sub * 4 + q) ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+        sts128(my_row + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4), o[0], o[1], o[2], o[3]);
       }
       if (stats) {
         // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
@@ -299,17 +309,17 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     acquire();
     if (half >= ncg) release();
     for (int cg = half; cg < ncg; cg += 2) {
-      const int co_base = n_tile * p.block_n + cg * 64;
+      const int co_base = n_tile * p.block_n + cg * GC;
       const bool more = cg + 2 < ncg;
-      if (lane < 16)
+      if (lane < GC / 4)
         sts128(addv + (uint32_t)lane * 16u, __float_as_uint(av.x * scale), __float_as_uint(av.y * scale),
                __float_as_uint(av.z * scale), __float_as_uint(av.w * scale));
       if (p.res) {
         if (!kPrefetchRes && cg != half) load_res(cg);
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = 4 * it + sub_row;
-          sts128(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4),
+        for (int it = 0; it < ITS; ++it) {
+          const int row = RPI * it + sub_row;
+          sts128(stg + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4),
                  rq[it].x, rq[it].y, rq[it].z, rq[it].w);
         }
       }
@@ -320,8 +330,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       }
       {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)acc * 256u + (uint32_t)(cg * 64);
-        if (kPrefetchRes) {
+                               (uint32_t)acc * 256u + (uint32_t)(cg * GC);
+        if (NSUB == 1) {
+          uint32_t r[32];
+          tmem_ld32(taddr, r);
+          tmem_ld_wait();
+          if (!more) release();
+          process(r, 0, co_base);
+        } else if (kPrefetchRes) {
           uint32_t r0[32], r1[32];
           tmem_ld32(taddr, r0);
           tmem_ld_wait();
@@ -344,19 +360,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       __syncwarp();
       {
         __nv_bfloat16* yp = p.y + co_base + chunk * 8 + (m_base + sub_row) * p.Cout;
-        uint4 q[8];
+        uint4 q[ITS];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = 4 * it + sub_row;
-          q[it] = lds128(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+        for (int it = 0; it < ITS; ++it) {
+          const int row = RPI * it + sub_row;
+          q[it] = lds128(stg + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4));
         }
         if (full) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(yp + it * row4) = q[it];
+          for (int it = 0; it < ITS; ++it) *reinterpret_cast<uint4*>(yp + it * rowstep) = q[it];
         } else {
 #pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (m_base + 4 * it + sub_row < p.M) *reinterpret_cast<uint4*>(yp + it * row4) = q[it];
+          for (int it = 0; it < ITS; ++it)
+            if (m_base + RPI * it + sub_row < p.M) *reinterpret_cast<uint4*>(yp + it * rowstep) = q[it];
         }
       }
       __syncwarp();
