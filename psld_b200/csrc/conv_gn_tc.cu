@@ -58,6 +58,14 @@ struct ConvGnState {
   int grid;
 };
 
+// tap issue order: the three centre-column taps first, so that the centre slot (where the next
+// raw tile lands) is released after a third of the chunk's MMAs
+__device__ __forceinline__ int gn_tap(int t9) {
+  const int kx = t9 < 3 ? 1 : (t9 < 6 ? 0 : 2);
+  const int ky = t9 < 3 ? t9 : (t9 < 6 ? t9 - 3 : t9 - 6);
+  return ky * 3 + kx;
+}
+
 __device__ __forceinline__ float silu_fast(float x) {
   const float h = 0.5f * x;
   float t;
@@ -84,7 +92,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   auto b_empty = [&](int s) { return bar_base + 8u * (6 + GN_B_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (6 + 2 * GN_B_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (8 + 2 * GN_B_STAGES + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (10 + 2 * GN_B_STAGES);
+  auto c_empty = [&](int b) { return bar_base + 8u * (10 + 2 * GN_B_STAGES + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (12 + 2 * GN_B_STAGES);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -100,6 +109,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       mbar_init(raw_full(b), 1);
       mbar_init(a_ready(b), 2);       // one elected arrive per CTA of the pair
       mbar_init(a_empty(b), 1);
+      mbar_init(c_empty(b), 1);
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 16);
     }
@@ -135,7 +145,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int n0 = m_tile / p.tiles_y;
         const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
         for (int cc = 0; cc < p.kchunks; ++cc) {
-          mbar_wait(a_empty(buf), ph ^ 1);
+          mbar_wait(c_empty(buf), ph ^ 1);      // centre slot free (its 3 taps are issued first)
           mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
           const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
           const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
@@ -154,7 +164,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int n_tile = unit % p.n_tiles_n;
         const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
         for (int cc = 0; cc < p.kchunks; ++cc) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int tap = gn_tap(t9);
             mbar_wait(b_empty(stage), ph ^ 1);
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
@@ -183,7 +194,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         for (int cc = 0; cc < p.kchunks; ++cc) {
           mbar_wait_cluster(a_ready(buf), aph);
           tc_fence_after();
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int tap = gn_tap(t9);
             const int ky = tap / 3, kx = tap - ky * 3;
             mbar_wait(b_full(stage), bph);
             tc_fence_after();
@@ -195,9 +207,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / 16; ++k)
                 tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                 (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                                 (cc > 0 || t9 > 0 || k > 0) ? 1u : 0u);
               tc_commit_pair(b_empty(stage));
-              if (tap == 8) tc_commit_pair(a_empty(buf));
+              if (t9 == 2) tc_commit_pair(c_empty(buf));   // raw tile of chunk cc+2 may land
+              if (t9 == 8) tc_commit_pair(a_empty(buf));
             }
             __syncwarp();
             if (++stage == GN_B_STAGES) { stage = 0; bph ^= 1; }
@@ -270,6 +283,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             }
           }
         }
+        mbar_wait(a_empty(buf), ph ^ 1);          // left / right variants no longer being read
 #pragma unroll
         for (int u = 0; u < ITEMS; ++u) {
           if (!inb[u]) continue;

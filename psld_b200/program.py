@@ -370,7 +370,9 @@ class Plan:
             aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
-            if self.fuse_gn_residual and self._gn_fusable(h, None, m.out_ch):
+            gn1 = self.fuse_gn_residual or (os.environ.get("PSLD_TC_FUSE_GN1", "0") == "1"
+                                            and not hasattr(m, "Conv_2"))
+            if gn1 and self._gn_fusable(h, None, m.out_ch):
                 aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
                 b, b_aff = h, aff1
             else:
