@@ -46,6 +46,14 @@ struct ConvTcState {
   bool pair;      // 2-CTA (cta_group::2) variant
 };
 
+// Optional per-CTA phase timeline (build with -DPSLD_TC_TRACE; scripts/tc_trace.py reads it)
+#ifdef PSLD_TC_TRACE
+__device__ long long g_tc_trace[160 * 8];
+#define TC_TRACE(slot) do { if ((threadIdx.x & 31) == 0) g_tc_trace[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
+
 template <bool kPair>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -54,6 +62,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   using Cfg = TcCfg<kPair>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) TC_TRACE(0);
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + kStages * Cfg::kStageBytes;
@@ -103,6 +112,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   // K = taps x input channels, optionally followed by a 1x1 "extension" over a second input
   // (the residual block's Conv_2 shortcut accumulated into the same tile, layerspp.py:269-274)
@@ -193,6 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kb == 0 && unit == unit0) TC_TRACE(2);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
@@ -220,6 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      TC_TRACE(3);
     }
   } else if (warp < 10) {
     // ===================== epilogue (warps 2..9) =====================
@@ -237,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (warp == 2) TC_TRACE(4);
           },
           [&]() {
             // the accumulator is in registers: hand it back before the stores are issued
@@ -247,12 +260,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               else mbar_arrive(tempty_bar(acc));
             }
           });
+      if (warp == 2) TC_TRACE(5);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) TC_TRACE(6);
   if (warp == 1) {
     tc_fence_after();
     if (kPair)
@@ -477,3 +492,9 @@ int run_conv_tc(const psld_op& op, cudaStream_t s) {
 }
 
 }  // namespace psld
+
+#ifdef PSLD_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int psld_debug_tc_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, psld::g_tc_trace, sizeof(psld::g_tc_trace));
+}
+#endif

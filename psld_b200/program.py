@@ -17,6 +17,7 @@ Fusions relative to the reference's eager graph:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -83,7 +84,6 @@ class Plan:
     def _gn_fusable(self, x1, x2, cout):
         """Host mirror of prepare_conv_gn_tc (csrc/conv_gn_tc.cu): can act(GroupNorm(x)) -> conv3x3
         run as ONE kernel that normalises its input tile in shared memory?"""
-        import os
         if not self.bf16 or not self.fuse_gn or os.environ.get("PSLD_TC_FUSE_GN", "1") == "0":
             return False
         N, H, W, C1 = x1.shape
@@ -370,7 +370,7 @@ class Plan:
             aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
-            gn1 = self.fuse_gn_residual or (os.environ.get("PSLD_TC_FUSE_GN1", "0") == "1"
+            gn1 = self.fuse_gn_residual or (os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
                                             and not hasattr(m, "Conv_2"))
             if gn1 and self._gn_fusable(h, None, m.out_ch):
                 aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
