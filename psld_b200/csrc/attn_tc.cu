@@ -82,6 +82,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // q|k|v come from the previous kernel (prologue above overlaps its tail)
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tmem_S = tmem_base;                 // columns [0, HW)
   const uint32_t tmem_O = tmem_base + 256u;          // columns [256, 256 + C)
@@ -292,7 +293,8 @@ int release_attn_tc(psld_op& op) {
 int run_attn_tc(const psld_op& op, cudaStream_t s) {
   const AttnTcState* st = (const AttnTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
-  attn_tc_kernel<<<st->grid, AT_THREADS, AT_SMEM_BYTES, s>>>(st->tq, st->tkv, st->p);
+  PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES, s, 1, st->tq,
+                             st->tkv, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

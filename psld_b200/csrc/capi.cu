@@ -7,6 +7,7 @@
 // incurs 9 `.item()` syncs per SSCS step).
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -20,6 +21,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PSLD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 static int op_launch_count(const psld_op& op) {

@@ -78,6 +78,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                   const __grid_constant__ CUtensorMap tmB, const ConvGnParams gp) {
   const ConvTcParams& p = gp.c;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();      // single wave of persistent CTAs (see conv_tc.cu)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto abuf = [&](int b) { return base + (uint32_t)b * GN_ABUF_BYTES; };
   const uint32_t bring = base + 2 * GN_ABUF_BYTES;
@@ -137,6 +138,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 
   if (warp == 0) {
     // ===================== raw activation tile producer =====================
+    pdl_wait();
     if (lane == 0) {
       int buf = 0;
       uint32_t ph = 0;
@@ -236,6 +238,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     auto sptr = [&](uint32_t a) { return reinterpret_cast<uint4*>(smem_raw + (a - sm0)); };
     int buf = 0;
     uint32_t ph = 0;
+    pdl_wait();                 // the affine table comes from the GroupNorm fold just before
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       const int n0 = m_tile / p.tiles_y;
@@ -316,6 +319,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    pdl_wait();
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
@@ -476,19 +480,8 @@ int release_conv_gn_tc(psld_op& op) {
 int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
   const ConvGnState* st = (const ConvGnState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)st->grid);
-  cfg.blockDim = dim3(GN_THREADS);
-  cfg.dynamicSmemBytes = GN_SMEM_BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gn_tc_kernel, st->a1, st->a2, st->b, st->p));
+  PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
+                             s, 2, st->a1, st->a2, st->b, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

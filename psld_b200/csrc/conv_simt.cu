@@ -36,6 +36,7 @@ __device__ __forceinline__ float load_in(const ConvP& p, int n, int iy, int ix, 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const ConvP p) {
+  pdl_wait();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -177,13 +178,13 @@ int run_conv_simt(const psld_op& op, cudaStream_t s) {
   PSLD_CHECK_ARG(!p.res || op.i[PSLD_CONV_RES_DTYPE] == odt, "conv: residual dtype != out dtype");
   const int64_t M = (int64_t)p.N * p.OH * p.OW;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p.Cout, BN));
-  if (idt == PSLD_F32 && odt == PSLD_F32) conv_simt_kernel<float, float><<<grid, 256, 0, s>>>(p);
+  if (idt == PSLD_F32 && odt == PSLD_F32) launch_pdl(conv_simt_kernel<float, float>, dim3(grid), dim3(256), 0, s, 1, p);
   else if (idt == PSLD_BF16 && odt == PSLD_BF16)
-    conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
+    launch_pdl(conv_simt_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, p);
   else if (idt == PSLD_BF16 && odt == PSLD_F32)
-    conv_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>(p);
+    launch_pdl(conv_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, s, 1, p);
   else if (idt == PSLD_F32 && odt == PSLD_BF16)
-    conv_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
+    launch_pdl(conv_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, p);
   else { set_error("conv: unsupported dtypes %d -> %d", idt, odt); return PSLD_EINVAL; }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
@@ -198,6 +199,7 @@ constexpr int TQ = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int HW, int C, float scale) {
+  pdl_wait();
   extern __shared__ float smem[];
   float* S = smem;                               // [TQ][HW + 1]
   float* buf = smem + TQ * (HW + 1);             // tile buffers
@@ -310,12 +312,12 @@ int run_attn_simt(const psld_op& op, cudaStream_t s) {
   if (dt == PSLD_BF16) {
     PSLD_CHECK_CUDA(cudaFuncSetAttribute(attn_simt_kernel<__nv_bfloat16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_simt_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)op.in[0],
+    launch_pdl(attn_simt_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, s, 1, (const __nv_bfloat16*)op.in[0],
                                                            (__nv_bfloat16*)op.out[0], HW, C, op.f[0]);
   } else {
     PSLD_CHECK_CUDA(cudaFuncSetAttribute(attn_simt_kernel<float>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_simt_kernel<float><<<grid, 256, smem, s>>>((const float*)op.in[0], (float*)op.out[0], HW, C,
+    launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(256), smem, s, 1, (const float*)op.in[0], (float*)op.out[0], HW, C,
                                                    op.f[0]);
   }
   PSLD_CHECK_LAUNCH();

@@ -63,6 +63,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 0) TC_TRACE(0);
+  // PDL: the next kernel's CTAs may take this SM as soon as this CTA exits (one wave, persistent)
+  pdl_launch_dependents();
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + kStages * Cfg::kStageBytes;
@@ -127,6 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // warp stays converged and one elected lane issues (uniform-datapath coordinates).
     {
       const bool is_a = warp == 0;
+      if (is_a) pdl_wait();     // activations come from the previous kernel; weights do not
       const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) *
                              (kPair ? 2u : 1u);
       int stage = 0;
@@ -240,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const uint32_t leader_tempty0 = kPair ? mapa_rank(tempty_bar(0), 0) : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
+    pdl_wait();                 // residual / temb reads and every global write come after this
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
@@ -469,23 +473,13 @@ int run_conv_tc(const psld_op& op, cudaStream_t s) {
   const ConvTcState* st = (const ConvTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_tc: op not prepared (call psld_op_prepare)");
   if (st->pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)st->grid);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TcCfg<true>::kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PSLD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, st->a1, st->a2, st->b, st->e1,
-                                       st->e2, st->p));
+    PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<true>, dim3((unsigned)st->grid), dim3(TC_THREADS),
+                               TcCfg<true>::kSmemBytes, s, 2, st->a1, st->a2, st->b, st->e1, st->e2,
+                               st->p));
   } else {
-    conv_tc_kernel<false><<<st->grid, TC_THREADS, TcCfg<false>::kSmemBytes, s>>>(
-        st->a1, st->a2, st->b, st->e1, st->e2, st->p);
+    PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<false>, dim3((unsigned)st->grid), dim3(TC_THREADS),
+                               TcCfg<false>::kSmemBytes, s, 1, st->a1, st->a2, st->b, st->e1, st->e2,
+                               st->p));
   }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;

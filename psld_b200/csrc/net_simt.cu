@@ -22,6 +22,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int HW,
                     int CP) {
+  pdl_wait();
   const int64_t total = (int64_t)N * CP * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -36,6 +37,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, in
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+  pdl_wait();
   const int64_t total = (int64_t)N * C * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -63,17 +65,17 @@ int run_layout(const psld_op& op, cudaStream_t s) {
   const int grid = ew_grid((int64_t)N * CP * HW);
   if (dir == 0) {
     if (dt == PSLD_BF16)
-      nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const float*)op.in[0],
+      launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
                                                             (__nv_bfloat16*)op.out[0], N, C, HW, CP);
     else
-      nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)op.in[0], (float*)op.out[0],
+      launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0],
                                                     N, C, HW, CP);
   } else {
     if (dt == PSLD_BF16)
-      nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)op.in[0],
+      launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const __nv_bfloat16*)op.in[0],
                                                             (float*)op.out[0], N, C, HW);
     else
-      nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>((const float*)op.in[0], (float*)op.out[0],
+      launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0],
                                                     N, C, HW);
   }
   PSLD_CHECK_LAUNCH();
@@ -86,6 +88,7 @@ int run_layout(const psld_op& op, cudaStream_t s) {
 __global__ void temb_embed_kernel(const float* __restrict__ t, const float* __restrict__ W,
                                   float* __restrict__ emb, int nt, int nf, int emb_type,
                                   int logged, const int* __restrict__ step_ptr) {
+  pdl_wait();
   if (step_ptr) t += *step_ptr;      // graph replay: t is a per-call table, the step lives on device
   const int E = emb_type == 0 ? 2 * nf : nf;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +115,7 @@ template <bool kSiluIn>
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ in, const float* __restrict__ W,
                    const float* __restrict__ b, float* __restrict__ out, int rows, int K, int O) {
+  pdl_wait();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= (int64_t)rows * O) return;
@@ -140,16 +144,16 @@ int run_temb(const psld_op& op, cudaStream_t s) {
   float* emb = (float*)op.out[1];
   float* h0 = emb + (int64_t)nt * E;
   float* h1 = h0 + (int64_t)nt * D;
-  temb_embed_kernel<<<(int)ceil_div((int64_t)nt * E, 128), 128, 0, s>>>(
+  launch_pdl(temb_embed_kernel, dim3((unsigned)((int)ceil_div((int64_t)nt * E, 128))), dim3(128), 0, s, 1, 
       (const float*)op.in[0], (const float*)op.in[1], emb, nt, nf, et, logged, (const int*)op.out[2]);
   PSLD_CHECK_LAUNCH();
-  linear_rows_kernel<false><<<(int)ceil_div((int64_t)nt * D * 32, 256), 256, 0, s>>>(
+  launch_pdl(linear_rows_kernel<false>, dim3((unsigned)((int)ceil_div((int64_t)nt * D * 32, 256))), dim3(256), 0, s, 1, 
       emb, (const float*)op.in[2], (const float*)op.in[3], h0, nt, E, D);
   PSLD_CHECK_LAUNCH();
-  linear_rows_kernel<true><<<(int)ceil_div((int64_t)nt * D * 32, 256), 256, 0, s>>>(
+  launch_pdl(linear_rows_kernel<true>, dim3((unsigned)((int)ceil_div((int64_t)nt * D * 32, 256))), dim3(256), 0, s, 1, 
       h0, (const float*)op.in[4], (const float*)op.in[5], h1, nt, D, D);
   PSLD_CHECK_LAUNCH();
-  linear_rows_kernel<true><<<(int)ceil_div((int64_t)nt * totalC * 32, 256), 256, 0, s>>>(
+  launch_pdl(linear_rows_kernel<true>, dim3((unsigned)((int)ceil_div((int64_t)nt * totalC * 32, 256))), dim3(256), 0, s, 1, 
       h1, (const float*)op.in[6], (const float*)op.in[7], (float*)op.out[0], nt, D, totalC);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
@@ -219,6 +223,7 @@ template <typename T, int VW>   // VW = channels per thread (8, or 4 when C % 8 
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ part,
                 int HW, int C1, int C2, int G, int nchunk) {
+  pdl_wait();
   extern __shared__ double sh[];  // [2*G]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int C = C1 + C2, vpr = C / VW, cpg = C / G;
@@ -294,6 +299,7 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
                 const double* __restrict__ part, const float* __restrict__ gamma,
                 const float* __restrict__ beta, TO* __restrict__ y, int HW, int C1, int C2, int G,
                 int nchunk, int nchunk_apply, float eps, int silu) {
+  pdl_wait();
   extern __shared__ float shf[];  // mean[G], rstd[G]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int C = C1 + C2, vpr = C / VW, cpg = C / G;
@@ -379,6 +385,7 @@ gn_finalize_kernel(const float* __restrict__ mg1, const float* __restrict__ mg2,
                    double* __restrict__ part, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ affine, int HW, int C1, int C2,
                    int G, float eps) {
+  pdl_wait();
   extern __shared__ double sh[];  // [2*G] (+ mean/rstd floats behind it when kAffine)
   const int n = blockIdx.x;
   const int C = C1 + C2, cpg = C / G;
@@ -448,6 +455,7 @@ __global__ void __launch_bounds__(256)
 gn_affine_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ affine, int HW, int C, int G,
                  int nchunk, float eps) {
+  pdl_wait();
   extern __shared__ float shf[];  // mean[G], rstd[G]
   const int n = blockIdx.x;
   const int cpg = C / G;
@@ -496,19 +504,19 @@ int run_gn(const psld_op& op, cudaStream_t s) {
     PSLD_CHECK_ARG(HW % 32 == 0 && (C / G) % 4 == 0,
                    "gn: fused statistics need HW %% 32 == 0 and (C/G) %% 4 == 0");
     if (op.i[PSLD_GN_AFFINE_ONLY]) {     // fold + affine in one launch
-      gn_finalize_kernel<true><<<N, 256, sh1 + sh2, s>>>(
+      launch_pdl(gn_finalize_kernel<true>, dim3((unsigned)(N)), dim3(256), sh1 + sh2, s, 1, 
           (const float*)op.in[4], (const float*)op.in[5], part, (const float*)op.in[2],
           (const float*)op.in[3], (float*)op.out[0], HW, C1, C2, G, op.f[0]);
       PSLD_CHECK_LAUNCH();
       return PSLD_OK;
     }
-    gn_finalize_kernel<false><<<N, 256, sh1, s>>>((const float*)op.in[4], (const float*)op.in[5], part,
+    launch_pdl(gn_finalize_kernel<false>, dim3((unsigned)(N)), dim3(256), sh1, s, 1, (const float*)op.in[4], (const float*)op.in[5], part,
                                                  nullptr, nullptr, nullptr, HW, C1, C2, G, op.f[0]);
     nchunk_eff = 1;
   } else {
     dim3 grid(nchunk, N);
 #define GN_STATS(T, VW)                                                                        \
-  gn_stats_kernel<T, VW><<<grid, 256, sh1, s>>>((const T*)op.in[0], (const T*)op.in[1], part, HW, \
+  launch_pdl(gn_stats_kernel<T, VW>, dim3(grid), dim3(256), sh1, s, 1, (const T*)op.in[0], (const T*)op.in[1], part, HW, \
                                                 C1, C2, G, nchunk)
     if (idt == PSLD_BF16) { if (v8) GN_STATS(__nv_bfloat16, 8); else GN_STATS(__nv_bfloat16, 4); }
     else { if (v8) GN_STATS(float, 8); else GN_STATS(float, 4); }
@@ -518,7 +526,7 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   const float* ga0 = (const float*)op.in[2];
   const float* be0 = (const float*)op.in[3];
   if (op.i[PSLD_GN_AFFINE_ONLY]) {
-    gn_affine_kernel<<<N, 256, sh2, s>>>(part, ga0, be0, (float*)op.out[0], HW, C, G, nchunk_eff,
+    launch_pdl(gn_affine_kernel, dim3((unsigned)(N)), dim3(256), sh2, s, 1, part, ga0, be0, (float*)op.out[0], HW, C, G, nchunk_eff,
                                         op.f[0]);
     PSLD_CHECK_LAUNCH();
     return PSLD_OK;
@@ -532,7 +540,7 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   const float* ga = (const float*)op.in[2];
   const float* be = (const float*)op.in[3];
 #define GN_APPLY(T, VW, FAST)                                                                   \
-  gn_apply_kernel<T, T, VW, FAST><<<grid2, 256, sh2, s>>>((const T*)op.in[0], (const T*)op.in[1], \
+  launch_pdl(gn_apply_kernel<T, T, VW, FAST>, grid2, dim3(256), sh2, s, 1, (const T*)op.in[0], (const T*)op.in[1], \
                                                           part, ga, be, (T*)op.out[0], HW, C1, C2, \
                                                           G, nchunk_eff, nca, eps, silu)
   if (idt == PSLD_BF16) { if (v8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 4, true); }
@@ -552,6 +560,7 @@ template <typename T, int VW, int UP, int DOWN>
 __global__ void __launch_bounds__(256)
 fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C,
            int OH, int OW, int up_rt, int down_rt, int pad0, int KH) {
+  pdl_wait();
   const int up = UP ? UP : up_rt, down = DOWN ? DOWN : down_rt;
   const int vpr = C / VW;
   const int64_t total = (int64_t)N * OH * OW * vpr;
@@ -606,6 +615,7 @@ fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int 
                   int C, int OH, int OW, int up_x, int up_y, int down_x, int down_y, int pad_x0,
                   int pad_y0, int KH, int KW, int64_t sn, int64_t sy, int64_t sx, int64_t sc,
                   int64_t on, int64_t oyS, int64_t oxS, int64_t oc) {
+  pdl_wait();
   const int64_t total = (int64_t)N * OH * OW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -650,7 +660,7 @@ int run_fir(const psld_op& op, cudaStream_t s) {
     const int vw = C % 8 == 0 ? 8 : 4;
     const int grid = (int)ceil_div((int64_t)N * OH * OW * (C / vw), 256);
 #define FIR_LAUNCH2(T, VW, U, D)                                                              \
-  fir_kernel<T, VW, U, D><<<grid, 256, 0, s>>>((const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, \
+  launch_pdl(fir_kernel<T, VW, U, D>, dim3(grid), dim3(256), 0, s, 1, (const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, \
                                                OH, OW, up, down, pad0, KH)
 #define FIR_LAUNCH(T, VW)                                          \
   do {                                                             \
@@ -668,11 +678,11 @@ int run_fir(const psld_op& op, cudaStream_t s) {
     const int64_t sn = (int64_t)H * W * C, sy = (int64_t)W * C, sx = C, sc = 1;
     const int64_t on = (int64_t)OH * OW * C, oyS = (int64_t)OW * C, oxS = C, oc = 1;
     if (dt == PSLD_BF16)
-      fir_scalar_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
+      launch_pdl(fir_scalar_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, 
           (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C, OH, OW, up,
           up, down, down, pad0, pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc);
     else
-      fir_scalar_kernel<float><<<grid, 256, 0, s>>>((const float*)op.in[0], (float*)op.out[0], taps,
+      launch_pdl(fir_scalar_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0], taps,
                                                   N, H, W, C, OH, OW, up, up, down, down, pad0,
                                                   pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc);
   }
@@ -700,7 +710,7 @@ extern "C" int psld_upfirdn2d(const float* input, float* output, const float* ta
   for (int i = 0; i < 16; ++i) taps.k[i] = i < kh * kw ? taps_host[i] : 0.f;
   const int grid = ew_grid(planes * OH * OW);
   // planes-as-batch, C = 1, contiguous W
-  fir_scalar_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(fir_scalar_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, 
       input, output, taps, (int)planes, in_h, in_w, 1, OH, OW, up_x, up_y, down_x, down_y, pad_x0,
       pad_y0, kh, kw, (int64_t)in_h * in_w, in_w, 1, 0, (int64_t)OH * OW, OW, 1, 0);
   PSLD_CHECK_LAUNCH();

@@ -211,6 +211,7 @@ __device__ __forceinline__ void sscs_update_body(S* __restrict__ u_out, const S*
 template <typename S>
 __global__ void __launch_bounds__(256)
 sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams p) {
+  pdl_wait();
   sscs_update_body<S>(u_out, u_in, p);
 }
 
@@ -218,6 +219,7 @@ sscs_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const Sscs
 template <typename S>
 __global__ void __launch_bounds__(256)
 sscs_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const SscsParams pp) {
+  pdl_wait();
   __shared__ SscsParams p;
   const int step = *pp.step_ptr;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.table + step);
@@ -295,12 +297,14 @@ __device__ __forceinline__ void em_update_body(S* __restrict__ u_out, const S* _
 template <typename S>
 __global__ void __launch_bounds__(256)
 em_update_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams p) {
+  pdl_wait();
   em_update_body<S>(u_out, u_in, p);
 }
 
 template <typename S>
 __global__ void __launch_bounds__(256)
 em_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const EmParams pp) {
+  pdl_wait();
   __shared__ EmParams p;
   const int step = *pp.step_ptr;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.table + step);
@@ -316,6 +320,7 @@ em_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const 
 
 __global__ void __launch_bounds__(256)
 prior_kernel(float* __restrict__ u, float m_std, uint64_t seed, int64_t B, int64_t chw) {
+  pdl_wait();
   const int64_t nvec = B * (chw >> 2);
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (int64_t)gridDim.x * blockDim.x) {
@@ -336,6 +341,7 @@ prior_kernel(float* __restrict__ u, float m_std, uint64_t seed, int64_t B, int64
 template <typename S>
 __global__ void __launch_bounds__(256)
 quantize_kernel(const S* __restrict__ u, uint8_t* __restrict__ out, int64_t B, int C, int HW) {
+  pdl_wait();
   const int64_t total = B * HW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -362,10 +368,11 @@ static inline int grid_for(int64_t nvec) {
 using namespace psld;
 
 namespace psld {
-__global__ void step_inc_kernel(int* p) { *p += 1; }
+__global__ void step_inc_kernel(int* p) {
+  pdl_wait(); *p += 1; }
 
 int launch_step_inc(int* step_ptr, cudaStream_t s) {
-  step_inc_kernel<<<1, 1, 0, s>>>(step_ptr);
+  launch_pdl(step_inc_kernel, dim3((unsigned)(1)), dim3(1), 0, s, 1, step_ptr);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
@@ -380,9 +387,9 @@ int launch_sscs_table(void* u, int state_dtype, float* net_in, const float* eps,
   p.eps = eps; p.net_in = net_in; p.seed = seed; p.B = B; p.chw = chw; p.stages = stages;
   const int grid = grid_for(B * (chw / 4));
   if (state_dtype == PSLD_F64)
-    sscs_update_table_kernel<double><<<grid, 256, 0, s>>>((double*)u, (const double*)u, p);
+    launch_pdl(sscs_update_table_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)u, (const double*)u, p);
   else
-    sscs_update_table_kernel<float><<<grid, 256, 0, s>>>((float*)u, (const float*)u, p);
+    launch_pdl(sscs_update_table_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)u, (const float*)u, p);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
@@ -396,9 +403,9 @@ int launch_em_table(void* u, int state_dtype, float* net_in, const float* eps,
   p.eps = eps; p.net_in = net_in; p.seed = seed; p.B = B; p.chw = chw; p.use_philox = 1;
   const int grid = grid_for(B * (chw / 4));
   if (state_dtype == PSLD_F64)
-    em_update_table_kernel<double><<<grid, 256, 0, s>>>((double*)u, (const double*)u, p);
+    launch_pdl(em_update_table_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)u, (const double*)u, p);
   else
-    em_update_table_kernel<float><<<grid, 256, 0, s>>>((float*)u, (const float*)u, p);
+    launch_pdl(em_update_table_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)u, (const float*)u, p);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
@@ -423,9 +430,9 @@ extern "C" int psld_sscs_update(void* u_out, const void* u_in, int state_dtype, 
   const int grid = grid_for(B * (chw / 4));
   cudaStream_t s = (cudaStream_t)stream;
   if (state_dtype == PSLD_F64)
-    sscs_update_kernel<double><<<grid, 256, 0, s>>>((double*)u_out, (const double*)u_in, p);
+    launch_pdl(sscs_update_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)u_out, (const double*)u_in, p);
   else
-    sscs_update_kernel<float><<<grid, 256, 0, s>>>((float*)u_out, (const float*)u_in, p);
+    launch_pdl(sscs_update_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)u_out, (const float*)u_in, p);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
@@ -446,9 +453,9 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
   const int grid = grid_for(B * (chw / 4));
   cudaStream_t s = (cudaStream_t)stream;
   if (state_dtype == PSLD_F64)
-    em_update_kernel<double><<<grid, 256, 0, s>>>((double*)u_out, (const double*)u_in, p);
+    launch_pdl(em_update_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)u_out, (const double*)u_in, p);
   else
-    em_update_kernel<float><<<grid, 256, 0, s>>>((float*)u_out, (const float*)u_in, p);
+    launch_pdl(em_update_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)u_out, (const float*)u_in, p);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
@@ -456,7 +463,7 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
 extern "C" int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                                  psld_stream_t stream) {
   PSLD_CHECK_ARG(u && B > 0 && chw > 0 && chw % 4 == 0, "psld_prior_sample: bad arguments");
-  prior_kernel<<<grid_for(B * (chw / 4)), 256, 0, (cudaStream_t)stream>>>(u, (float)m_std, seed,
+  launch_pdl(prior_kernel, dim3((unsigned)(grid_for(B * (chw / 4)))), dim3(256), 0, (cudaStream_t)stream, 1, u, (float)m_std, seed,
                                                                          B, chw);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
@@ -470,9 +477,9 @@ extern "C" int psld_quantize_images(const void* state, int state_dtype, uint8_t*
   const int grid = grid_for(B * HW * C);
   cudaStream_t s = (cudaStream_t)stream;
   if (state_dtype == PSLD_F64)
-    quantize_kernel<double><<<grid, 256, 0, s>>>((const double*)state, out_nhwc, B, C, HW);
+    launch_pdl(quantize_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (const double*)state, out_nhwc, B, C, HW);
   else
-    quantize_kernel<float><<<grid, 256, 0, s>>>((const float*)state, out_nhwc, B, C, HW);
+    launch_pdl(quantize_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)state, out_nhwc, B, C, HW);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }
