@@ -128,6 +128,29 @@ PSLD_API int psld_em_update(void* u_out, const void* u_in, int state_dtype, floa
                    const psld_score_step* coeffs /* host */, uint64_t seed, uint64_t step,
                    int64_t B, int64_t chw, psld_stream_t stream);
 
+/* One Split-Perturb-Combine step of the inpainting sampler ES3EulerMaruyamaInpainter
+ * (main/samplers/sde.py:134-186; perturbation kernel PSLD._mean / cond_marginal_prob /
+ * perturb_data, main/models/sde/psld.py:62-84,222-228,262-287), fused into one pass:
+ *   m0   = m0_std * z_m0                      (DSM; HSM passes m0_std = 0, sde.py:137-143)
+ *   mu_x = a_xx x0 + a_xm m0 ;  mu_m = a_mx x0 + a_mm m0
+ *   x_k  = mu_x + c11 e_x + c12 e_m ;  m_k = mu_m + c21 e_x + c22 e_m   (mean_only: x_k = mu_x, ...)
+ *   x    = x (1 - mask) + x_k mask ;  m = m (1 - mask) + m_k mask        (sde.py:175-178)
+ * u: [B,2C,H,W] state (in place, f64 or f32); x0, mask: fp32 [B,C,H,W]; z_m0 [B,C,H,W] and
+ * z_eps [B,2C,H,W] are pre-drawn N(0,1) tensors or NULL (both NULL: Philox4x32-10 keyed by
+ * (seed, step)); net_in (optional): fp32 copy of the new state for the next score_fn call. */
+typedef struct psld_inpaint_step {
+  double a_xx, a_xm, a_mx, a_mm;
+  double c11, c12, c21, c22;
+  double m0_std;
+  int32_t mean_only;
+  int32_t _pad;
+} psld_inpaint_step;
+
+PSLD_API int psld_inpaint_combine(void* u, int state_dtype, float* net_in, const float* x0,
+                                  const float* mask, const float* z_m0, const float* z_eps,
+                                  const psld_inpaint_step* coeffs /* host */, uint64_t seed,
+                                  uint64_t step, int64_t B, int64_t chw, psld_stream_t stream);
+
 /* PSLD.prior_sampling (psld.py:366-370) on device: x ~ N(0,1), m ~ N(0, M); fp32 NCHW. */
 PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                       psld_stream_t stream);

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle.ref_loader import NoiseBank, load_reference, reference_time_grid  # noqa: E402
-from oracle.weights import fill_state_dict, noise_bank, prior  # noqa: E402
+from oracle.weights import inpaint_draws, inpaint_inputs, fill_state_dict, noise_bank, prior  # noqa: E402
 from psld_b200.config import celeba64_config, cifar10_config, mid_config, tiny_config  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -181,6 +181,25 @@ def golden_sampler(R, cfg, fname, B, seed_w=0, seed_p=1, seed_n=2, keep=2, score
           probe=np.asarray(probe), **states)
 
 
+def golden_inpaint(R, cfg, fname, B, seed_w=0, seed_p=1, seed_n=2, seed_x=3, score="fake"):
+    sde = R.PSLD(cfg)
+    H = cfg.data.image_size
+    net = fake_score if score == "fake" else ref_net(R, cfg, seed_w)[0]
+    ts, n = reference_time_grid(cfg)
+    d = inpaint_draws(n, B, H, seed_n)
+    u0 = prior((B, 3, H, H), float(np.sqrt(sde.m)), seed_p)
+    x_0, mask = inpaint_inputs(B, H, seed_x)
+    order = [d["m0"][0], d["eps"][0]]
+    for i in range(n + 1):
+        order += [d["pred"][i], d["m0"][i + 1], d["eps"][i + 1]]
+    S = R.get_module("samplers", "ip_em_sde")(cfg, sde, net)
+    sde.prior_sampling = lambda shape: u0.clone()    # the only non-randn_like draw (psld.py:366-370)
+    with NoiseBank(order):
+        out = S.sample((x_0, mask), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    _save(fname, final=out.double().numpy(), ts=ts.numpy(), n=np.asarray(n), B=np.asarray(B),
+          seeds=np.asarray([seed_w, seed_p, seed_n, seed_x]))
+
+
 def fake_score(u, t):
     """Deterministic smooth stand-in score network (tests the sampler algebra alone)."""
     return (torch.tanh(u * 0.3) * 0.7 + 0.1 * torch.sin(torch.roll(u, 1, 1))) * t.view(-1, 1, 1, 1)
@@ -189,6 +208,8 @@ def fake_score(u, t):
 def main():
     torch.set_num_threads(os.cpu_count())
     R = load_reference()
+    if "--only-inpaint" in sys.argv:
+        return golden_inpaint_all(R)
     golden_scalars(R)
     golden_upfirdn(R)
     golden_modules(R)
@@ -215,6 +236,16 @@ def main():
         cfg.model.sde.update(sd)
         cfg.data.image_size = 8
         golden_sampler(R, cfg, f"sampler_{tag}.npz", B=3, keep=3, score="fake")
+    golden_inpaint_all(R)
+
+
+def golden_inpaint_all(R):
+    # inpainting sampler (ip_em_sde), HSM and DSM perturbation, sampler algebra alone
+    for mode in ("hsm", "dsm"):
+        cfg = tiny_config(sampler="ip_em_sde", n_discrete_steps=30)
+        cfg.training.mode = mode
+        cfg.data.image_size = 8
+        golden_inpaint(R, cfg, f"sampler_ip_em_fake_{mode}.npz", B=3)
 
 
 if __name__ == "__main__":

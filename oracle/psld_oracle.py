@@ -256,6 +256,63 @@ def sscs_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, reco
     return u
 
 
+def mean_coeffs(sde: PSLDScalars, tau: float):
+    """``PSLD._mean`` (``psld.py:62-84``) as coefficients: mu_x = a_xx x0 + a_xm m0, mu_m = ..."""
+    mu_lam = (sde.nu + sde.gamma) / 4
+    b = sde.b_t(tau)
+    s = math.exp(-mu_lam * b)
+    a1, a2 = (sde.nu - sde.gamma) / 4, (sde.gamma - sde.nu) ** 2 / 8
+    c1, c2 = -0.5, (sde.gamma - sde.nu) / 4
+    return s * (1 + a1 * b), s * (a2 * b), s * (c1 * b), s * (1 + c2 * b)
+
+
+def inpaint_em_sample(config, score_fn, x_0, mask, prior, ts, n, noise, denoise=True, eps=1e-3,
+                      record=None):
+    """``ES3EulerMaruyamaInpainter.sample`` (``sde.py:188-224``).  ``prior`` = the tensor
+    ``sde.prior_sampling`` returned; ``noise`` = dict of draws in the reference's order:
+    ``pred[i]`` (predictor, sde.py:158), ``m0[k]`` / ``eps[k]`` (``_perturb``, sde.py:137-146) with
+    k = 0 for the initial latent, i+1 after step i and n+1 for the denoise call."""
+    sde = PSLDScalars(config)
+    hsm = str(config.training.mode) == "hsm"
+    C = x_0.shape[1]
+    x0 = x_0.to(torch.float64)
+    mk = mask.to(torch.float64)
+
+    def perturb(tau, k):                                           # sde.py:134-150
+        m_0 = math.sqrt(sde.mm_0) * noise["m0"][k].to(torch.float64)
+        mm_0 = 0.0
+        if hsm:
+            m_0 = torch.zeros_like(x0)
+            mm_0 = sde.mm_0
+        axx, axm, amx, amm = mean_coeffs(sde, tau)
+        mu = torch.cat([axx * x0 + axm * m_0, amx * x0 + amm * m_0], dim=1)
+        c11, c12, c21, c22 = sde.get_coeff(sde.cov(0.0, mm_0, tau))
+        ex, em = torch.chunk(noise["eps"][k].to(torch.float64), 2, dim=1)
+        return mu + torch.cat([c11 * ex + c12 * em, c21 * ex + c22 * em], dim=1), mu
+
+    def combine(u, other):                                         # sde.py:174-178
+        a, b = torch.chunk(u, 2, dim=1)
+        ok, om = torch.chunk(other, 2, dim=1)
+        return torch.cat([a * (1 - mk) + ok * mk, b * (1 - mk) + om * mk], dim=1)
+
+    u = combine(prior.to(torch.float64), perturb(sde.T, 0)[0])     # sde.py:193-202
+    with torch.no_grad():
+        for i in range(n):
+            t, dt = float(ts[i]), float(ts[i + 1] - ts[i])
+            fbar, (gx, gm) = reverse_drift(sde, score_fn, u, t)
+            g = torch.cat([torch.full_like(u[:, :C], gx), torch.full_like(u[:, C:], gm)], dim=1)
+            u = (u + fbar * dt) + g * math.sqrt(dt) * noise["pred"][i].to(torch.float64)
+            u = combine(u, perturb(sde.T - t, i + 1)[0])           # perturbed at T - ts[i], sde.py:168-172
+            if record is not None:
+                record(i, u)
+        if denoise:                                                # sde.py:213-222: float32 t and dt
+            t32 = np.float32(sde.T - eps)
+            fbar, _ = reverse_drift(sde, score_fn, u, float(t32))
+            mean = u + fbar * float(np.float32(eps))
+            u = combine(mean, perturb(float(np.float32(sde.T) - t32), n + 1)[1])
+    return u
+
+
 # --------------------------------------------------------------------------------------
 # 3. upfirdn2d (op/upfirdn2d.py:159-200): zero-stuff, pad/crop, TRUE convolution, decimate
 # --------------------------------------------------------------------------------------

@@ -53,6 +53,12 @@ class SscsCoeffs(C.Structure):
                 ("score", ScoreStep)]
 
 
+class InpaintStep(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("a_xx", "a_xm", "a_mx", "a_mm", "c11", "c12", "c21", "c22", "m0_std")] + \
+               [("mean_only", C.c_int32), ("_pad", C.c_int32)]
+
+
 class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("engine", C.c_int32),
                 ("i", C.c_int32 * OP_NI), ("f", C.c_float * OP_NF),
@@ -82,6 +88,9 @@ EXPORTS = {
     "psld_em_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.POINTER(ScoreStep), C.c_uint64, C.c_uint64,
                                  C.c_int64, C.c_int64, C.c_void_p]),
+    "psld_inpaint_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(InpaintStep), C.c_uint64,
+                                       C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),
     "psld_prior_sample": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_int64, C.c_int64,
                                     C.c_void_p]),
     "psld_quantize_images": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,

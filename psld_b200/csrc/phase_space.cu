@@ -460,6 +460,83 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
   return PSLD_OK;
 }
 
+// ---------------------------------------------------------------- inpainting combine
+template <typename S>
+__global__ void __launch_bounds__(256)
+inpaint_combine_kernel(S* __restrict__ u, float* __restrict__ net_in, const float* __restrict__ x0,
+                       const float* __restrict__ mask, const float* __restrict__ z_m0,
+                       const float* __restrict__ z_eps, psld_inpaint_step c, uint64_t seed,
+                       uint64_t step, int64_t B, int64_t chw) {
+  pdl_wait();
+  const int64_t q = chw / 4;
+  const int64_t total = B * q;
+  const S axx = (S)c.a_xx, axm = (S)c.a_xm, amx = (S)c.a_mx, amm = (S)c.a_mm;
+  const S c11 = (S)c.c11, c12 = (S)c.c12, c21 = (S)c.c21, c22 = (S)c.c22, ms = (S)c.m0_std;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / q, j = (i - b * q) * 4;
+    S* px = u + b * 2 * chw + j;
+    S* pm = px + chw;
+    St4<S> x = load4<S>(px), m = load4<S>(pm);
+    const float4 x0v = *reinterpret_cast<const float4*>(x0 + b * chw + j);
+    const float4 mkv = *reinterpret_cast<const float4*>(mask + b * chw + j);
+    float4 zm, ex, em;
+    if (z_eps) {
+      zm = z_m0 ? *reinterpret_cast<const float4*>(z_m0 + b * chw + j) : make_float4(0, 0, 0, 0);
+      ex = *reinterpret_cast<const float4*>(z_eps + b * 2 * chw + j);
+      em = *reinterpret_cast<const float4*>(z_eps + b * 2 * chw + chw + j);
+    } else {      // three independent Philox streams per step, disjoint from the predictor's
+      zm = Philox::normal4(seed, (step << 2) | (1ull << 62), (uint64_t)i);
+      ex = Philox::normal4(seed, (step << 2) | (1ull << 62) | 1ull, (uint64_t)i);
+      em = Philox::normal4(seed, (step << 2) | (1ull << 62) | 2ull, (uint64_t)i);
+    }
+    const float x0a[4] = {x0v.x, x0v.y, x0v.z, x0v.w}, mka[4] = {mkv.x, mkv.y, mkv.z, mkv.w};
+    const float zma[4] = {zm.x, zm.y, zm.z, zm.w}, exa[4] = {ex.x, ex.y, ex.z, ex.w};
+    const float ema[4] = {em.x, em.y, em.z, em.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const S xo = (S)x0a[k], mk = (S)mka[k];
+      const S m0 = ms * (S)zma[k];
+      S xk = axx * xo + axm * m0, mkk = amx * xo + amm * m0;
+      if (!c.mean_only) {
+        xk += c11 * (S)exa[k] + c12 * (S)ema[k];
+        mkk += c21 * (S)exa[k] + c22 * (S)ema[k];
+      }
+      x.v[k] = x.v[k] * ((S)1 - mk) + xk * mk;
+      m.v[k] = m.v[k] * ((S)1 - mk) + mkk * mk;
+    }
+    store4<S>(px, x);
+    store4<S>(pm, m);
+    if (net_in) {
+      *reinterpret_cast<float4*>(net_in + b * 2 * chw + j) =
+          make_float4((float)x.v[0], (float)x.v[1], (float)x.v[2], (float)x.v[3]);
+      *reinterpret_cast<float4*>(net_in + b * 2 * chw + chw + j) =
+          make_float4((float)m.v[0], (float)m.v[1], (float)m.v[2], (float)m.v[3]);
+    }
+  }
+}
+
+extern "C" int psld_inpaint_combine(void* u, int state_dtype, float* net_in, const float* x0,
+                                    const float* mask, const float* z_m0, const float* z_eps,
+                                    const psld_inpaint_step* coeffs, uint64_t seed, uint64_t step,
+                                    int64_t B, int64_t chw, psld_stream_t stream) {
+  PSLD_CHECK_ARG(u && x0 && mask && coeffs && B > 0 && chw > 0 && chw % 4 == 0,
+                 "psld_inpaint_combine: bad arguments");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
+                 "psld_inpaint_combine: state dtype must be f64 or f32");
+  PSLD_CHECK_ARG(!(z_m0 && !z_eps), "psld_inpaint_combine: z_m0 given without z_eps");
+  const int grid = grid_for(B * (chw / 4));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    launch_pdl(inpaint_combine_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)u, net_in, x0,
+               mask, z_m0, z_eps, *coeffs, seed, step, B, chw);
+  else
+    launch_pdl(inpaint_combine_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)u, net_in, x0,
+               mask, z_m0, z_eps, *coeffs, seed, step, B, chw);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
 extern "C" int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                                  psld_stream_t stream) {
   PSLD_CHECK_ARG(u && B > 0 && chw > 0 && chw % 4 == 0, "psld_prior_sample: bad arguments");

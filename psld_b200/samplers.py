@@ -28,7 +28,7 @@ import torch
 from . import _lib as L
 from .ncsnpp import NCSNpp
 from .registry import register_module
-from .schedule import PSLDSchedule, StepTables
+from .schedule import InpaintTables, PSLDSchedule, StepTables
 
 
 class Sampler(abc.ABC):
@@ -248,3 +248,92 @@ class SSCSSampler(_FusedSampler):
 class EulerMaruyamaSampler(_FusedSampler):
     """Euler-Maruyama sampler (reference sde.py:8-58)."""
     KIND = "em_sde"
+
+
+@register_module(category="samplers", name="ip_em_sde_b200")
+class InpaintEulerMaruyamaSampler(_FusedSampler):
+    """Euler-Maruyama inpainting sampler (reference ``ES3EulerMaruyamaInpainter``,
+    sde.py:125-224): ``sample((x_0, mask), ts, n, denoise, eps)``; after every predictor step
+    the known region (``mask == 1``) is replaced by a fresh perturbation of ``x_0`` at the
+    current noise level (one fused ``psld_inpaint_combine`` pass).
+
+    ``self.prior`` (optional ``[B,2C,H,W]``) replaces the device-drawn prior; ``self.noise``
+    (optional, parity mode) is a dict of pre-drawn N(0,1) tensors in the reference's draw
+    order: ``pred [n(+1),B,2C,H,W]``, ``m0 [n+2,B,C,H,W]``, ``eps [n+2,B,2C,H,W]`` (index 0 =
+    initial latent, 1..n = steps, n+1 = denoise call; the denoise entries may be omitted when
+    ``denoise`` is False).  HSM / DSM follows ``config.training.mode`` (sde.py:137-143)."""
+    KIND = "em_sde"
+
+    def __init__(self, config, sde, score_fn, corrector_fn=None):
+        super().__init__(config, sde, score_fn, corrector_fn=corrector_fn)
+        self.prior = None
+        tr = getattr(config, "training", None)
+        mode = tr.get("mode", "hsm") if hasattr(tr, "get") else getattr(tr, "mode", "hsm")
+        self.hsm = str(mode) == "hsm"
+
+    def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
+        lib = L.lib()
+        x_0, mask = batch
+        n = int(n_discrete_steps)
+        self.nfe = n
+        if isinstance(self.score_fn, NCSNpp):
+            dev = next(self.score_fn.parameters()).device
+        else:
+            dev = x_0.device if x_0.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
+        if x_0.dim() != 4:
+            raise ValueError(f"expected x_0 [B,C,H,W], got {tuple(x_0.shape)}")
+        B, Cc, H, W = x_0.shape
+        chw = Cc * H * W
+        if chw % 4:
+            raise ValueError("C*H*W must be a multiple of 4")
+        with torch.no_grad(), torch.cuda.device(dev):
+            x0 = x_0.to(device=dev, dtype=torch.float32).contiguous()
+            mk = mask.to(device=dev, dtype=torch.float32).expand(B, Cc, H, W).contiguous()
+            stream = L.stream_ptr(dev)
+            if self.prior is not None:
+                state = self.prior.to(device=dev, dtype=self.state_dtype).contiguous().clone()
+            else:
+                pr = torch.empty(B, 2 * Cc, H, W, dtype=torch.float32, device=dev)
+                L.check(lib.psld_prior_sample(L.ptr(pr), float(self.schedule.m) ** 0.5, self.seed, B,
+                                              chw, stream), "psld_prior_sample")
+                state = pr.to(self.state_dtype)
+            tabs = StepTables(self.schedule, ts.detach().to("cpu", torch.float64), n, "em_sde",
+                              bool(denoise), float(eps), self._embedding())
+            ip = InpaintTables(self.schedule, ts.detach().to("cpu", torch.float64), n, bool(denoise),
+                               float(eps), self.hsm)
+            bank = None
+            if self.noise is not None:
+                bank = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in self.noise.items()}
+            net_in = torch.empty(B, 2 * Cc, H, W, dtype=torch.float32, device=dev)
+            sdt = L.dtype_code(self.state_dtype)
+            sp, np_ = L.ptr(state), L.ptr(net_in)
+            tau32 = tabs.tau32.to(dev)
+
+            def combine(k):
+                zm = L.ptr(bank["m0"][k]) if bank is not None and not self.hsm else None
+                ze = L.ptr(bank["eps"][k]) if bank is not None else None
+                L.check(lib.psld_inpaint_combine(sp, sdt, np_, L.ptr(x0), L.ptr(mk), zm, ze,
+                                                 C.byref(ip.steps[k]), self.seed, k, B, chw, stream),
+                        "psld_inpaint_combine")
+
+            def score(i):
+                e = self.score_fn(net_in, tau32[i].expand(B))
+                return e.to(torch.float32).contiguous()
+
+            combine(0)
+            for i in range(n):
+                e = score(i)
+                z = L.ptr(bank["pred"][i]) if bank is not None else None
+                L.check(lib.psld_em_update(sp, sp, sdt, np_, L.ptr(e), z, 0 if bank is not None else 1,
+                                           C.byref(tabs.em[i]), self.seed, i, B, chw, stream),
+                        "psld_em_update")
+                combine(i + 1)
+            if denoise:
+                e = score(n)
+                L.check(lib.psld_em_update(sp, sp, sdt, np_, L.ptr(e), None, 0, C.byref(tabs.den),
+                                           self.seed, n, B, chw, stream), "psld_em_update")
+                combine(n + 1)
+            self._keep = (x0, mk, bank, net_in, tabs, ip)
+        return state

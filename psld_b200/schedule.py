@@ -129,6 +129,16 @@ class PSLDSchedule:
         _nan_guard(out)
         return out
 
+    # ---- mean of the perturbation kernel as a 2x2 map of (x_0, m_0) (psld.py:62-84) ----
+    def mean_coeffs(self, tau):
+        mu_lam = (self.nu + self.gamma) / 4
+        b = self.b_t(tau)
+        s = torch.exp(-mu_lam * b)
+        a1 = (self.nu - self.gamma) / 4
+        a2 = (self.gamma - self.nu) ** 2 / 8
+        c2 = (self.gamma - self.nu) / 4
+        return s * (1 + a1 * b), s * (a2 * b), s * (-0.5 * b), s * (1 + c2 * b)
+
     # ---- SSCS analytic half-step over [t, t+h] in reverse time (sde.py:236-292) ----
     def half_step(self, t, h):
         nu, ga = self.nu, self.gamma
@@ -278,3 +288,33 @@ class StepTables:
     @property
     def n_calls(self):
         return int(self.tau32.numel())
+
+
+class InpaintTables:
+    """Per-call coefficients of the inpainting sampler's Split-Perturb-Combine
+    (reference sde.py:134-186): call 0 = initial latent (t = T), calls 1..n = after predictor
+    step i at forward time T - ts[i] (the reference perturbs at the time the step STARTED from,
+    sde.py:168-172), call n+1 = the denoise call at T - fl32(T - eps), mean only."""
+
+    def __init__(self, sch: PSLDSchedule, ts, n: int, denoise: bool, eps: float, hsm: bool):
+        ts = torch.as_tensor(ts, dtype=_F64).cpu()
+        taus = [torch.tensor([sch.T], dtype=_F64), sch.T - ts[:n]]
+        if denoise:
+            # `self.sde.T - t` with t = torch.tensor(T - eps) is a float32 subtraction (sde.py:211-219)
+            t32 = torch.tensor(sch.T - eps, dtype=torch.float32)
+            taus.append((sch.T - t32).to(_F64).reshape(1))
+        tau = torch.cat(taus)
+        mm_0 = sch.mm_0 if hsm else 0.0
+        a = sch.mean_coeffs(tau)
+        c = sch.factor(sch.cov(0.0, mm_0, tau))
+        k = int(tau.numel())
+        self.steps = (L.InpaintStep * k)()
+        for i in range(k):
+            st = self.steps[i]
+            st.a_xx, st.a_xm, st.a_mx, st.a_mm = (float(v[i]) for v in a)
+            st.c11, st.c12, st.c21, st.c22 = (float(v[i]) for v in c)
+            st.m0_std = 0.0 if hsm else float(sch.mm_0) ** 0.5
+            st.mean_only = 0
+        if denoise:
+            self.steps[k - 1].mean_only = 1
+        self.tau = tau

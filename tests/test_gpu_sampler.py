@@ -15,7 +15,9 @@ import torch
 from _net import fake_score, make_net, sampler_inputs
 from _ops import max_rel, rel_l2
 from oracle import psld_oracle as O
-from psld_b200 import EulerMaruyamaSampler, PSLD, SSCSSampler, time_grid, tiny_config
+from oracle.weights import inpaint_draws, inpaint_inputs, prior
+from psld_b200 import (EulerMaruyamaSampler, InpaintEulerMaruyamaSampler, PSLD, SSCSSampler, time_grid,
+                       tiny_config)
 
 pytestmark = pytest.mark.gpu
 
@@ -198,3 +200,57 @@ def test_image_quantisation_bit_exact(dtype):
     ref = O.images_uint8(st)
     assert got.shape == ref.shape == (7, 32, 32, 3) and got.dtype == ref.dtype
     assert (got == ref).all()
+
+
+def _inpaint_cfg(mode):
+    cfg = tiny_config(sampler="ip_em_sde", n_discrete_steps=30)
+    cfg.training.mode = mode
+    cfg.data.image_size = 8
+    return cfg
+
+
+@pytest.mark.parametrize("mode", ["hsm", "dsm"])
+def test_inpaint_sampler_vs_reference_golden(golden_dir, mode):
+    """ip_em_sde (reference sde.py:125-224): EM predictor + fused Split-Perturb-Combine kernel vs the
+    reference's own output on the same draws."""
+    g = np.load(f"{golden_dir}/sampler_ip_em_fake_{mode}.npz")
+    cfg = _inpaint_cfg(mode)
+    n, B = int(g["n"]), int(g["B"])
+    sde = PSLD(cfg)
+    ts, n2 = time_grid(cfg)
+    assert n2 == n
+    x_0, mask = inpaint_inputs(B, 8, 3)
+    S = InpaintEulerMaruyamaSampler(cfg, sde, fake_score)
+    S.state_dtype = torch.float64
+    S.prior = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+    S.noise = inpaint_draws(n, B, 8, 2)
+    out = S.sample((x_0.cuda(), mask.cuda()), ts, n, denoise=cfg.evaluation.denoise,
+                   eps=cfg.evaluation.eval_eps).cpu()
+    ref = torch.from_numpy(g["final"])
+    e = max_rel(out, ref)
+    print(f"ip_em_sde {mode}: max-abs/max|ref| {e:.3e}")
+    assert e <= 1e-6
+    # fp32 state
+    S.state_dtype = torch.float32
+    out32 = S.sample((x_0.cuda(), mask.cuda()), ts, n, denoise=cfg.evaluation.denoise,
+                     eps=cfg.evaluation.eval_eps).cpu()
+    assert rel_l2(out32, ref) <= 2e-5
+
+
+def test_inpaint_sampler_philox_keeps_known_region():
+    """Device-drawn prior and noise: reproducible, and the known region of the denoised result is
+    the perturbation mean of x_0 (HSM), i.e. x_0 scaled by the mean coefficient at tau = eps."""
+    cfg = _inpaint_cfg("hsm")
+    sde = PSLD(cfg)
+    ts, n = time_grid(cfg)
+    x_0, mask = inpaint_inputs(4, 8, 5)
+    S = InpaintEulerMaruyamaSampler(cfg, sde, fake_score)
+    a = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()
+    b = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    s = O.PSLDScalars(cfg)
+    axx = O.mean_coeffs(s, float(np.float32(1.0) - np.float32(1.0 - cfg.evaluation.eval_eps)))[0]
+    known = mask == 1
+    assert torch.allclose(a[:, :3][known], (axx * x_0.double())[known], rtol=1e-12, atol=1e-13)
+    free = ~known
+    assert (a[:, :3][free] - (axx * x_0.double())[free]).abs().max() > 1e-3

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import psld_oracle as O
-from oracle.weights import fill_state_dict, noise_bank, prior
+from oracle.weights import fill_state_dict, inpaint_draws, inpaint_inputs, noise_bank, prior
 from psld_b200 import mid_config, tiny_config
 from _net import fake_score
 from test_gpu_sampler import _golden_cfg
@@ -142,3 +142,33 @@ def test_sampler_with_network(golden_dir, kind, fname):
     out = fn(cfg, O.OracleScoreFn(cfg, sd), u0, ts, n, nb)
     ref = g["final"]
     assert np.abs(out.numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
+def inpaint_cfg(mode):
+    cfg = tiny_config(sampler="ip_em_sde", n_discrete_steps=30)
+    cfg.training.mode = mode
+    cfg.data.image_size = 8
+    return cfg
+
+
+@pytest.mark.parametrize("mode", ["hsm", "dsm"])
+def test_inpaint_sampler_algebra(golden_dir, mode):
+    """Oracle restatement of ES3EulerMaruyamaInpainter (sde.py:125-224) vs the reference's output."""
+    g = np.load(f"{golden_dir}/sampler_ip_em_fake_{mode}.npz")
+    cfg = inpaint_cfg(mode)
+    ts, n = O.time_grid(cfg)
+    assert n == int(g["n"])
+    B = int(g["B"])
+    sde = O.PSLDScalars(cfg)
+    u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+    x_0, mask = inpaint_inputs(B, 8, 3)
+    out = O.inpaint_em_sample(cfg, fake_score, x_0, mask, u0, ts, n, inpaint_draws(n, B, 8, 2),
+                              denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-7 * np.abs(ref).max()
+    # the known region of the result is the perturbation mean of x_0 at tau = T - fl32(T - eps)
+    axx = O.mean_coeffs(sde, float(np.float32(1.0) - np.float32(1.0 - cfg.evaluation.eval_eps)))[0]
+    if mode == "hsm":
+        known = (mask.numpy() == 1)
+        np.testing.assert_allclose(out.numpy()[:, :3][known], (axx * x_0.double().numpy())[known],
+                                   rtol=1e-12, atol=1e-14)
