@@ -110,3 +110,32 @@ def test_forward_odd_configs_vs_oracle(sf, B, precision, tol):
     err = rel_l2(y, ref)
     print(f"odd config {sf} B={B} {precision}: rel-L2 {err:.3e} engines {net.plan(B, B, False).engine_count}")
     assert err <= tol, err
+
+
+def test_full_size_workload_properties():
+    """BASELINE configs[1] at its full size (CIFAR-10 NCSN++, B = 256, bf16 tensor-core plan, the
+    bench workload), checked through size-independent properties: per-sample independence (the
+    same samples through a B = 4 plan, whose tiling / grid sizes differ), the shared-time-row
+    fast path, and agreement with the fp32 CUDA-core path on a slice."""
+    cfg = _full(cifar10_config())
+    net, _ = make_net(cfg, "bf16")
+    r = np.random.default_rng(11)
+    x = torch.from_numpy(r.standard_normal((256, 6, 32, 32)).astype(np.float32)).cuda()
+    t = torch.full((256,), 0.43, device="cuda")
+    y = net(x, t)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    idx = [0, 1, 130, 255]
+    ys = net(x[idx].contiguous(), t[:4])
+    e_shard = rel_l2(ys, y[idx])
+    p1 = net.plan(256, 1, True)             # sampling plan: one time row for the whole batch
+    p1.x_in.copy_(x)
+    p1.time_buf.copy_(torch.log(t[:1].cpu()).cuda())
+    p1.run()
+    torch.cuda.synchronize()
+    e_row = rel_l2(p1.eps, y)
+    net32, _ = make_net(cfg, "fp32")
+    y32 = net32(x[idx].contiguous(), t[:4])
+    e_prec = rel_l2(ys, y32)
+    print(f"B=256 vs B=4 plan {e_shard:.3e}; shared time row {e_row:.3e}; bf16 vs fp32 path {e_prec:.3e}")
+    assert e_shard <= 1e-3 and e_row <= 1e-3 and e_prec <= 3e-2
