@@ -151,6 +151,21 @@ PSLD_API int psld_inpaint_combine(void* u, int state_dtype, float* net_in, const
                                   const psld_inpaint_step* coeffs /* host */, uint64_t seed,
                                   uint64_t step, int64_t B, int64_t chw, psld_stream_t stream);
 
+/* Euler-Maruyama step of the VP-SDE baseline (reference main/models/sde/vpsde.py:42-74 under
+ * EulerMaruyamaSampler, main/samplers/sde.py:16-36):
+ *   score = eps * neg_inv_std ;  x' = x + (half_beta x + g2 score) dt + gs z
+ * x: [n] elements (f64 or f32, may be updated in place), eps fp32, z pre-drawn N(0,1) or NULL
+ * (use_philox: in-kernel Philox; neither: no noise = the denoising step), net_in (optional): fp32
+ * copy of x'.  n must be a multiple of 4. */
+typedef struct psld_vp_step {
+  double half_beta, g2, neg_inv_std, dt, gs;
+} psld_vp_step;
+
+PSLD_API int psld_vp_em_update(void* x_out, const void* x_in, int state_dtype, float* net_in,
+                               const float* eps, const float* z, int use_philox,
+                               const psld_vp_step* coeffs /* host */, uint64_t seed, uint64_t step,
+                               int64_t n, psld_stream_t stream);
+
 /* PSLD.prior_sampling (psld.py:366-370) on device: x ~ N(0,1), m ~ N(0, M); fp32 NCHW. */
 PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                       psld_stream_t stream);

@@ -210,6 +210,8 @@ def main():
     R = load_reference()
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
+    if "--only-vp" in sys.argv:
+        return golden_vp(R)
     golden_scalars(R)
     golden_upfirdn(R)
     golden_modules(R)
@@ -237,6 +239,33 @@ def main():
         cfg.data.image_size = 8
         golden_sampler(R, cfg, f"sampler_{tag}.npz", B=3, keep=3, score="fake")
     golden_inpaint_all(R)
+    golden_vp(R)
+
+
+def vp_config(**ev):
+    e = dict(sampler="em_sde", n_discrete_steps=40)
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.model.sde.update(name="vpsde", beta_min=0.1, beta_max=20.0)
+    cfg.model.score_fn.update(in_ch=3, out_ch=3)
+    cfg.data.image_size = 8
+    return cfg
+
+
+def golden_vp(R):
+    """EM on the VP-SDE baseline (sample_uncond_vpsde.sh): sampler algebra with the stand-in score."""
+    for tag, kw in [("uniform", {}), ("quad", dict(stride_type="quadratic"))]:
+        cfg = vp_config(**kw)
+        sde = R.get_module("sde", "vpsde")(cfg)
+        ts, n = reference_time_grid(cfg)
+        B = 3
+        nb = noise_bank(n, (B, 3, 8, 8), 2)
+        x0 = noise_bank(1, (B, 3, 8, 8), 1)[0]
+        S = R.get_module("samplers", "em_sde")(cfg, sde, fake_score)
+        with NoiseBank(nb):
+            out = S.sample(x0.clone(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+        _save(f"sampler_vp_em_fake_{tag}.npz", final=out.double().numpy(), ts=ts.numpy(), n=np.asarray(n),
+              B=np.asarray(B))
 
 
 def golden_inpaint_all(R):

@@ -313,6 +313,48 @@ def inpaint_em_sample(config, score_fn, x_0, mask, prior, ts, n, noise, denoise=
     return u
 
 
+class VPScalars:
+    """Scalar restatement of ``VPSDE`` (``vpsde.py:8-99``)."""
+
+    def __init__(self, config):
+        self.beta_0, self.beta_1 = float(config.model.sde.beta_min), float(config.model.sde.beta_max)
+        self.T = 1.0
+
+    def beta_t(self, t):                                           # vpsde.py:17-18
+        return self.beta_0 + t * (self.beta_1 - self.beta_0)
+
+    def std(self, t):                                              # vpsde.py:88-92
+        lmc = -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+        return math.sqrt(1.0 - math.exp(2.0 * lmc))
+
+
+def vp_reverse_drift(sde: VPScalars, score_fn, x: torch.Tensor, t: float):
+    """``VPSDE.reverse_sde`` (``vpsde.py:51-74``), probability_flow=False: (f_bar, g)."""
+    tau = sde.T - t
+    beta = sde.beta_t(tau)
+    g = math.sqrt(beta)
+    eps = score_fn(x.to(torch.float32), _tvec(x, float(np.float32(tau))))
+    score = -eps.to(torch.float64) / sde.std(tau)                  # vpsde.py:27-28
+    return 0.5 * beta * x + g ** 2 * score, g
+
+
+def vp_em_sample(config, score_fn, x0, ts, n, noise, denoise=True, eps=1e-3, record=None):
+    """``EulerMaruyamaSampler.sample`` (``sde.py:38-58``) on the VP-SDE; state ``[B,C,H,W]``."""
+    sde = VPScalars(config)
+    x = x0.to(torch.float64)
+    with torch.no_grad():
+        for i in range(n):
+            t, dt = float(ts[i]), float(ts[i + 1] - ts[i])
+            fbar, g = vp_reverse_drift(sde, score_fn, x, t)
+            x = (x + fbar * dt) + g * math.sqrt(dt) * noise[i].to(torch.float64)
+            if record is not None:
+                record(i, x)
+        if denoise:                                                # float32 t, dt (sde.py:52-57)
+            fbar, _ = vp_reverse_drift(sde, score_fn, x, float(np.float32(sde.T - eps)))
+            x = x + fbar * float(np.float32(eps))
+    return x
+
+
 # --------------------------------------------------------------------------------------
 # 3. upfirdn2d (op/upfirdn2d.py:159-200): zero-stuff, pad/crop, TRUE convolution, decimate
 # --------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ def load_reference():
         import samplers  # registers em_sde, sscs_sde, ...
         import samplers.sde as samplers_sde
         from models.sde.psld import PSLD
+        from models.sde.vpsde import VPSDE  # noqa: F401  (registers sde/vpsde)
         from models.score_fn.song_sde.ncsnpp import NCSNpp
         from models.score_fn.song_sde import layerspp, up_or_down_sampling
         from models.score_fn.song_sde.op.upfirdn2d import upfirdn2d_native
@@ -61,7 +62,7 @@ def load_reference():
     finally:
         ce.load = real_load
     _loaded = types.SimpleNamespace(
-        PSLD=PSLD, NCSNpp=NCSNpp, samplers=samplers, samplers_sde=samplers_sde,
+        PSLD=PSLD, VPSDE=VPSDE, NCSNpp=NCSNpp, samplers=samplers, samplers_sde=samplers_sde,
         get_module=util.get_module, util=util, layerspp=layerspp,
         up_or_down_sampling=up_or_down_sampling, upfirdn2d_native=upfirdn2d_native,
     )

@@ -59,6 +59,10 @@ class InpaintStep(C.Structure):
                [("mean_only", C.c_int32), ("_pad", C.c_int32)]
 
 
+class VpStep(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("half_beta", "g2", "neg_inv_std", "dt", "gs")]
+
+
 class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("engine", C.c_int32),
                 ("i", C.c_int32 * OP_NI), ("f", C.c_float * OP_NF),
@@ -91,6 +95,9 @@ EXPORTS = {
     "psld_inpaint_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(InpaintStep), C.c_uint64,
                                        C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),
+    "psld_vp_em_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.POINTER(VpStep), C.c_uint64, C.c_uint64, C.c_int64,
+                                    C.c_void_p]),
     "psld_prior_sample": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_int64, C.c_int64,
                                     C.c_void_p]),
     "psld_quantize_images": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,

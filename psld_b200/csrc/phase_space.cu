@@ -460,6 +460,56 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
   return PSLD_OK;
 }
 
+// ---------------------------------------------------------------- VP-SDE Euler-Maruyama
+template <typename S>
+__global__ void __launch_bounds__(256)
+vp_em_update_kernel(S* __restrict__ xo, const S* __restrict__ xi, float* __restrict__ net_in,
+                    const float* __restrict__ eps, const float* __restrict__ z, int use_philox,
+                    psld_vp_step c, uint64_t seed, uint64_t step, int64_t n) {
+  pdl_wait();
+  const int64_t total = n / 4;
+  const S hb = (S)c.half_beta, g2 = (S)c.g2, nis = (S)c.neg_inv_std, dt = (S)c.dt, gs = (S)c.gs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    St4<S> x = load4<S>(xi + 4 * i);
+    const float4 e = *reinterpret_cast<const float4*>(eps + 4 * i);
+    float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (z) zz = *reinterpret_cast<const float4*>(z + 4 * i);
+    else if (use_philox) zz = Philox::normal4(seed, step, (uint64_t)i);
+    const float ea[4] = {e.x, e.y, e.z, e.w}, za[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const S score = (S)ea[k] * nis;                       // vpsde.py:27-28
+      const S fbar = hb * x.v[k] + g2 * score;              // vpsde.py:60-68
+      x.v[k] = (x.v[k] + fbar * dt) + gs * (S)za[k];        // sde.py:23-25
+    }
+    store4<S>(xo + 4 * i, x);
+    if (net_in)
+      *reinterpret_cast<float4*>(net_in + 4 * i) =
+          make_float4((float)x.v[0], (float)x.v[1], (float)x.v[2], (float)x.v[3]);
+  }
+}
+
+extern "C" int psld_vp_em_update(void* x_out, const void* x_in, int state_dtype, float* net_in,
+                                 const float* eps, const float* z, int use_philox,
+                                 const psld_vp_step* coeffs, uint64_t seed, uint64_t step, int64_t n,
+                                 psld_stream_t stream) {
+  PSLD_CHECK_ARG(x_out && x_in && eps && coeffs && n > 0 && n % 4 == 0,
+                 "psld_vp_em_update: bad arguments");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
+                 "psld_vp_em_update: state dtype must be f64 or f32");
+  const int grid = grid_for(n / 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    launch_pdl(vp_em_update_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (double*)x_out,
+               (const double*)x_in, net_in, eps, z, use_philox, *coeffs, seed, step, n);
+  else
+    launch_pdl(vp_em_update_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (float*)x_out,
+               (const float*)x_in, net_in, eps, z, use_philox, *coeffs, seed, step, n);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
 // ---------------------------------------------------------------- inpainting combine
 template <typename S>
 __global__ void __launch_bounds__(256)

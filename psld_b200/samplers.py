@@ -28,7 +28,7 @@ import torch
 from . import _lib as L
 from .ncsnpp import NCSNpp
 from .registry import register_module
-from .schedule import InpaintTables, PSLDSchedule, StepTables
+from .schedule import InpaintTables, PSLDSchedule, StepTables, VPSchedule, VPStepTables
 
 
 class Sampler(abc.ABC):
@@ -73,7 +73,15 @@ class _FusedSampler(Sampler):
 
     def __init__(self, config, sde, score_fn, corrector_fn=None):
         super().__init__(config, sde, score_fn, corrector_fn=corrector_fn)
-        self.schedule = sde if isinstance(sde, PSLDSchedule) else PSLDSchedule.from_sde(sde)
+        # the reference's em_sde also drives the VP-SDE baseline (duck-typed on sde.reverse_sde)
+        self.vp = None
+        if isinstance(sde, VPSchedule) or str(getattr(sde, "type", "")) == "vpsde":
+            if self.KIND != "em_sde":
+                raise ValueError("the VP-SDE is sampled with em_sde (SSCS is specific to PSLD)")
+            self.vp = sde if isinstance(sde, VPSchedule) else VPSchedule.from_sde(sde)
+            self.schedule = None
+        else:
+            self.schedule = sde if isinstance(sde, PSLDSchedule) else PSLDSchedule.from_sde(sde)
         # options (extra keys under evaluation.sampler.*, all optional)
         sd = str(_opt(config, "state_dtype", os.environ.get("PSLD_B200_STATE", "float64")))
         self.state_dtype = torch.float64 if sd in ("float64", "f64", "fp64") else torch.float32
@@ -92,10 +100,57 @@ class _FusedSampler(Sampler):
     def _embedding(self):
         return getattr(self.score_fn, "embedding_type", "fourier")
 
+    def _sample_vp(self, batch, ts, n, denoise, eps):
+        """Euler-Maruyama on the VP-SDE (state [B,C,H,W]): score_fn + one fused update per step."""
+        lib = L.lib()
+        if isinstance(self.score_fn, NCSNpp):
+            dev = next(self.score_fn.parameters()).device
+        else:
+            dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
+        if batch.numel() % 4:
+            raise ValueError("the state must hold a multiple of 4 elements")
+        B = batch.shape[0]
+        with torch.no_grad(), torch.cuda.device(dev):
+            state = batch.to(device=dev, dtype=self.state_dtype, non_blocking=True).contiguous()
+            if state.data_ptr() == batch.data_ptr():
+                state = state.clone()
+            tabs = VPStepTables(self.vp, ts.detach().to("cpu", torch.float64), n, bool(denoise),
+                                float(eps), self._embedding())
+            noise = None
+            if self.noise is not None:
+                noise = self.noise.to(device=dev, dtype=torch.float32).contiguous()
+                if noise.shape[0] < n or tuple(noise.shape[1:]) != tuple(batch.shape):
+                    raise ValueError(f"noise bank must be [{n},{tuple(batch.shape)}], got {tuple(noise.shape)}")
+            net_in = state.to(torch.float32)
+            tau32 = tabs.tau32.to(dev)
+            sdt = L.dtype_code(self.state_dtype)
+            stream = L.stream_ptr(dev)
+            sp, ip, cnt = L.ptr(state), L.ptr(net_in), state.numel()
+            record = None
+            if self.record is not None:
+                record = torch.empty(n, *state.shape, dtype=self.state_dtype, device=dev)
+            for i in range(n + (1 if denoise else 0)):
+                e = self.score_fn(net_in, tau32[i].expand(B)).to(torch.float32).contiguous()
+                z = L.ptr(noise[i]) if (noise is not None and i < n) else None
+                philox = 1 if (noise is None and i < n) else 0
+                L.check(lib.psld_vp_em_update(sp, sp, sdt, ip, L.ptr(e), z, philox,
+                                              C.byref(tabs.steps[i]), self.seed, i, cnt, stream),
+                        "psld_vp_em_update")
+                if i < n:
+                    self._post_step(state, net_in, record, i, ts)
+            if record is not None:
+                self.record = record
+            self._keep = (tabs, noise, net_in)
+        return state
+
     def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
         lib = L.lib()
         n = int(n_discrete_steps)
         self.nfe = n
+        if self.vp is not None:
+            return self._sample_vp(batch, ts, n, denoise, eps)
         native = isinstance(self.score_fn, NCSNpp)
         if native:
             dev = next(self.score_fn.parameters()).device

@@ -318,3 +318,54 @@ class InpaintTables:
         if denoise:
             self.steps[k - 1].mean_only = 1
         self.tau = tau
+
+
+class VPSchedule:
+    """Scalars of the VP-SDE baseline (reference ``VPSDE``, vpsde.py:8-99)."""
+
+    def __init__(self, config):
+        self.beta_0 = float(config.model.sde.beta_min)
+        self.beta_1 = float(config.model.sde.beta_max)
+
+    @classmethod
+    def from_sde(cls, sde):
+        self = cls.__new__(cls)
+        self.beta_0, self.beta_1 = float(sde.beta_0), float(sde.beta_1)
+        return self
+
+    T = 1.0
+
+    def beta_t(self, t):
+        return self.beta_0 + t * (self.beta_1 - self.beta_0)
+
+    def log_mean_coeff(self, t):                                   # vpsde.py:78-80
+        return -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+
+    def std(self, t):                                              # vpsde.py:88-92
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.log_mean_coeff(t)))
+
+
+class VPStepTables:
+    """Per-step coefficients of Euler-Maruyama on the VP-SDE (sde.py:16-36 x vpsde.py:42-74)."""
+
+    def __init__(self, sch: VPSchedule, ts, n: int, denoise: bool, eps: float, embedding="fourier"):
+        ts = torch.as_tensor(ts, dtype=_F64).cpu()
+        t, dt = ts[:n], ts[1:n + 1] - ts[:n]
+        taus, dts = [sch.T - t], [dt]
+        if denoise:        # float32 t and dt of the denoising call (sde.py:52-57)
+            taus.append(sch.T - torch.tensor([sch.T - eps], dtype=torch.float32).to(_F64))
+            dts.append(torch.tensor([eps], dtype=torch.float32).to(_F64))
+        tau, dta = torch.cat(taus), torch.cat(dts)
+        beta = sch.beta_t(tau)
+        g = torch.sqrt(beta)
+        k = int(tau.numel())
+        self.steps = (L.VpStep * k)()
+        for i in range(k):
+            st = self.steps[i]
+            st.half_beta = float(0.5 * beta[i])
+            st.g2 = float(g[i] ** 2)
+            st.neg_inv_std = float(-1.0 / sch.std(tau[i]))
+            st.dt = float(dta[i])
+            st.gs = float(g[i] * torch.sqrt(dta[i])) if i < n else 0.0
+        self.tau32 = tau.to(torch.float32)
+        self.time_table = torch.log(self.tau32) if embedding == "fourier" else self.tau32.clone()

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as L
 from .registry import register_module
-from .schedule import PSLDSchedule
+from .schedule import PSLDSchedule, VPSchedule
 
 
 @register_module(category="sde", name="psld_b200")
@@ -44,3 +44,19 @@ class PSLD(PSLDSchedule):
         L.check(L.lib().psld_prior_sample(L.ptr(u), float(np.sqrt(self.m)), int(seed), B,
                                           Cc * H * W, L.stream_ptr(u.device)), "psld_prior_sample")
         return u
+
+
+@register_module(category="sde", name="vpsde_b200")
+class VPSDE(VPSchedule):
+    """The VP-SDE baseline (reference ``VPSDE``, vpsde.py:8-99): attribute surface used by sampling."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.N = int(config.model.sde.n_timesteps)
+
+    @property
+    def type(self):
+        return "vpsde"
+
+    def prior_sampling(self, shape):
+        return torch.randn(*shape)

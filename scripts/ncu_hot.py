@@ -12,9 +12,10 @@ topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = rows[1]
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]     # one table per captured launch
+hdr = rows[heads[0]]
 idx = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = rows[heads[0] + 1:(heads[1] - 1 if len(heads) > 1 else len(rows))]
 lo = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 hi = int(sys.argv[4]) if len(sys.argv) > 4 else len(data)
 S = lambda r: int(r[idx["# Samples"]])

@@ -31,3 +31,15 @@ def sampler_inputs(cfg, B, n, kind, seed_p=1, seed_n=2):
 def fake_score(u, t):
     """Same deterministic stand-in network as oracle/make_golden.py (device-agnostic)."""
     return (torch.tanh(u * 0.3) * 0.7 + 0.1 * torch.sin(torch.roll(u, 1, 1))) * t.view(-1, 1, 1, 1)
+
+
+def vp_config(**ev):
+    """VP-SDE baseline config of oracle/make_golden.py::vp_config (sample_uncond_vpsde.sh keys)."""
+    from psld_b200 import tiny_config
+    e = dict(sampler="em_sde", n_discrete_steps=40)
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.model.sde.update(name="vpsde", beta_min=0.1, beta_max=20.0)
+    cfg.model.score_fn.update(in_ch=3, out_ch=3)
+    cfg.data.image_size = 8
+    return cfg

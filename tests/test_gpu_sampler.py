@@ -254,3 +254,53 @@ def test_inpaint_sampler_philox_keeps_known_region():
     assert torch.allclose(a[:, :3][known], (axx * x_0.double())[known], rtol=1e-12, atol=1e-13)
     free = ~known
     assert (a[:, :3][free] - (axx * x_0.double())[free]).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("tag,kw", [("uniform", {}), ("quad", dict(stride_type="quadratic"))])
+def test_vp_sampler_vs_reference_golden(golden_dir, tag, kw):
+    """The reference's em_sde also drives the VP-SDE baseline (sample_uncond_vpsde.sh): fused
+    psld_vp_em_update + host schedule vs the reference's own output."""
+    from _net import vp_config
+    from oracle.weights import noise_bank
+    from psld_b200 import VPSDE
+    g = np.load(f"{golden_dir}/sampler_vp_em_fake_{tag}.npz")
+    cfg = vp_config(**kw)
+    ts, n = time_grid(cfg)
+    B = int(g["B"])
+    S = EulerMaruyamaSampler(cfg, VPSDE(cfg), fake_score)
+    S.state_dtype = torch.float64
+    S.noise = torch.stack(noise_bank(n, (B, 3, 8, 8), 2))
+    x0 = noise_bank(1, (B, 3, 8, 8), 1)[0]
+    out = S.sample(x0.cuda(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps).cpu()
+    ref = torch.from_numpy(g["final"])
+    e = max_rel(out, ref)
+    print(f"vp em_sde {tag}: max-abs/max|ref| {e:.3e}")
+    assert e <= 1e-6
+    with pytest.raises(ValueError):
+        SSCSSampler(cfg, VPSDE(cfg), fake_score)
+
+
+def test_vp_sampler_with_network_vs_oracle():
+    """VP-SDE + NCSN++ (in_ch = out_ch = 3) through the program path vs the CPU oracle."""
+    from _net import vp_config
+    from oracle.weights import noise_bank
+    from psld_b200 import VPSDE
+    cfg = vp_config(n_discrete_steps=12)
+    cfg.data.image_size = 32
+    net, sd = make_net(cfg, "fp32")
+    ts, n = time_grid(cfg)
+    B = 2
+    nb = noise_bank(n, (B, 3, 32, 32), 2)
+    x0 = noise_bank(1, (B, 3, 32, 32), 1)[0]
+    S = EulerMaruyamaSampler(cfg, VPSDE(cfg), net)
+    S.state_dtype = torch.float64
+    S.noise = torch.stack(nb)
+    out = S.sample(x0.cuda(), ts, n).cpu()
+    ref = O.vp_em_sample(cfg, lambda u, t: O.ncsnpp_forward(cfg, sd, u, t), x0, ts, n, nb)
+    e = rel_l2(out, ref)
+    print(f"vp em_sde + NCSN++ fp32: rel-L2 {e:.3e}")
+    assert e <= 1e-5
+    # Philox noise: reproducible and finite
+    S.noise = None
+    a, b = S.sample(x0.cuda(), ts, n), S.sample(x0.cuda(), ts, n)
+    assert torch.equal(a, b) and torch.isfinite(a).all()

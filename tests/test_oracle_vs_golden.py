@@ -172,3 +172,19 @@ def test_inpaint_sampler_algebra(golden_dir, mode):
         known = (mask.numpy() == 1)
         np.testing.assert_allclose(out.numpy()[:, :3][known], (axx * x_0.double().numpy())[known],
                                    rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag,kw", [("uniform", {}), ("quad", dict(stride_type="quadratic"))])
+def test_vp_sampler_algebra(golden_dir, tag, kw):
+    """EM on the VP-SDE baseline (vpsde.py:42-74 under sde.py:16-58) vs the reference's output."""
+    from _net import vp_config
+    g = np.load(f"{golden_dir}/sampler_vp_em_fake_{tag}.npz")
+    cfg = vp_config(**kw)
+    ts, n = O.time_grid(cfg)
+    assert n == int(g["n"])
+    B = int(g["B"])
+    x0 = noise_bank(1, (B, 3, 8, 8), 1)[0]
+    out = O.vp_em_sample(cfg, fake_score, x0, ts, n, noise_bank(n, (B, 3, 8, 8), 2),
+                         denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-7 * np.abs(ref).max()
