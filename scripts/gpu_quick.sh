@@ -6,8 +6,9 @@ mkdir -p gpurun_out
 PT="python -m pytest -q --no-header -p no:cacheprovider --timeout 600 -m gpu"
 if [ -n "${TESTS:-}" ]; then timeout 900 $PT $TESTS 2>&1 | tail -n ${TAILN:-6}; fi
 if [ "${LAUNCHES:-1}" = "1" ]; then
-  B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0 ${BENCH_ARGS:-}"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-1342} -c ${CNT:-450} --csv \
+  B="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --profile-ops 0 --no-graph ${BENCH_ARGS:-}"
+  read SKIP CNT < <(python scripts/launch_window.py 2>/dev/null)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $CNT --csv \
       --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
   echo "launch list rc=$?"
 fi
