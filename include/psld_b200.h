@@ -188,6 +188,8 @@ PSLD_API int psld_quantize_images(const void* state, int state_dtype, uint8_t* o
 #define PSLD_OP_FIR 4    /* upfirdn2d                                                   */
 #define PSLD_OP_CONV 5   /* conv3x3 / conv1x1 / NIN / strided conv as implicit GEMM     */
 #define PSLD_OP_ATTN 6   /* softmax(q k^T / sqrt(C)) v                                  */
+#define PSLD_OP_ZERO 7   /* out[0] = buffer, i[0] | i[1] << 31 = bytes: cudaMemsetAsync(0).  Clears
+                            the GroupNorm statistics accumulators at the top of a program   */
 
 #define PSLD_ENGINE_SIMT 0 /* fp32 FFMA implicit GEMM (any shape)                       */
 #define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0;
@@ -232,10 +234,10 @@ enum { PSLD_TEMB_NT = 0, PSLD_TEMB_NF, PSLD_TEMB_EMB, PSLD_TEMB_TOTALC, PSLD_TEM
  *   in[0] = x1 [N,HW,C1], in[1] = x2 [N,HW,C2] or NULL (virtual torch.cat([x1,x2],1),
  *   ncsnpp.py:374), in[2] = gamma [C], in[3] = beta [C];  out[0] = y [N,HW,C1+C2],
  *   out[1] = scratch, >= N*NCHUNK*G*2 doubles
- *   in[4], in[5] = optional producer-side statistics of x1 / x2: fp32 [N*HW/32, C/4, 2] holding
- *   (sum, sum of squares) per 32 pixels x 4 channels, written by the PSLD_OP_CONV that produced
- *   the tensor (its out[1]).  When every source has them the full-tensor statistics pass is
- *   replaced by a fold over these micro-groups.
+ *   in[4], in[5] = optional producer-side statistics of x1 / x2: f64 [N, C/4, 2] holding
+ *   (sum, sum of squares) per sample x 4 channels, accumulated by the PSLD_OP_CONV that produced
+ *   the tensor (its out[1]).  When every source has them there is no statistics pass at all:
+ *   the apply (or affine) kernel sums the C/G/4 entries of each group itself.
  *   i: N, HW, C1, C2, G, SILU, IN_DTYPE, OUT_DTYPE, NCHUNK, AFFINE_ONLY ; f[0] = eps
  *   AFFINE_ONLY = 1: no apply pass; out[0] receives fp32 [N, C, 2] = (rstd*gamma,
  *   beta - mean*rstd*gamma) for a PSLD_ENGINE_TC_GN convolution to apply on load.            */
@@ -261,8 +263,10 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
  *           in affine-only mode: the conv input is silu?(x * scale + shift), applied in-kernel
  *           (i[GN_SILU] selects the SiLU); x1/x2 are then the RAW, un-normalised tensors
  *   out[0] = y
- *   out[1] = optional fp32 [N*OH*OW/32, Cout/4, 2] micro-group statistics of y for the GroupNorm
- *            that consumes it (TC engine, bf16 NHWC output, OH*OW % 32 == 0), or NULL
+ *   out[1] = optional f64 [N, Cout/4, 2] (sum, sum of squares) of y per sample x 4 channels for the
+ *            GroupNorms that consume it: ACCUMULATED with atomics by the epilogue, so the caller
+ *            zeroes it before the launch (PSLD_OP_ZERO) (TC engines, bf16 NHWC output,
+ *            OH*OW % 32 == 0), or NULL
  *   weight layout: SIMT engine f32 [K, Cout] ; TC engine bf16 [Cout, K], K = (ky*KW+kx)*Cin + c
  *   i: N, H, W, C1, C2, COUT, KS (1|3), STRIDE, PAD, OH, OW, IN_LAYOUT, OUT_LAYOUT,
  *      IN_DTYPE, OUT_DTYPE, RES_DTYPE, TEMB_OFF, TEMB_BSTRIDE ; f[0] = scale            */

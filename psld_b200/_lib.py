@@ -18,7 +18,7 @@ OK, EINVAL, ECUDA, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4
 F32, BF16, F64 = 0, 1, 2
 NHWC, NCHW = 0, 1
 STAGE_HALF_A, STAGE_SCORE, STAGE_HALF_B, STAGE_HALF_C = 1, 2, 4, 8
-OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN = 1, 2, 3, 4, 5, 6
+OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN, OP_ZERO = 1, 2, 3, 4, 5, 6, 7
 ENGINE_SIMT, ENGINE_TC, ENGINE_TC_GN = 0, 1, 2
 OP_NI, OP_NF, OP_NP = 28, 24, 8
 

@@ -35,8 +35,8 @@ static int op_launch_count(const psld_op& op) {
   switch (op.kind) {
     case PSLD_OP_LAYOUT: return 1;
     case PSLD_OP_TEMB: return 4;
-    case PSLD_OP_GN:             // statistics (or fold of producer statistics) + apply / affine;
-      return (op.i[PSLD_GN_AFFINE_ONLY] && op.in[4] && (op.i[PSLD_GN_C2] == 0 || op.in[5])) ? 1 : 2;
+    case PSLD_OP_GN:             // producer-side statistics: apply (or affine) only; else + stats pass
+      return (op.in[4] && (op.i[PSLD_GN_C2] == 0 || op.in[5])) ? 1 : 2;
     case PSLD_OP_FIR: return 1;
     case PSLD_OP_CONV: return 1;
     case PSLD_OP_ATTN: return 1;
@@ -55,6 +55,13 @@ static int dispatch(const psld_op& op, cudaStream_t s) {
       return op.engine == PSLD_ENGINE_TC ? run_conv_tc(op, s) : run_conv_simt(op, s);
     case PSLD_OP_ATTN:
       return op.engine == PSLD_ENGINE_TC ? run_attn_tc(op, s) : run_attn_simt(op, s);
+    case PSLD_OP_ZERO: {         // statistics accumulators (a memset node, not a kernel of ours)
+      const size_t bytes = (size_t)op.i[0] | ((size_t)op.i[1] << 31);
+      if (bytes == 0) return PSLD_OK;
+      PSLD_CHECK_ARG(op.out[0] != nullptr, "zero: null pointer");
+      PSLD_CHECK_CUDA(cudaMemsetAsync(op.out[0], 0, bytes, s));
+      return PSLD_OK;
+    }
     default:
       set_error("unknown op kind %d", op.kind);
       return PSLD_EINVAL;

@@ -433,7 +433,7 @@ int prepare_conv_gn_tc(psld_op& op) {
   p.y = (__nv_bfloat16*)op.out[0];
   p.y_nchw = nullptr;
   p.cout_valid = Cout;
-  p.mg_stats = (float*)op.out[1];
+  p.mg_stats = (double*)op.out[1];
   p.scale = op.f[0];
   p.temb_off = op.i[PSLD_CONV_TEMB_OFF];
   p.temb_bstride = op.i[PSLD_CONV_TEMB_BSTRIDE];

@@ -414,7 +414,7 @@ int prepare_conv_tc(psld_op& op) {
   p.y = head ? nullptr : (__nv_bfloat16*)op.out[0];
   p.y_nchw = head ? (float*)op.out[0] : nullptr;
   p.cout_valid = head ? (int)op.f[1] : Cout;
-  p.mg_stats = (float*)op.out[1];
+  p.mg_stats = (double*)op.out[1];
   if (p.mg_stats && (head || (OH * OW) % 32 != 0)) {
     delete st;
     set_error("conv_tc: micro-group stats need NHWC bf16 output and H*W %% 32 == 0");

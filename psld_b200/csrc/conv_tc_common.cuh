@@ -24,7 +24,8 @@ struct ConvTcParams {
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
   float* y_nchw;             // when non-null: fp32 NCHW output, first cout_valid channels only
-  float* mg_stats;           // optional [M/32, Cout/4, 2] micro-group (sum, sumsq) of the output
+  double* mg_stats;          // optional [N, Cout/4, 2] per-sample (sum, sumsq) of the output per 4
+                             // channels, accumulated with atomics (zeroed by the caller)
   int cout_valid;
   float scale;
   int temb_off, temb_bstride;
@@ -273,9 +274,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       }
       if (stats) {
         // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
-        // granularity: (sum, sum of squares) over this warp's 32 pixels.  16 values per lane are
-        // transposed-and-reduced across the warp with 16 shuffles (halving butterfly); the
-        // consumer GroupNorm combines micro-groups into its groups (gn_finalize_kernel).
+        // granularity: (sum, sum of squares) over this warp's 32 pixels (one sample: HW % 32 ==
+        // 0).  16 values per lane are transposed-and-reduced across the warp with 16 shuffles
+        // (halving butterfly) and accumulated per sample with f64 atomics; the consumer
+        // GroupNorm sums the micro-groups of each of its groups.
         if (!full && !valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -298,8 +300,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
           }
         }
         a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-        if ((lane & 1) == 0)
-          p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1)] = a[0];
+        if ((lane & 1) == 0)     // 16 lanes: 8 micro-groups x (sum, sumsq) of this warp's 32 pixels
+          atomicAdd(p.mg_stats + ((m_base / p.HW) * (p.Cout >> 2) + (co0 >> 2)) * 2 + (lane >> 1),
+                    (double)a[0]);
       }
     };
     if (half < ncg) {
@@ -489,7 +492,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
       if ((lane & 1) == 0) {
         const int idx = lane >> 1;     // = bit4*8 + bit3*4 + bit2*2 + bit1
-        p.mg_stats[((int64_t)slot * (p.Cout >> 2) + (co0 >> 2)) * 2 + idx] = a[0];
+        atomicAdd(p.mg_stats + (((int64_t)slot * 32 / p.HW) * (p.Cout >> 2) + (co0 >> 2)) * 2 + idx,
+                  (double)a[0]);
       }
     }
   }

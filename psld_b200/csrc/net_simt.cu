@@ -293,10 +293,32 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
 }
 
-template <typename TI, typename TO, int VW, bool kFast>
+// (sum, sumsq) of group g of sample n from the producers' per-sample micro-group accumulators
+// (f64 [N, C/4, 2] per source, conv_tc epilogue): cpg/4 consecutive entries, which may straddle
+// the two sources of a virtual concat.
+__device__ __forceinline__ void gn_group_sums(const double* __restrict__ mg1,
+                                              const double* __restrict__ mg2, int n, int C1, int C2,
+                                              int cpg, int g, double& su, double& sq) {
+  const int nmg1 = C1 >> 2, nmg2 = C2 >> 2, per = cpg >> 2;
+  su = 0.0;
+  sq = 0.0;
+  for (int k = 0; k < per; ++k) {
+    const int m = g * per + k;
+    const double2 v = m < nmg1
+        ? *reinterpret_cast<const double2*>(mg1 + ((int64_t)n * nmg1 + m) * 2)
+        : *reinterpret_cast<const double2*>(mg2 + ((int64_t)n * nmg2 + (m - nmg1)) * 2);
+    su += v.x;
+    sq += v.y;
+  }
+}
+
+// kMicro: group statistics come straight from the producers' accumulators (mg1, mg2); otherwise
+// from the `part` chunks written by gn_stats_kernel.
+template <typename TI, typename TO, int VW, bool kFast, bool kMicro>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
-                const double* __restrict__ part, const float* __restrict__ gamma,
+                const double* __restrict__ part, const double* __restrict__ mg1,
+                const double* __restrict__ mg2, const float* __restrict__ gamma,
                 const float* __restrict__ beta, TO* __restrict__ y, int HW, int C1, int C2, int G,
                 int nchunk, int nchunk_apply, float eps, int silu) {
   pdl_wait();
@@ -305,10 +327,14 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
   const int C = C1 + C2, vpr = C / VW, cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double su = 0, sq = 0;
-    for (int k = 0; k < nchunk; ++k) {
-      const double* src = part + ((int64_t)n * nchunk + k) * 2 * G;
-      su += src[2 * g];
-      sq += src[2 * g + 1];
+    if (kMicro) {
+      gn_group_sums(mg1, mg2, n, C1, C2, cpg, g, su, sq);
+    } else {
+      for (int k = 0; k < nchunk; ++k) {
+        const double* src = part + ((int64_t)n * nchunk + k) * 2 * G;
+        su += src[2 * g];
+        sq += src[2 * g + 1];
+      }
     }
     const double cntd = (double)HW * cpg;
     const double mean = su / cntd;
@@ -371,81 +397,26 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
   }
 }
 
-// Pass 1 alternative: the producer convolutions already wrote (sum, sumsq) per 32 pixels x 4
-// channels (conv_tc epilogue); fold those "micro-groups" into this GroupNorm's groups.  Reads
-// ~3% of the tensor instead of all of it.  Output format = one chunk of gn_stats_kernel.
-// All 256 threads stream the (slot, micro-group) items with 8 independent loads in flight (the
-// first version walked the slots serially per thread: ~32 dependent L2 round trips, 8 us).
-// kAffine: write the per-(sample, channel) (scale, shift) pairs for a GroupNorm-on-load
-// convolution directly (no separate gn_affine launch); otherwise write the (sum, sumsq) partials
-// in the format of one gn_stats_kernel chunk for gn_apply_kernel.
-template <bool kAffine>
+// Affine table for a GroupNorm-on-load convolution straight from the producers' accumulators:
+// per (sample, channel) scale = rstd*gamma, shift = beta - mean*scale.  One thread per channel.
 __global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float* __restrict__ mg1, const float* __restrict__ mg2,
-                   double* __restrict__ part, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* __restrict__ affine, int HW, int C1, int C2,
-                   int G, float eps) {
+gn_affine_micro_kernel(const double* __restrict__ mg1, const double* __restrict__ mg2,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ affine, int HW, int C1, int C2, int G, float eps) {
   pdl_wait();
-  extern __shared__ double sh[];  // [2*G] (+ mean/rstd floats behind it when kAffine)
   const int n = blockIdx.x;
   const int C = C1 + C2, cpg = C / G;
-  const int nmg1 = C1 >> 2, nmg = C >> 2, nmg2 = nmg - nmg1, slots = HW >> 5;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
-  const float2* p1 = reinterpret_cast<const float2*>(mg1) + (int64_t)n * slots * nmg1;
-  const float2* p2 = reinterpret_cast<const float2*>(mg2) + (int64_t)n * slots * nmg2;
-  const int total = slots * nmg;
-  int gcur = -1;
-  double su = 0.0, sq = 0.0;
-  auto flush = [&]() {
-    if (gcur >= 0) { atomicAdd(&sh[2 * gcur], su); atomicAdd(&sh[2 * gcur + 1], sq); }
-    su = 0.0; sq = 0.0;
-  };
-  constexpr int U = 8;
-  for (int i0 = threadIdx.x; i0 < total; i0 += U * 256) {
-    float2 v[U];
-    int g[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 256;
-      v[u] = make_float2(0.f, 0.f);
-      g[u] = -1;
-      if (i < total) {
-        const int k = i / nmg, m = i - k * nmg;
-        v[u] = m < nmg1 ? __ldg(p1 + (int64_t)k * nmg1 + m) : __ldg(p2 + (int64_t)k * nmg2 + (m - nmg1));
-        g[u] = (m * 4) / cpg;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (g[u] < 0) continue;
-      if (g[u] != gcur) { flush(); gcur = g[u]; }
-      su += v[u].x;
-      sq += v[u].y;
-    }
-  }
-  flush();
-  __syncthreads();
-  if (!kAffine) {
-    double* dst = part + (int64_t)n * 2 * G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = sh[i];
-  } else {
-    float* mr = reinterpret_cast<float*>(sh + 2 * G);   // mean[G], rstd[G]
-    for (int gq = threadIdx.x; gq < G; gq += blockDim.x) {
-      const double cntd = (double)HW * cpg;
-      const double mean = sh[2 * gq] / cntd;
-      double var = sh[2 * gq + 1] / cntd - mean * mean;
-      if (var < 0) var = 0;
-      mr[gq] = (float)mean;
-      mr[G + gq] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int gq = c / cpg;
-      const float sc = mr[G + gq] * gamma[c];
-      affine[((int64_t)n * C + c) * 2] = sc;
-      affine[((int64_t)n * C + c) * 2 + 1] = beta[c] - sc * mr[gq];
-    }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double su, sq;
+    gn_group_sums(mg1, mg2, n, C1, C2, cpg, c / cpg, su, sq);
+    const double cntd = (double)HW * cpg;
+    const double mean = su / cntd;
+    double var = sq / cntd - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    affine[((int64_t)n * C + c) * 2] = sc;
+    affine[((int64_t)n * C + c) * 2 + 1] = beta[c] - sc * (float)mean;
   }
 }
 
@@ -501,18 +472,15 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   const bool fused = op.in[4] && (C2 == 0 || op.in[5]);
   int nchunk_eff = nchunk;
   if (fused) {
-    PSLD_CHECK_ARG(HW % 32 == 0 && (C / G) % 4 == 0,
-                   "gn: fused statistics need HW %% 32 == 0 and (C/G) %% 4 == 0");
-    if (op.i[PSLD_GN_AFFINE_ONLY]) {     // fold + affine in one launch
-      launch_pdl(gn_finalize_kernel<true>, dim3((unsigned)(N)), dim3(256), sh1 + sh2, s, 1, 
-          (const float*)op.in[4], (const float*)op.in[5], part, (const float*)op.in[2],
-          (const float*)op.in[3], (float*)op.out[0], HW, C1, C2, G, op.f[0]);
+    PSLD_CHECK_ARG((C / G) % 4 == 0, "gn: fused statistics need (C/G) %% 4 == 0");
+    if (op.i[PSLD_GN_AFFINE_ONLY]) {
+      launch_pdl(gn_affine_micro_kernel, dim3((unsigned)N), dim3(256), 0, s, 1, (const double*)op.in[4],
+                 (const double*)op.in[5], (const float*)op.in[2], (const float*)op.in[3],
+                 (float*)op.out[0], HW, C1, C2, G, op.f[0]);
       PSLD_CHECK_LAUNCH();
       return PSLD_OK;
     }
-    launch_pdl(gn_finalize_kernel<false>, dim3((unsigned)(N)), dim3(256), sh1, s, 1, (const float*)op.in[4], (const float*)op.in[5], part,
-                                                 nullptr, nullptr, nullptr, HW, C1, C2, G, op.f[0]);
-    nchunk_eff = 1;
+    nchunk_eff = 1;      // gn_apply_kernel<.., kMicro = true> reads the accumulators itself
   } else {
     dim3 grid(nchunk, N);
 #define GN_STATS(T, VW)                                                                        \
@@ -539,12 +507,16 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   const float eps = op.f[0];
   const float* ga = (const float*)op.in[2];
   const float* be = (const float*)op.in[3];
-#define GN_APPLY(T, VW, FAST)                                                                   \
-  launch_pdl(gn_apply_kernel<T, T, VW, FAST>, grid2, dim3(256), sh2, s, 1, (const T*)op.in[0], (const T*)op.in[1], \
-                                                          part, ga, be, (T*)op.out[0], HW, C1, C2, \
-                                                          G, nchunk_eff, nca, eps, silu)
-  if (idt == PSLD_BF16) { if (v8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 4, true); }
-  else { if (v8) GN_APPLY(float, 8, false); else GN_APPLY(float, 4, false); }
+  const double* m1 = (const double*)op.in[4];
+  const double* m2 = (const double*)op.in[5];
+#define GN_APPLY(T, VW, FAST, MICRO)                                                            \
+  launch_pdl(gn_apply_kernel<T, T, VW, FAST, MICRO>, grid2, dim3(256), sh2, s, 1, (const T*)op.in[0], \
+             (const T*)op.in[1], part, m1, m2, ga, be, (T*)op.out[0], HW, C1, C2, G, nchunk_eff, nca, \
+             eps, silu)
+#define GN_APPLY2(T, VW, FAST) do { if (fused) GN_APPLY(T, VW, FAST, true); else GN_APPLY(T, VW, FAST, false); } while (0)
+  if (idt == PSLD_BF16) { if (v8) GN_APPLY2(__nv_bfloat16, 8, true); else GN_APPLY2(__nv_bfloat16, 4, true); }
+  else { if (v8) GN_APPLY2(float, 8, false); else GN_APPLY2(float, 4, false); }
+#undef GN_APPLY2
 #undef GN_APPLY
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;

@@ -8,7 +8,7 @@ import torch
 from . import _lib as L
 
 KIND_NAMES = {L.OP_LAYOUT: "layout", L.OP_TEMB: "temb", L.OP_GN: "groupnorm", L.OP_FIR: "fir",
-              L.OP_CONV: "conv", L.OP_ATTN: "attention"}
+              L.OP_CONV: "conv", L.OP_ATTN: "attention", L.OP_ZERO: "zero"}
 
 
 def op_name(op):

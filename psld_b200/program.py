@@ -54,7 +54,9 @@ class Plan:
         self.ops = []
         self.pool = {}
         self.engine_count = {"tc": 0, "simt": 0}
-        self.mg = {}            # data_ptr of an activation -> its micro-group statistics tensor
+        self.mg = {}            # data_ptr of an activation -> its GroupNorm statistics accumulator
+        self.stat_chunks = []   # f64 arenas the accumulators are carved from (zeroed by OP_ZERO)
+        self.stat_used = []
         self.fused_stats = True
         self.fuse_gn = True
         self.fuse_gn_residual = False   # also fuse GroupNorm_1 into Conv_1 (residual epilogue)
@@ -107,14 +109,33 @@ class Plan:
 
     def _release(self, t):
         self.pool.setdefault(tuple(t.shape), []).append(t)
-        st = self.mg.pop(t.data_ptr(), None)
-        if st is not None:
-            self.pool.setdefault(("mg",) + tuple(st.shape), []).append(st)
+        self.mg.pop(t.data_ptr(), None)     # accumulators are never reused within a step
 
-    def _mg_buffer(self, rows, cout):
-        key = ("mg", rows // 32, cout // 4, 2)
-        lst = self.pool.setdefault(key, [])
-        return lst.pop() if lst else self._new(rows // 32, cout // 4, 2, dtype=torch.float32)
+    _STAT_CHUNK = 1 << 22       # doubles per arena (32 MB)
+    _STAT_SLOTS = 4             # OP_ZERO placeholders at the top of the program
+
+    def _mg_buffer(self, n, cout):
+        """f64 [n, cout/4, 2] accumulator (sum, sumsq per sample x 4 channels), carved from an
+        arena that one OP_ZERO clears at the top of every program run."""
+        need = n * (cout // 4) * 2
+        if not self.stat_chunks or self.stat_used[-1] + need > self.stat_chunks[-1].numel():
+            if len(self.stat_chunks) == self._STAT_SLOTS:
+                raise RuntimeError("psld_b200: GroupNorm statistics arena exhausted")
+            self.stat_chunks.append(self._new(max(self._STAT_CHUNK, need), dtype=torch.float64))
+            self.stat_used.append(0)
+        off = self.stat_used[-1]
+        self.stat_used[-1] = off + need
+        view = self.stat_chunks[-1].narrow(0, off, need).view(n, cout // 4, 2)
+        self.keep.append(view)
+        return view
+
+    def _finish_stat_arenas(self, zero_ops):
+        for k, idx in enumerate(zero_ops):
+            op = self.ops[idx]
+            if k < len(self.stat_chunks):
+                nbytes = self.stat_used[k] * 8
+                op.out[0] = self.stat_chunks[k].data_ptr()
+                op.i[0], op.i[1] = nbytes & 0x7FFFFFFF, nbytes >> 31
 
     def _w(self, t, dtype=torch.float32):
         t = t.detach().to(device=self.dev, dtype=dtype).contiguous()
@@ -254,7 +275,7 @@ class Plan:
             op.inp[4] = wt.data_ptr()
             mg = None
             if self.fused_stats and want_stats and (OH * OW) % 32 == 0:
-                mg = self._mg_buffer(N * OH * OW, Cout)
+                mg = self._mg_buffer(N, Cout)
                 op.out[1] = mg.data_ptr()
             if not self.dry:
                 L.check(self.lib.psld_op_prepare(C.byref(op)), "psld_op_prepare(conv_gn)")
@@ -293,14 +314,13 @@ class Plan:
             op.f[1] = float(Cout)                    # valid output channels (NCHW f32 epilogue)
             mg = None
             if self.fused_stats and want_stats and not out_nchw_f32 and (OH * OW) % 32 == 0 and Cout % 32 == 0:
-                mg = self._mg_buffer(N * OH * OW, Cout)
+                mg = self._mg_buffer(N, Cout)
                 op.out[1] = mg.data_ptr()
             rc = self._tc_eligible(op) if self.dry else self.lib.psld_op_prepare(C.byref(op))
             if rc == L.OK and mg is not None:
                 self.mg[out.data_ptr()] = mg
             elif mg is not None:
                 op.out[1] = None
-                self.pool.setdefault(("mg",) + tuple(mg.shape), []).append(mg)
             if rc == L.OK:
                 done = True
                 self.engine_count["tc"] += 1
@@ -462,6 +482,8 @@ class Plan:
         self.gn_scratch = None
         self.x_in = self._new(B, net.in_ch, H, H, dtype=torch.float32)        # NCHW fp32 input
         self.time_buf = self._new(self.nt, dtype=torch.float32)
+        # the GroupNorm statistics accumulators are cleared first (pointers / sizes filled in at the end)
+        zero_ops = [self._push(self._op(L.OP_ZERO)) for _ in range(self._STAT_SLOTS)]
         i = 0
         # ---- time embedding + every Dense_0 projection in one op
         if not net.noise_cond:
@@ -545,6 +567,7 @@ class Plan:
         a = self.op_gn(h, None, mods[i], True, h.shape[1] * h.shape[2]); i += 1
         self.eps = self.op_conv(a, None, mods[i].weight, mods[i].bias, ks=3, out_nchw_f32=True); i += 1
         assert i == len(mods), (i, len(mods))
+        self._finish_stat_arenas(zero_ops)
 
     # ---------------------------------------------------------------- execution
     def run(self, stream=None):

@@ -93,7 +93,7 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
         i[L.CONV_GN_SILU] = int(gn_silu)
         keep.append(affine)
     if mg_stats:
-        mg = torch.full((N * OH * OW // 32, Cout // 4, 2), float("nan"), dtype=torch.float32, device=dev)
+        mg = torch.zeros((N, Cout // 4, 2), dtype=torch.float64, device=dev)    # accumulated: zero first
         op.out[1] = mg.data_ptr()
         keep.append(mg)
     return op, out, keep
@@ -120,8 +120,8 @@ def conv_ref(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=No
 
 
 def mg_ref(y_nhwc):
-    """Micro-group statistics [rows/32, C/4, 2] of an NHWC tensor (fp64)."""
-    v = y_nhwc.double().cpu().reshape(-1, 32, y_nhwc.shape[-1] // 4, 4)
+    """Per-sample micro-group statistics [N, C/4, 2] of an NHWC tensor (fp64)."""
+    v = y_nhwc.double().cpu().reshape(y_nhwc.shape[0], -1, y_nhwc.shape[-1] // 4, 4)
     return torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1)
 
 

@@ -32,7 +32,13 @@ def run_plan(plan, x, t):
     plan.time_buf.copy_(t)
     for op in plan.ops:
         i, f = op.i, op.f
-        if op.kind == L.OP_LAYOUT:
+        if op.kind == L.OP_ZERO:
+            if op.out[0]:
+                ch = next(c for c in plan.stat_chunks if c.data_ptr() == op.out[0])
+                nbytes = i[0] | (i[1] << 31)
+                assert nbytes % 8 == 0 and nbytes // 8 <= ch.numel()
+                ch[: nbytes // 8].zero_()
+        elif op.kind == L.OP_LAYOUT:
             src, dst = g(op.inp[0]), g(op.out[0])
             if i[L.LAYOUT_DIR] == 0:
                 dst.zero_()
@@ -63,7 +69,7 @@ def run_plan(plan, x, t):
                 for src, st in ((x1, g(op.inp[4])), (x2, g(op.inp[5]))):
                     if src is None:
                         continue
-                    v = _f(src).reshape(-1, 32, src.shape[-1] // 4, 4)
+                    v = _f(src).double().reshape(src.shape[0], -1, src.shape[-1] // 4, 4)
                     ref = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1)
                     assert st is not None and tuple(st.shape) == tuple(ref.shape), (st.shape, ref.shape)
                     # bf16 plans: the producer summed unrounded fp32 values, tolerate the rounding
@@ -133,9 +139,9 @@ def run_plan(plan, x, t):
                 y = y + _f(g(op.inp[2])).permute(0, 3, 1, 2)
             y = y * f[0]
             out = g(op.out[0])
-            if op.out[1]:
-                v = y.permute(0, 2, 3, 1).reshape(-1, 32, cout // 4, 4)
-                g(op.out[1]).copy_(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1))
+            if op.out[1]:      # accumulated (the program zeroes the arena first)
+                v = y.permute(0, 2, 3, 1).double().reshape(y.shape[0], -1, cout // 4, 4)
+                g(op.out[1]).add_(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1))
             if i[L.CONV_OUT_LAYOUT] == L.NCHW:
                 valid = int(f[1]) if op.engine == L.ENGINE_TC else cout
                 out.copy_(y[:, :valid])
