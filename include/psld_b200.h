@@ -200,7 +200,7 @@ PSLD_API int psld_quantize_images(const void* state, int state_dtype, uint8_t* o
 
 #define PSLD_OP_NI 28
 #define PSLD_OP_NF 24
-#define PSLD_OP_NP 8
+#define PSLD_OP_NP 10
 
 /* Generic op record.  Slot meaning per kind is documented next to each PSLD_*_ index
  * enum below; unused slots must be zero.                                              */
@@ -255,13 +255,14 @@ enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR
  *   up_or_down_sampling.py:178; epilogue terms layerspp.py:262-274,88-91, ncsnpp.py:353-356)
  *   in[0] = x1, in[1] = x2 or NULL, in[2] = residual [N,OH,OW,Cout] or NULL,
  *   in[3] = temb proj (f32) or NULL, in[4] = weight, in[5] = bias f32 [Cout] or NULL
- *   in[6], in[7] = (engine PSLD_ENGINE_TC, i[EXT_C1] > 0) a second input cat(e1, e2) [N,OH,OW,EXT_C1+EXT_C2]
+ *   in[8], in[9] = (tensor-core engines, i[EXT_C1] > 0) a second input cat(e1, e2) [N,OH,OW,EXT_C1+EXT_C2]
  *           whose 1x1 convolution is accumulated into the same output tile: y = scale*(conv(x,W) +
  *           conv1x1(e, We) + bias + ...); the weight is then [Cout, K + EXT_C1 + EXT_C2] with the
  *           1x1 part appended along K (ResnetBlockBigGANpp's Conv_2 shortcut, layerspp.py:269-274)
  *   in[6] = (engine PSLD_ENGINE_TC_GN) fp32 [N, Cin, 2] (scale, shift) produced by a PSLD_OP_GN
  *           in affine-only mode: the conv input is silu?(x * scale + shift), applied in-kernel
- *           (i[GN_SILU] selects the SiLU); x1/x2 are then the RAW, un-normalised tensors
+ *           (i[GN_SILU] selects the SiLU); x1/x2 are then the RAW, un-normalised tensors (the
+ *           extension input e, if any, is never normalised)
  *   out[0] = y
  *   out[1] = optional f64 [N, Cout/4, 2] (sum, sum of squares) of y per sample x 4 channels for the
  *            GroupNorms that consume it: ACCUMULATED with atomics by the epilogue, so the caller

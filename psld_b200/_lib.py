@@ -20,7 +20,7 @@ NHWC, NCHW = 0, 1
 STAGE_HALF_A, STAGE_SCORE, STAGE_HALF_B, STAGE_HALF_C = 1, 2, 4, 8
 OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN, OP_ZERO = 1, 2, 3, 4, 5, 6, 7
 ENGINE_SIMT, ENGINE_TC, ENGINE_TC_GN = 0, 1, 2
-OP_NI, OP_NF, OP_NP = 28, 24, 8
+OP_NI, OP_NF, OP_NP = 28, 24, 10
 
 # slot indices
 (LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE, LAYOUT_CPAD) = range(6)

@@ -53,7 +53,7 @@ struct ConvGnParams {
 };
 
 struct ConvGnState {
-  CUtensorMap a1, a2, b;
+  CUtensorMap a1, a2, b, e1, e2;
   ConvGnParams p;
   int grid;
 };
@@ -75,7 +75,8 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 __global__ void __launch_bounds__(GN_THREADS, 1)
 conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const ConvGnParams gp) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmE1,
+                  const __grid_constant__ CUtensorMap tmE2, const ConvGnParams gp) {
   const ConvTcParams& p = gp.c;
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();      // single wave of persistent CTAs (see conv_tc.cu)
@@ -106,6 +107,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.ext_kchunks > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE2) : "memory");
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(raw_full(b), 1);
       mbar_init(a_ready(b), 2);       // one elected arrive per CTA of the pair
@@ -135,6 +140,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   // added spills; all warps keep the launch allocation.)
   const int b_rows = p.block_n >> 1;
   const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
+  // K = 9 taps x normalised input chunks, then the 1x1 shortcut chunks over a second, raw input
+  const int total_chunks = p.kchunks + p.ext_kchunks;
 
   if (warp == 0) {
     // ===================== raw activation tile producer =====================
@@ -146,11 +153,19 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
         const int n0 = m_tile / p.tiles_y;
         const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
-        for (int cc = 0; cc < p.kchunks; ++cc) {
+        for (int cc = 0; cc < total_chunks; ++cc) {
           mbar_wait(c_empty(buf), ph ^ 1);      // centre slot free (its 3 taps are issued first)
           mbar_arrive_expect_tx(raw_full(buf), raw_bytes);
-          const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
-          const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+          const CUtensorMap* tmA;
+          int c0;
+          if (cc < p.kchunks) {
+            tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
+            c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+          } else {                              // un-normalised shortcut input (centre tap only)
+            const int e = cc - p.kchunks;
+            tmA = e < p.ext_kchunks1 ? &tmE1 : &tmE2;
+            c0 = (e < p.ext_kchunks1 ? e : e - p.ext_kchunks1) * TC_BLOCK_K;
+          }
           tma_load_4d(abuf(buf) + GN_VAR_BYTES, tmA, raw_full(buf), c0, 0, y0, n0);  // centre slot
           if (++buf == 2) { buf = 0; ph ^= 1; }
         }
@@ -165,14 +180,15 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
         const int n_tile = unit % p.n_tiles_n;
         const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
-        for (int cc = 0; cc < p.kchunks; ++cc) {
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int tap = gn_tap(t9);
+        for (int cc = 0; cc < total_chunks; ++cc) {
+          const int ntap = cc < p.kchunks ? 9 : 1;
+          for (int t9 = 0; t9 < ntap; ++t9) {
+            const int kblk = cc < p.kchunks ? gn_tap(t9) * p.kchunks + cc : 8 * p.kchunks + cc;
             mbar_wait(b_empty(stage), ph ^ 1);
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
               tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, &tmB, b_full(stage),
-                               (tap * p.kchunks + cc) * TC_BLOCK_K, bn0);
+                               kblk * TC_BLOCK_K, bn0);
             }
             __syncwarp();
             if (++stage == GN_B_STAGES) { stage = 0; ph ^= 1; }
@@ -193,11 +209,12 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int cc = 0; cc < p.kchunks; ++cc) {
+        for (int cc = 0; cc < total_chunks; ++cc) {
           mbar_wait_cluster(a_ready(buf), aph);
           tc_fence_after();
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int tap = gn_tap(t9);
+          const int ntap = cc < p.kchunks ? 9 : 1;     // shortcut chunks: the centre tap of the raw tile
+          for (int t9 = 0; t9 < ntap; ++t9) {
+            const int tap = ntap == 9 ? gn_tap(t9) : 4;
             const int ky = tap / 3, kx = tap - ky * 3;
             mbar_wait(b_full(stage), bph);
             tc_fence_after();
@@ -211,8 +228,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                 tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                  (cc > 0 || t9 > 0 || k > 0) ? 1u : 0u);
               tc_commit_pair(b_empty(stage));
-              if (t9 == 2) tc_commit_pair(c_empty(buf));   // raw tile of chunk cc+2 may land
-              if (t9 == 8) tc_commit_pair(a_empty(buf));
+              if (t9 == 2 || ntap == 1) tc_commit_pair(c_empty(buf));   // raw tile of chunk cc+2 may land
+              if (t9 == ntap - 1) tc_commit_pair(a_empty(buf));
             }
             __syncwarp();
             if (++stage == GN_B_STAGES) { stage = 0; bph ^= 1; }
@@ -244,7 +261,17 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const int n0 = m_tile / p.tiles_y;
       const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
       const bool img_ok = n0 < gp.n_images;
-      for (int cc = 0; cc < p.kchunks; ++cc) {
+      for (int cc = 0; cc < total_chunks; ++cc) {
+        if (cc >= p.kchunks) {
+          // shortcut chunk: the tensor core reads the raw centre tile as it landed; only relay
+          // "this CTA's tile is in place" to the leader (same barrier protocol as a transform)
+          mbar_wait(raw_full(buf), ph);
+          mbar_wait(a_empty(buf), ph ^ 1);
+          asm volatile("bar.sync 1, %0;" ::"n"(GN_TRANSFORM_WARPS * 32) : "memory");
+          if (tt == 0) mbar_arrive_remote(leader_ready0 + 8u * (uint32_t)buf);
+          if (++buf == 2) { buf = 0; ph ^= 1; }
+          continue;
+        }
         float sc[8], sh[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) { sc[q] = 0.f; sh[q] = 0.f; }
@@ -422,7 +449,20 @@ int prepare_conv_gn_tc(psld_op& op) {
   if (rc == PSLD_OK)
     rc = C2 > 0 ? encode_raw_map(&st->a2, op.in[1], N, H, W, C2, BH + 2)
                 : encode_raw_map(&st->a2, op.in[0], N, H, W, C1, BH + 2);
-  const int K = 9 * (C1 + C2);
+  // optional 1x1 shortcut over a second, un-normalised input cat(e1, e2): extra K-blocks
+  const int E1 = op.i[PSLD_CONV_EXT_C1], E2 = op.i[PSLD_CONV_EXT_C2];
+  const bool ext = op.in[8] != nullptr && E1 > 0;
+  if (ext && (E1 % TC_BLOCK_K || E2 % TC_BLOCK_K || (E2 > 0 && !op.in[9]))) {
+    delete st;
+    return unsupported("shortcut extension needs E %% 64 == 0");
+  }
+  if (rc == PSLD_OK)
+    rc = ext ? encode_raw_map(&st->e1, op.in[8], N, H, W, E1, BH + 2)
+             : encode_raw_map(&st->e1, op.in[0], N, H, W, C1, BH + 2);
+  if (rc == PSLD_OK)
+    rc = (ext && E2 > 0) ? encode_raw_map(&st->e2, op.in[9], N, H, W, E2, BH + 2)
+                         : encode_raw_map(&st->e2, op.in[0], N, H, W, C1, BH + 2);
+  const int K = 9 * (C1 + C2) + (ext ? E1 + E2 : 0);
   if (rc == PSLD_OK) rc = encode_w_half_map(&st->b, op.in[4], Cout, K, block_n / 2);
   if (rc != PSLD_OK) { delete st; return rc; }
   ConvGnParams& g = st->p;
@@ -442,7 +482,8 @@ int prepare_conv_gn_tc(psld_op& op) {
   p.BH = BH; p.BN_img = 1; p.tiles_y = H / BH;
   p.kchunks1 = C1 / TC_BLOCK_K; p.kchunks = (C1 + C2) / TC_BLOCK_K;
   p.taps = 9; p.KS = 3;
-  p.ext_kchunks1 = 0; p.ext_kchunks = 0;
+  p.ext_kchunks1 = ext ? E1 / TC_BLOCK_K : 0;
+  p.ext_kchunks = ext ? (E1 + E2) / TC_BLOCK_K : 0;
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * H * W;
   p.num_tiles = (int)(((m_tiles + 1) / 2) * p.n_tiles_n);
@@ -481,7 +522,7 @@ int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
   const ConvGnState* st = (const ConvGnState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
   PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
-                             s, 2, st->a1, st->a2, st->b, st->p));
+                             s, 2, st->a1, st->a2, st->b, st->e1, st->e2, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

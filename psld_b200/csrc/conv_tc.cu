@@ -392,16 +392,16 @@ int prepare_conv_tc(psld_op& op) {
     rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, OW, BH, BN_img, stride)
                 : encode_act_map(&st->a2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   const int E1 = op.i[PSLD_CONV_EXT_C1], E2 = op.i[PSLD_CONV_EXT_C2];
-  const bool ext = op.in[6] != nullptr && E1 > 0;
-  if (ext && (stride != 1 || E1 % TC_BLOCK_K || E2 % TC_BLOCK_K || (E2 > 0 && !op.in[7]))) {
+  const bool ext = op.in[8] != nullptr && E1 > 0;
+  if (ext && (stride != 1 || E1 % TC_BLOCK_K || E2 % TC_BLOCK_K || (E2 > 0 && !op.in[9]))) {
     delete st;
     return unsupported("1x1 extension needs stride 1 and channel counts %% 64 == 0");
   }
   if (rc == PSLD_OK)
-    rc = ext ? encode_act_map(&st->e1, op.in[6], N, OH, OW, E1, OW, BH, BN_img, 1)
+    rc = ext ? encode_act_map(&st->e1, op.in[8], N, OH, OW, E1, OW, BH, BN_img, 1)
              : encode_act_map(&st->e1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   if (rc == PSLD_OK)
-    rc = (ext && E2 > 0) ? encode_act_map(&st->e2, op.in[7], N, OH, OW, E2, OW, BH, BN_img, 1)
+    rc = (ext && E2 > 0) ? encode_act_map(&st->e2, op.in[9], N, OH, OW, E2, OW, BH, BN_img, 1)
                          : encode_act_map(&st->e2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
   const int K = KS * KS * (C1 + C2) + (ext ? E1 + E2 : 0);
   if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, pair ? block_n / 2 : block_n);

@@ -271,7 +271,19 @@ class Plan:
             op.engine = L.ENGINE_TC_GN
             op.inp[6] = affine.data_ptr()
             i[L.CONV_GN_SILU] = int(gn_silu)
-            wt = self._w(w.permute(0, 2, 3, 1).reshape(Cout, -1), torch.bfloat16)
+            wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+            if ext is not None:      # 1x1 shortcut over the (un-normalised) block input: extra K-blocks
+                e1, e2, we, be = ext
+                wt = torch.cat([wt, we.detach().to(self.dev, torch.float32).reshape(Cout, -1)], 1)
+                op.inp[8] = e1.data_ptr()
+                op.inp[9] = e2.data_ptr() if e2 is not None else None
+                i[L.CONV_EXT_C1] = e1.shape[-1]
+                i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
+                if be is not None:
+                    b32 = self._w((bias.detach().to(self.dev, torch.float32) if bias is not None else 0) +
+                                  be.detach().to(self.dev, torch.float32))
+                    op.inp[5] = b32.data_ptr()
+            wt = self._w(wt, torch.bfloat16)
             op.inp[4] = wt.data_ptr()
             mg = None
             if self.fused_stats and want_stats and (OH * OW) % 32 == 0:
@@ -294,8 +306,8 @@ class Plan:
                 # A source (centre tap), its bias joins the conv bias
                 e1, e2, we, be = ext
                 wt = torch.cat([wt, we.detach().to(self.dev, torch.float32).reshape(Cout, -1)], 1)
-                op.inp[6] = e1.data_ptr()
-                op.inp[7] = e2.data_ptr() if e2 is not None else None
+                op.inp[8] = e1.data_ptr()
+                op.inp[9] = e2.data_ptr() if e2 is not None else None
                 i[L.CONV_EXT_C1] = e1.shape[-1]
                 i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
                 if be is not None:
@@ -384,14 +396,20 @@ class Plan:
         scale = _SQRT1_2 if net.skip_rescale else 1.0
         if not (m.up or m.down) and self._gn_fusable(x1, x2, m.out_ch):
             # act(GroupNorm_0(.)) -> Conv_0 runs as ONE GroupNorm-on-load convolution: the
-            # statistics pass only emits a per-(sample, channel) affine, there is no apply pass.
-            # (Conv_1 keeps the separate apply: measured, the fused kernel loses more on its
-            # residual epilogue - 96 registers per thread with 640 threads - than the apply costs.)
+            # GroupNorm op only emits a per-(sample, channel) affine, there is no apply pass.  The
+            # same for act(GroupNorm_1(.)) -> Conv_1 of the identity-shortcut blocks (residual add
+            # in the epilogue).
             aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
-            gn1 = self.fuse_gn_residual or (os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
-                                            and not hasattr(m, "Conv_2"))
+            gn1 = self.fuse_gn_residual or os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
+            if gn1 and hasattr(m, "Conv_2"):
+                # blocks with a Conv_2 shortcut keep the unfused Conv_1 (apply pass + conv_tc with
+                # the shortcut as K-extension): the fused kernel accepts the extension too, but its
+                # two big operand buffers cannot hide the load latency of one-tap chunks (measured
+                # +1.1 ms of conv for -0.64 ms of GroupNorm per step); PSLD_TC_FUSE_GN_EXT=1 enables it
+                gn1 = (os.environ.get("PSLD_TC_FUSE_GN_EXT", "0") == "1"
+                       and self._ext_fusable(h, x1, x2, m.out_ch))
             if gn1 and self._gn_fusable(h, None, m.out_ch):
                 aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
                 b, b_aff = h, aff1
@@ -401,7 +419,7 @@ class Plan:
                 b_aff = None
             ext, sc = None, None
             if hasattr(m, "Conv_2"):
-                if b_aff is None and self._ext_fusable(b, x1, x2, m.out_ch):
+                if self._ext_fusable(b, x1, x2, m.out_ch):
                     ext = (x1, x2, m.Conv_2.weight, m.Conv_2.bias)
                 else:
                     sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)

@@ -65,8 +65,8 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
         if ext is not None:      # (e1, e2, w_ext [Cout, E, 1, 1]): fused 1x1 shortcut
             e1, e2, we = ext
             wt = torch.cat([wt, we.to(dev, torch.float32).reshape(Cout, -1)], 1)
-            op.inp[6] = e1.data_ptr()
-            op.inp[7] = e2.data_ptr() if e2 is not None else None
+            op.inp[8] = e1.data_ptr()
+            op.inp[9] = e2.data_ptr() if e2 is not None else None
             i[L.CONV_EXT_C1] = e1.shape[-1]
             i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
             keep += [e1, e2]

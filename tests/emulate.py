@@ -110,11 +110,11 @@ def run_plan(plan, x, t):
                 xx = xx.to(torch.bfloat16).float()
             w = _f(g(op.inp[4]))
             w_ext, x_ext = None, None
-            if op.engine == L.ENGINE_TC and i[L.CONV_EXT_C1] > 0:    # fused 1x1 shortcut (K-extension)
+            if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN) and i[L.CONV_EXT_C1] > 0:    # fused 1x1 shortcut (K-extension)
                 ne = i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]
                 w_ext = w[:, ks * ks * Cin:].reshape(cout, ne, 1, 1)
                 w = w[:, : ks * ks * Cin]
-                e1, e2 = g(op.inp[6]), g(op.inp[7])
+                e1, e2 = g(op.inp[8]), g(op.inp[9])
                 x_ext = _f(e1) if e2 is None else torch.cat([_f(e1), _f(e2)], -1)
                 assert x_ext.shape[-1] == ne
             if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN):

@@ -384,6 +384,33 @@ def test_conv_tc_fused_shortcut(case):
     assert err <= 4e-3, err
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 256, 256, 256, 256), (3, 16, 16, 256, 256, 0, 256),
+                                  (2, 32, 32, 128, 64, 0, 128), (3, 16, 16, 256, 128, 256, 256)])
+def test_conv_gn_fused_with_shortcut(case):
+    """GroupNorm_1+SiLU on load -> Conv_1, plus the Conv_2 1x1 shortcut over the RAW block input
+    cat(e1, e2) as extra K-blocks of the same accumulation (layerspp.py:262-274)."""
+    N, H, W, Cb, E1, E2, Cout = case
+    r = _rng(sum(case) + 13)
+    h = _t(r.standard_normal((N, H, W, Cb)) * 1.5 + 0.2, torch.bfloat16)
+    e1 = _t(r.standard_normal((N, H, W, E1)), torch.bfloat16)
+    e2 = _t(r.standard_normal((N, H, W, E2)), torch.bfloat16) if E2 else None
+    w = _t(r.standard_normal((Cout, Cb, 3, 3)) / np.sqrt(Cb * 9))
+    we = _t(r.standard_normal((Cout, E1 + E2, 1, 1)) / np.sqrt(E1 + E2))
+    bias = _t(0.1 * r.standard_normal(Cout))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cb)), 0.2 * r.standard_normal((N, Cb))], -1))
+    op, out, keep = conv_op(h, None, w, bias, engine=L.ENGINE_TC_GN, scale=0.7071, ext=(e1, e2, we),
+                            mg_stats=True, affine=aff, gn_silu=True)
+    run_op(op, prepare=True)
+    a = F.silu(h.float().cpu() * aff.cpu()[:, None, None, :, 0] + aff.cpu()[:, None, None, :, 1])
+    a = a.to(torch.bfloat16)
+    ref = conv_ref(a, None, w.to(torch.bfloat16), bias) + conv_ref(e1, e2, we.to(torch.bfloat16), None)
+    ref = ref * 0.7071
+    err = rel_l2(out.float().permute(0, 3, 1, 2), ref)
+    assert err <= 6e-3, err
+    mref = mg_ref(ref.permute(0, 2, 3, 1))
+    assert float((keep[-1].double().cpu() - mref).abs().max()) <= 5e-3 * float(mref.abs().max())
+
+
 def test_conv_tc_output_head():
     """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
     r = _rng(77)
