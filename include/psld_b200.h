@@ -246,9 +246,11 @@ enum { PSLD_GN_N = 0, PSLD_GN_HW, PSLD_GN_C1, PSLD_GN_C2, PSLD_GN_G, PSLD_GN_SIL
 
 /* --- PSLD_OP_FIR (upfirdn2d, op/upfirdn2d.py:159-200; callers up_or_down_sampling.py:195-257):
  *   in[0] = x [N,H,W,C] ; out[0] = y [N,OH,OW,C]
- *   i: N, H, W, C, UP, DOWN, PAD0, PAD1, KH (== KW <= 4), DTYPE ; f[0..KH*KW) = taps (unflipped) */
+ *   i: N, H, W, C, UP, DOWN, PAD0, PAD1, KH (== KW <= 4), DTYPE, CACT ; f[0..KH*KW) = taps (unflipped)
+ *   CACT > 0: only channels [0, CACT) are filtered and written (C and CACT multiples of 8): for the
+ *   channel-padded network input, whose padding channels stay at the zeros they were allocated with */
 enum { PSLD_FIR_N = 0, PSLD_FIR_H, PSLD_FIR_W, PSLD_FIR_C, PSLD_FIR_UP, PSLD_FIR_DOWN,
-       PSLD_FIR_PAD0, PSLD_FIR_PAD1, PSLD_FIR_KH, PSLD_FIR_DTYPE };
+       PSLD_FIR_PAD0, PSLD_FIR_PAD1, PSLD_FIR_KH, PSLD_FIR_DTYPE, PSLD_FIR_CACT };
 
 /* --- PSLD_OP_CONV: y = scale * (conv(cat(x1,x2), W) + bias + temb[n,:] + residual)
  *   (ddpm_conv3x3/conv1x1 layers.py:85-109; NIN layers.py:531-540; F.conv2d(stride=2)

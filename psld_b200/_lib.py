@@ -27,7 +27,8 @@ OP_NI, OP_NF, OP_NP = 28, 24, 10
 (TEMB_NT, TEMB_NF, TEMB_EMB, TEMB_TOTALC, TEMB_LOGGED) = range(5)
 (GN_N, GN_HW, GN_C1, GN_C2, GN_G, GN_SILU, GN_IN_DTYPE, GN_OUT_DTYPE, GN_NCHUNK,
  GN_AFFINE_ONLY) = range(10)
-(FIR_N, FIR_H, FIR_W, FIR_C, FIR_UP, FIR_DOWN, FIR_PAD0, FIR_PAD1, FIR_KH, FIR_DTYPE) = range(10)
+(FIR_N, FIR_H, FIR_W, FIR_C, FIR_UP, FIR_DOWN, FIR_PAD0, FIR_PAD1, FIR_KH, FIR_DTYPE,
+ FIR_CACT) = range(11)
 (CONV_N, CONV_H, CONV_W, CONV_C1, CONV_C2, CONV_COUT, CONV_KS, CONV_STRIDE, CONV_PAD, CONV_OH,
  CONV_OW, CONV_IN_LAYOUT, CONV_OUT_LAYOUT, CONV_IN_DTYPE, CONV_OUT_DTYPE, CONV_RES_DTYPE,
  CONV_TEMB_OFF, CONV_TEMB_BSTRIDE, CONV_GN_SILU, CONV_EXT_C1, CONV_EXT_C2) = range(21)

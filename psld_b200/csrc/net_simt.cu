@@ -531,10 +531,10 @@ struct FirTaps { float k[16]; };
 template <typename T, int VW, int UP, int DOWN>
 __global__ void __launch_bounds__(256)
 fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C,
-           int OH, int OW, int up_rt, int down_rt, int pad0, int KH) {
+           int Cact, int OH, int OW, int up_rt, int down_rt, int pad0, int KH) {
   pdl_wait();
   const int up = UP ? UP : up_rt, down = DOWN ? DOWN : down_rt;
-  const int vpr = C / VW;
+  const int vpr = Cact / VW;      // only the first Cact channels are filtered (rest: left as is)
   const int64_t total = (int64_t)N * OH * OW * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -615,6 +615,64 @@ fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int 
   }
 }
 
+// upsample_2d (up_or_down_sampling.py:195-224: up = 2, 4x4 taps, pad = (2, 1)) in polyphase form:
+// one thread = one INPUT pixel (8 channels) -> its 2x2 output quad, from the 3x3 input
+// neighbourhood.  Output (2qy+dy, 2qx+dx) sees the zero-stuffed image at uy = 2qy+dy+ky-2, which is
+// an input row only for ky = 2*ry + 2 - dy (ry = iy - qy): 2x2 of the 16 taps per output, 9 loads
+// per 4 outputs instead of 16.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fir_up2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C) {
+  pdl_wait();
+  const int vpr = C / 8;
+  const int64_t total = (int64_t)N * H * W * vpr;
+  const int OW = 2 * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpr);
+    int64_t r = i / vpr;
+    const int qx = (int)(r % W); r /= W;
+    const int qy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
+#pragma unroll
+    for (int ry = -1; ry <= 1; ++ry) {
+      const int iy = qy + ry;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int rx = -1; rx <= 1; ++rx) {
+        const int ix = qx + rx;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * C + cv * 8, v);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int ky = 2 * ry + 2 - dy;
+          if (ky < 0 || ky > 3) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int kx = 2 * rx + 2 - dx;
+            if (kx < 0 || kx > 3) continue;
+            const float w = taps.k[(3 - ky) * 4 + (3 - kx)];     // true convolution: flipped
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[dy * 2 + dx][k] = fmaf(w, v[k], acc[dy * 2 + dx][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        Vec8<T>::store(y + (((int64_t)n * 2 * H + 2 * qy + dy) * OW + 2 * qx + dx) * C + cv * 8,
+                       acc[dy * 2 + dx]);
+  }
+}
+
 int run_fir(const psld_op& op, cudaStream_t s) {
   const int N = op.i[PSLD_FIR_N], H = op.i[PSLD_FIR_H], W = op.i[PSLD_FIR_W], C = op.i[PSLD_FIR_C];
   const int up = op.i[PSLD_FIR_UP], down = op.i[PSLD_FIR_DOWN];
@@ -628,12 +686,22 @@ int run_fir(const psld_op& op, cudaStream_t s) {
   PSLD_CHECK_ARG(OH > 0 && OW > 0, "fir: empty output");
   FirTaps taps;
   for (int i = 0; i < 16; ++i) taps.k[i] = i < KH * KH ? op.f[i] : 0.f;
-  if (C % 4 == 0) {
+  int Cact = op.i[PSLD_FIR_CACT] > 0 ? op.i[PSLD_FIR_CACT] : C;
+  PSLD_CHECK_ARG(Cact <= C && (Cact == C || (C % 8 == 0 && Cact % 8 == 0)), "fir: bad active channel count");
+  if (C % 8 == 0 && Cact == C && up == 2 && down == 1 && KH == 4 && pad0 == 2 && pad1 == 1) {
+    const int grid = (int)ceil_div((int64_t)N * H * W * (C / 8), 256);
+    if (dt == PSLD_BF16)
+      launch_pdl(fir_up2_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1,
+                 (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C);
+    else
+      launch_pdl(fir_up2_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
+                 (float*)op.out[0], taps, N, H, W, C);
+  } else if (C % 4 == 0) {
     const int vw = C % 8 == 0 ? 8 : 4;
-    const int grid = (int)ceil_div((int64_t)N * OH * OW * (C / vw), 256);
+    const int grid = (int)ceil_div((int64_t)N * OH * OW * (Cact / vw), 256);
 #define FIR_LAUNCH2(T, VW, U, D)                                                              \
   launch_pdl(fir_kernel<T, VW, U, D>, dim3(grid), dim3(256), 0, s, 1, (const T*)op.in[0], (T*)op.out[0], taps, N, H, W, C, \
-                                               OH, OW, up, down, pad0, KH)
+                                               Cact, OH, OW, up, down, pad0, KH)
 #define FIR_LAUNCH(T, VW)                                          \
   do {                                                             \
     if (up == 2 && down == 1) FIR_LAUNCH2(T, VW, 2, 1);            \

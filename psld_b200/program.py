@@ -206,17 +206,24 @@ class Plan:
         self._push(op)
         return y
 
-    def op_fir(self, x, taps, up, down, pad0, pad1):
+    def op_fir(self, x, taps, up, down, pad0, pad1, cact=0):
         N, H, W, Cc = x.shape
         KH = taps.shape[0]
         OH = (H * up + pad0 + pad1 - KH) // down + 1
         OW = (W * up + pad0 + pad1 - KH) // down + 1
-        y = self._acquire(N, OH, OW, Cc)
+        if cact and cact < Cc:
+            # only the first `cact` channels carry data (zero-padded network input): the output's
+            # padding channels keep the zeros of a dedicated, never-pooled buffer
+            y = torch.zeros(N, OH, OW, Cc, dtype=self.adt, device=self.dev)
+            self.keep.append(y)
+        else:
+            cact = 0
+            y = self._acquire(N, OH, OW, Cc)
         op = self._op(L.OP_FIR)
         i = op.i
         i[L.FIR_N], i[L.FIR_H], i[L.FIR_W], i[L.FIR_C] = N, H, W, Cc
         i[L.FIR_UP], i[L.FIR_DOWN], i[L.FIR_PAD0], i[L.FIR_PAD1] = up, down, pad0, pad1
-        i[L.FIR_KH], i[L.FIR_DTYPE] = KH, self.acode
+        i[L.FIR_KH], i[L.FIR_DTYPE], i[L.FIR_CACT] = KH, self.acode, cact
         for j, v in enumerate(taps.reshape(-1)):
             op.f[j] = float(v)
         op.inp[0], op.out[0] = x.data_ptr(), y.data_ptr()
@@ -558,12 +565,14 @@ class Plan:
                     pm = mods[i]; i += 1
                     # conv_downsample_2d: upfirdn2d(pad=(2,2)) then conv(stride 2, pad 0) + bias,
                     # merged with h: (pyr + h)/sqrt(2)   (ncsnpp.py:350-357)
-                    padded = self.op_fir(pyr, _fir_taps(net.fir_kernel, 1.0), 1, 1, 2, 2)
+                    cact = 8 if (pyr is x and cpad > net.in_ch and net.in_ch <= 8) else 0
+                    padded = self.op_fir(pyr, _fir_taps(net.fir_kernel, 1.0), 1, 1, 2, 2, cact=cact)
                     scale = _SQRT1_2 if net.skip_rescale else 1.0
                     pyr = self.op_conv(padded, None, pm.Conv2d_0.weight, pm.Conv2d_0.bias, ks=3,
                                        stride=2, pad=0, residual=h, scale=scale,
                                        out=self._new(*h.shape))
-                    self._release(padded)
+                    if not cact:                    # (the zero-padded buffer is never pooled)
+                        self._release(padded)
                     h = pyr
                 hs.append(h)
         h = hs[-1]

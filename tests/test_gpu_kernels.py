@@ -216,6 +216,31 @@ def test_upfirdn2d_golden(golden_dir):
                 assert rel_l2(o.float().permute(0, 3, 1, 2), refd) <= tol, (name, Cc, dt)
 
 
+def test_fir_up2_polyphase_and_channel_subset():
+    """upsample_2d through the polyphase kernel (one thread per input pixel -> 2x2 output quad) on a
+    ragged map, and the active-channel subset used for the zero-padded network input."""
+    k = np.outer([1, 3, 3, 1], [1, 3, 3, 1]).astype(np.float32)
+    k = k / k.sum()
+    r = _rng(21)
+    x = torch.from_numpy(r.standard_normal((3, 5, 7, 16)).astype(np.float32)).to(DEV)
+    for dt, tol in [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)]:
+        op, o = fir_op(x.to(dt), k * 4, 2, 1, 2, 1)
+        run_op(op)
+        ref = O.upfirdn2d(x.to(dt).float().cpu().permute(0, 3, 1, 2), k * 4, up=2, down=1, pad=(2, 1))
+        assert o.shape == (3, 10, 14, 16)
+        assert rel_l2(o.float().permute(0, 3, 1, 2), ref) <= tol, dt
+    # channel subset: only [0, 8) filtered and written, the rest of the output untouched
+    xp = torch.zeros(2, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    xp[..., :6] = torch.from_numpy(r.standard_normal((2, 8, 8, 6)).astype(np.float32)).to(DEV)
+    op, o = fir_op(xp, k, 1, 1, 2, 2)
+    o.zero_()
+    op.i[L.FIR_CACT] = 8
+    run_op(op)
+    ref = O.upfirdn2d(xp.float().cpu().permute(0, 3, 1, 2), k, up=1, down=1, pad=(2, 2))
+    assert rel_l2(o.float().permute(0, 3, 1, 2), ref) <= 6e-3
+    assert float(o[..., 8:].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------ convolution, CUDA-core engine
 CONV_SIMT_CASES = [
     # N, H, W, C1, C2, Cout, ks, stride, pad
