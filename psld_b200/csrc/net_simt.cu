@@ -673,6 +673,63 @@ fir_up2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, 
   }
 }
 
+// downsample_2d (up_or_down_sampling.py:227-257: down = 2, 4x4 taps, pad = (1, 1)): one thread = a
+// 2x2 output quad (8 channels) from the 6x6 input patch it covers: 36 loads per 4 outputs instead
+// of 64.  Output (2qy+dy, 2qx+dx) reads input row 4qy - 1 + r with tap ky = r - 2dy.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fir_down2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W,
+                 int C) {
+  pdl_wait();
+  const int vpr = C / 8;
+  const int OH = H / 2, OW = W / 2, QH = OH / 2, QW = OW / 2;
+  const int64_t total = (int64_t)N * QH * QW * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpr);
+    int64_t q = i / vpr;
+    const int qx = (int)(q % QW); q /= QW;
+    const int qy = (int)(q % QH);
+    const int n = (int)(q / QH);
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const int iy = 4 * qy - 1 + r;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int ix = 4 * qx - 1 + c;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * C + cv * 8, v);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int ky = r - 2 * dy;
+          if (ky < 0 || ky > 3) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int kx = c - 2 * dx;
+            if (kx < 0 || kx > 3) continue;
+            const float w = taps.k[(3 - ky) * 4 + (3 - kx)];     // true convolution: flipped
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[dy * 2 + dx][k] = fmaf(w, v[k], acc[dy * 2 + dx][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        Vec8<T>::store(y + (((int64_t)n * OH + 2 * qy + dy) * OW + 2 * qx + dx) * C + cv * 8,
+                       acc[dy * 2 + dx]);
+  }
+}
+
 int run_fir(const psld_op& op, cudaStream_t s) {
   const int N = op.i[PSLD_FIR_N], H = op.i[PSLD_FIR_H], W = op.i[PSLD_FIR_W], C = op.i[PSLD_FIR_C];
   const int up = op.i[PSLD_FIR_UP], down = op.i[PSLD_FIR_DOWN];
@@ -695,6 +752,15 @@ int run_fir(const psld_op& op, cudaStream_t s) {
                  (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C);
     else
       launch_pdl(fir_up2_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
+                 (float*)op.out[0], taps, N, H, W, C);
+  } else if (C % 8 == 0 && Cact == C && up == 1 && down == 2 && KH == 4 && pad0 == 1 && pad1 == 1 &&
+             H % 4 == 0 && W % 4 == 0) {
+    const int grid = (int)ceil_div((int64_t)N * (H / 4) * (W / 4) * (C / 8), 256);
+    if (dt == PSLD_BF16)
+      launch_pdl(fir_down2_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1,
+                 (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C);
+    else
+      launch_pdl(fir_down2_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
                  (float*)op.out[0], taps, N, H, W, C);
   } else if (C % 4 == 0) {
     const int vw = C % 8 == 0 ? 8 : 4;

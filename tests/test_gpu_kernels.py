@@ -229,6 +229,14 @@ def test_fir_up2_polyphase_and_channel_subset():
         ref = O.upfirdn2d(x.to(dt).float().cpu().permute(0, 3, 1, 2), k * 4, up=2, down=1, pad=(2, 1))
         assert o.shape == (3, 10, 14, 16)
         assert rel_l2(o.float().permute(0, 3, 1, 2), ref) <= tol, dt
+    # downsample_2d through the quad kernel (H, W multiples of 4) and the generic one (ragged)
+    for shape in [(3, 8, 12, 16), (2, 6, 10, 8)]:
+        xd = torch.from_numpy(r.standard_normal(shape).astype(np.float32)).to(DEV)
+        for dt, tol in [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)]:
+            op, o = fir_op(xd.to(dt), k, 1, 2, 1, 1)
+            run_op(op)
+            ref = O.upfirdn2d(xd.to(dt).float().cpu().permute(0, 3, 1, 2), k, up=1, down=2, pad=(1, 1))
+            assert rel_l2(o.float().permute(0, 3, 1, 2), ref) <= tol, (shape, dt)
     # channel subset: only [0, 8) filtered and written, the rest of the output untouched
     xp = torch.zeros(2, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
     xp[..., :6] = torch.from_numpy(r.standard_normal((2, 8, 8, 6)).astype(np.float32)).to(DEV)
