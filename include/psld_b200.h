@@ -215,9 +215,11 @@ typedef struct {
 } psld_op;
 
 /* --- PSLD_OP_LAYOUT: in[0] -> out[0].  i: N, C, HW, dir (0: NCHW f32 -> NHWC T, 1: NHWC T
- *     -> NCHW f32), dtype (T), CPAD (dir 0 only: NHWC channel count >= C, zero padded; 0 = C) */
+ *     -> NCHW f32), dtype (T), CPAD (dir 0 only: NHWC channel count >= C, zero padded; 0 = C),
+ *     CWRITE (dir 0 only: channels [0, CWRITE) are written, C <= CWRITE <= CPAD; 0 = CPAD: the
+ *     caller zeroed the remaining padding channels once)                                   */
 enum { PSLD_LAYOUT_N = 0, PSLD_LAYOUT_C, PSLD_LAYOUT_HW, PSLD_LAYOUT_DIR, PSLD_LAYOUT_DTYPE,
-       PSLD_LAYOUT_CPAD };
+       PSLD_LAYOUT_CPAD, PSLD_LAYOUT_CWRITE };
 
 /* --- PSLD_OP_TEMB (ncsnpp.py:292-311, layerspp.py:32-41,262-263, layers.py:500-514):
  *   in[0] = time [nt] f32 (forward time tau, or log(tau) when i[LOGGED]=1)

@@ -23,7 +23,7 @@ ENGINE_SIMT, ENGINE_TC, ENGINE_TC_GN = 0, 1, 2
 OP_NI, OP_NF, OP_NP = 28, 24, 10
 
 # slot indices
-(LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE, LAYOUT_CPAD) = range(6)
+(LAYOUT_N, LAYOUT_C, LAYOUT_HW, LAYOUT_DIR, LAYOUT_DTYPE, LAYOUT_CPAD, LAYOUT_CWRITE) = range(7)
 (TEMB_NT, TEMB_NF, TEMB_EMB, TEMB_TOTALC, TEMB_LOGGED) = range(5)
 (GN_N, GN_HW, GN_C1, GN_C2, GN_G, GN_SILU, GN_IN_DTYPE, GN_OUT_DTYPE, GN_NCHUNK,
  GN_AFFINE_ONLY) = range(10)

@@ -21,16 +21,18 @@ namespace psld {
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int HW,
-                    int CP) {
+                    int CP, int CW) {
   pdl_wait();
-  const int64_t total = (int64_t)N * CP * HW;
+  // only channels [0, CW) of the CP-wide rows are written (CW < CP: the rest keeps the zeros the
+  // buffer was allocated with)
+  const int64_t total = (int64_t)N * CW * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CP);
-    const int64_t r = i / CP;
+    const int c = (int)(i % CW);
+    const int64_t r = i / CW;
     const int p = (int)(r % HW);
     const int n = (int)(r / HW);
-    out[i] = c < C ? from_f32<T>(in[((int64_t)n * C + c) * HW + p]) : from_f32<T>(0.f);
+    out[r * CP + c] = c < C ? from_f32<T>(in[((int64_t)n * C + c) * HW + p]) : from_f32<T>(0.f);
   }
 }
 
@@ -62,14 +64,17 @@ int run_layout(const psld_op& op, cudaStream_t s) {
   int CP = op.i[PSLD_LAYOUT_CPAD];
   if (CP <= 0) CP = C;
   PSLD_CHECK_ARG(CP >= C && (dir == 0 || CP == C), "layout: bad channel padding");
-  const int grid = ew_grid((int64_t)N * CP * HW);
+  int CW = op.i[PSLD_LAYOUT_CWRITE];
+  if (CW <= 0) CW = CP;
+  PSLD_CHECK_ARG(CW >= C && CW <= CP, "layout: bad written-channel count");
+  const int grid = ew_grid((int64_t)N * (dir == 0 ? CW : CP) * HW);
   if (dir == 0) {
     if (dt == PSLD_BF16)
       launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
-                                                            (__nv_bfloat16*)op.out[0], N, C, HW, CP);
+                                                            (__nv_bfloat16*)op.out[0], N, C, HW, CP, CW);
     else
       launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0],
-                                                    N, C, HW, CP);
+                                                    N, C, HW, CP, CW);
   } else {
     if (dt == PSLD_BF16)
       launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const __nv_bfloat16*)op.in[0],

@@ -153,10 +153,11 @@ class Plan:
         return len(self.ops) - 1
 
     # ---------------------------------------------------------------- op builders
-    def op_layout(self, src, dst, N, Cc, HW, direction, cpad=0):
+    def op_layout(self, src, dst, N, Cc, HW, direction, cpad=0, cwrite=0):
         op = self._op(L.OP_LAYOUT)
         op.i[L.LAYOUT_N], op.i[L.LAYOUT_C], op.i[L.LAYOUT_HW] = N, Cc, HW
         op.i[L.LAYOUT_DIR], op.i[L.LAYOUT_DTYPE], op.i[L.LAYOUT_CPAD] = direction, self.acode, cpad
+        op.i[L.LAYOUT_CWRITE] = cwrite
         op.inp[0], op.out[0] = src.data_ptr(), dst.data_ptr()
         self._push(op)
 
@@ -546,8 +547,13 @@ class Plan:
         # bf16 plans zero-pad the 6 input channels to 64 so that the input conv and the first
         # pyramid conv are tensor-core eligible (K chunks are 64 channels)
         cpad = 64 if (self.bf16 and net.in_ch < 64) else net.in_ch
-        x = self._new(B, H, H, cpad)
-        self.op_layout(self.x_in, x, B, net.in_ch, H * H, 0, cpad)
+        if cpad > net.in_ch:     # padding channels: zeroed once here, never written again
+            x = torch.zeros(B, H, H, cpad, dtype=self.adt, device=self.dev)
+            self.keep.append(x)
+            cwrite = min(cpad, -(-net.in_ch // 8) * 8)
+        else:
+            x, cwrite = self._new(B, H, H, cpad), 0
+        self.op_layout(self.x_in, x, B, net.in_ch, H * H, 0, cpad, cwrite)
         pyr = x if net.progressive_input != "none" else None
         hs = [self.op_conv(x, None, mods[i].weight, mods[i].bias, ks=3,
                            out=self._new(B, H, H, net.nf))]; i += 1
