@@ -350,7 +350,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
-      tc_epilogue_tile<false, 32>(
+      tc_epilogue_tile<true, 32, false>(
           p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
           stg_base + (uint32_t)(warp - 4) * 2048u, addv_base + (uint32_t)(warp - 4) * 256u,
           [&]() {

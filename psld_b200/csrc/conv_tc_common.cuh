@@ -171,9 +171,9 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 // `release()` right after this warp's LAST TMEM read (it hands the accumulator back to the MMA
 // warp before the global stores are issued, so the release never waits on them).
 // kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
-// processed and the second TMEM chunk in flight while the first is processed (64 registers; off
-// for kernels that are short of registers).
-template <bool kPrefetchRes = true, int GC = 64, class Acquire, class Release>
+// processed (GC/2 registers); kTmemAhead (GC = 64): second TMEM chunk in flight while the first is
+// processed (32 registers).  Both off for kernels that are short of registers.
+template <bool kPrefetchRes = true, int GC = 64, bool kTmemAhead = true, class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
                                                  int lane, uint32_t stg, uint32_t addv,
@@ -340,7 +340,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
           tmem_ld_wait();
           if (!more) release();
           process(r, 0, co_base);
-        } else if (kPrefetchRes) {
+        } else if (kTmemAhead) {
           uint32_t r0[32], r1[32];
           tmem_ld32(taddr, r0);
           tmem_ld_wait();

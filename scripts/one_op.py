@@ -25,6 +25,8 @@ SHAPES = {   # name: (HW, C1, C2, Cout, ks, residual, temb, stats, gn)
     "g32": (32, 256, 0, 256, 3, False, True, True, True),
     "g32cat": (32, 256, 256, 256, 3, False, True, True, True),
     "g16": (16, 256, 0, 256, 3, False, True, True, True),
+    "g32res": (32, 256, 0, 256, 3, True, False, True, True),
+    "g16res": (16, 256, 0, 256, 3, True, False, True, True),
 }
 
 
