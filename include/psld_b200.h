@@ -283,8 +283,12 @@ enum { PSLD_CONV_N = 0, PSLD_CONV_H, PSLD_CONV_W, PSLD_CONV_C1, PSLD_CONV_C2, PS
 
 /* --- PSLD_OP_ATTN (AttnBlockpp core, layerspp.py:82-86): single head over HW tokens.
  *   in[0] = qkv [N, HW, 3C] (q | k | v along the last axis) ; out[0] = o [N, HW, C]
- *   i: N, HW, C, DTYPE ; f[0] = softmax scale (C^-0.5)                                  */
-enum { PSLD_ATTN_N = 0, PSLD_ATTN_HW, PSLD_ATTN_C, PSLD_ATTN_DTYPE };
+ *   i: N, HW, C, DTYPE, PROJ ; f[0] = softmax scale (C^-0.5)
+ *   PROJ = 1 (PSLD_ENGINE_TC, HW % 128 == 0): the block's output projection and skip connection are
+ *   fused (layerspp.py:87-91): out[0] = (NIN_3(o) + x) * f[1] with in[1] = NIN_3 weight bf16
+ *   [C out, C in], in[2] = bias f32 [C] or NULL, in[3] = x [N, HW, C]; out[1] = optional GroupNorm
+ *   statistics accumulator of out[0] (as for PSLD_OP_CONV)                                 */
+enum { PSLD_ATTN_N = 0, PSLD_ATTN_HW, PSLD_ATTN_C, PSLD_ATTN_DTYPE, PSLD_ATTN_PROJ };
 
 /* Validate an op and build its per-op host state (TMA descriptors for PSLD_ENGINE_TC).
  * Returns PSLD_EUNSUPPORTED when the shape is not eligible for op->engine. */

@@ -32,7 +32,7 @@ OP_NI, OP_NF, OP_NP = 28, 24, 10
 (CONV_N, CONV_H, CONV_W, CONV_C1, CONV_C2, CONV_COUT, CONV_KS, CONV_STRIDE, CONV_PAD, CONV_OH,
  CONV_OW, CONV_IN_LAYOUT, CONV_OUT_LAYOUT, CONV_IN_DTYPE, CONV_OUT_DTYPE, CONV_RES_DTYPE,
  CONV_TEMB_OFF, CONV_TEMB_BSTRIDE, CONV_GN_SILU, CONV_EXT_C1, CONV_EXT_C2) = range(21)
-(ATTN_N, ATTN_HW, ATTN_C, ATTN_DTYPE) = range(4)
+(ATTN_N, ATTN_HW, ATTN_C, ATTN_DTYPE, ATTN_PROJ) = range(5)
 
 
 class HalfStep(C.Structure):

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "conv_tc_common.cuh"
 
 namespace psld {
 
@@ -27,6 +28,8 @@ constexpr int AT_SLOT_BYTES = 16384 + 32768;   // Q chunk [128 x 64] + K chunk /
 constexpr int AT_SLOTS = 3;
 constexpr int AT_P_BYTES = 128 * 256 * 2;      // P as 4 K-major tiles of [128 x 64] bf16
 constexpr int AT_SMEM_BYTES = AT_SLOTS * AT_SLOT_BYTES + AT_P_BYTES + 1024 + 256;
+// fused output projection: + 4 KB staging and 256 B additive vector per softmax/epilogue warp
+constexpr int AT_SMEM_BYTES_PROJ = AT_SMEM_BYTES + 4 * 4096 + 4 * 256;
 constexpr int AT_THREADS = 192;
 
 struct AttnTcParams {
@@ -34,17 +37,26 @@ struct AttnTcParams {
   int HW, C, N;
   int q_rows;        // rows of the Q box: min(128, HW)
   float scale_log2;  // C^-0.5 * log2(e)
+  ConvTcParams ep;   // kProj: epilogue of the fused NIN_3 projection (bias, residual, scale, stats)
 };
 
 struct AttnTcState {
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tw;
+  bool proj;
   AttnTcParams p;
   dim3 grid;
 };
 
+// kProj: the block's output projection rides along (AttnBlockpp, layerspp.py:87-91):
+//   h = (NIN_3(O / rowsum) + x) * scale.  The normalised O goes to shared memory as bf16 in the
+//   P buffer (K-major over channels), W3 streams through the ring as 64-channel chunks, the
+//   product accumulates in the TMEM columns S occupied, and the conv epilogue (bias, residual,
+//   scale, bf16 store, GroupNorm statistics) finishes the tile: no O round trip through HBM and
+//   no separate 1x1 convolution launch.
+template <bool kProj>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-               const AttnTcParams p) {
+               const __grid_constant__ CUtensorMap tmW, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t p_base = base + AT_SLOTS * AT_SLOT_BYTES;
@@ -54,7 +66,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t s_full = bar_base + 8u * (2 * AT_SLOTS);
   const uint32_t p_ready = s_full + 8u;
   const uint32_t o_full = s_full + 16u;
-  const uint32_t tmem_slot = s_full + 24u;
+  const uint32_t o_ready = s_full + 24u;
+  const uint32_t y_full = s_full + 32u;
+  const uint32_t tmem_slot = s_full + 40u;
+  const uint32_t stg_base = bar_base + 256u;             // kProj only
+  const uint32_t addv_base = stg_base + 4u * 4096u;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -72,6 +88,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
+    mbar_init(o_ready, 128);
+    mbar_init(y_full, 1);
+    if (kProj) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -107,6 +126,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sv = base + slot * AT_SLOT_BYTES + 16384;
         tma_load_3d(sv, &tmKV, full_bar(slot), 2 * p.C + g * 64, 0, n);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+      if (kProj) {       // W3 [C out rows x 64 input channels] per chunk
+        for (int c = 0; c < nck; ++c) {
+          mbar_wait(empty_bar(slot), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.C * 128u);
+          tma_load_2d(base + slot * AT_SLOT_BYTES + 16384, &tmW, full_bar(slot), c * 64, 0);
+          if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -149,6 +176,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       }
       tc_commit(o_full);
+      if (kProj) {
+        // Y[128 x C] = Onorm W3^T : A = Onorm (bf16, K-major over channels, in the P buffer),
+        // B = W3 chunk (K-major), accumulator in the columns S used
+        const uint32_t idesc_y = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.C >> 3) << 17) |
+                                 ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(o_ready, 0);
+        tc_fence_after();
+        for (int c = 0; c < nck; ++c) {
+          mbar_wait(full_bar(slot), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)c * 16384u);
+          const uint64_t bdesc = make_sw128_desc(base + slot * AT_SLOT_BYTES + 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_y,
+                        (c > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(slot));
+          if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+        }
+        tc_commit(y_full);
+      }
     }
   } else {
     // ===== softmax + epilogue: 128 threads, one query row each =====
@@ -201,6 +249,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const int q = q0 + row;
     const bool valid = q < p.HW;
+    if (kProj) {
+      // normalised O -> bf16 in the P buffer, same swizzled K-major tiles as P (tile = ch / 64)
+      for (int ch = 0; ch < p.C; ch += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_O + lane_addr + (uint32_t)ch, r);
+        tmem_ld_wait();
+        const uint32_t tile = p_base + (uint32_t)(ch >> 6) * 16384u + (uint32_t)row * 128u;
+        const int cbase = (ch & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * t]) * inv,
+                                                     __uint_as_float(r[j * 8 + 2 * t + 1]) * inv);
+            w[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          sts128(tile + (uint32_t)(((cbase + j) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(o_ready);
+      mbar_wait(y_full, 0);
+      tc_fence_after();
+      const int m_tile = n * (p.HW >> 7) + (int)blockIdx.x;
+      const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half)
+        tc_epilogue_tile<true, 64, true>(p.ep, tmem_S, 0, m_tile, 0, quarter, half, lane,
+                                         stg_base + (uint32_t)ew * 4096u,
+                                         addv_base + (uint32_t)ew * 256u, []() {}, []() {});
+    } else {
     __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * p.C;
     for (int ch = 0; ch < p.C; ch += 32) {
       uint32_t r[32];
@@ -220,6 +301,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       __syncwarp();
+    }
     }
   }
 
@@ -267,10 +349,43 @@ int prepare_attn_tc(psld_op& op) {
   st->p.HW = HW; st->p.C = C; st->p.N = N; st->p.q_rows = q_rows;
   st->p.scale_log2 = op.f[0] * 1.4426950408889634f;
   st->grid = dim3((unsigned)((HW + 127) / 128), (unsigned)N);
+  // optional fused output projection (in[1] = W3 bf16 [C out, C in], in[2] = bias, in[3] = residual)
+  st->proj = op.i[PSLD_ATTN_PROJ] != 0;
+  if (st->proj) {
+    if (HW % 128 || !op.in[1] || !op.in[3]) { delete st; return unsupported("fused projection needs HW %% 128 == 0, weight and residual"); }
+    EncodeTiledFn enc = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)C};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)C};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc ? enc(&st->tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.in[1]), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                     : CUDA_ERROR_UNKNOWN;
+    if (r != CUDA_SUCCESS) { delete st; set_error("cuTensorMapEncodeTiled(proj weight) failed: %d", (int)r); return PSLD_ECUDA; }
+    ConvTcParams& e = st->p.ep;
+    e = ConvTcParams{};
+    e.bias = (const float*)op.in[2];
+    e.temb = nullptr;
+    e.res = (const __nv_bfloat16*)op.in[3];
+    e.y = (__nv_bfloat16*)op.out[0];
+    e.y_nchw = nullptr;
+    e.mg_stats = (double*)op.out[1];
+    e.cout_valid = C;
+    e.scale = op.f[1];
+    e.HW = HW; e.Cout = C; e.H = 0; e.W = 0;
+    e.block_n = C; e.n_tiles_n = 1;
+    e.M = (int64_t)N * HW;
+  } else {
+    st->tw = st->tq;       // unused
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AT_SMEM_BYTES_PROJ);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -293,8 +408,12 @@ int release_attn_tc(psld_op& op) {
 int run_attn_tc(const psld_op& op, cudaStream_t s) {
   const AttnTcState* st = (const AttnTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
-  PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES, s, 1, st->tq,
-                             st->tkv, st->p));
+  if (st->proj)
+    PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES_PROJ, s, 1,
+                               st->tq, st->tkv, st->tw, st->p));
+  else
+    PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES, s, 1,
+                               st->tq, st->tkv, st->tw, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

@@ -375,12 +375,30 @@ class Plan:
               and pow2(i[L.CONV_OW]) and pow2(i[L.CONV_OH]) and 4 <= i[L.CONV_OW] <= 128)
         return L.OK if ok else L.EUNSUPPORTED
 
-    def op_attn(self, qkv, HW, Cc):
-        o = self._acquire(*qkv.shape[:-1], Cc)
+    def op_attn(self, qkv, HW, Cc, proj=None):
+        """proj = (W3 [out, in], bias, x, scale, out): the output projection + skip connection are
+        fused into the tensor-core attention kernel; returns None if that is not possible."""
         op = self._op(L.OP_ATTN)
         op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = self.B, HW, Cc, self.acode
         op.f[0] = float(int(Cc) ** (-0.5))
-        op.inp[0], op.out[0] = qkv.data_ptr(), o.data_ptr()
+        op.inp[0] = qkv.data_ptr()
+        fusable = Cc % 64 == 0 and 64 <= Cc <= 256 and HW in (128, 256)
+        if proj is not None:
+            if not (self.bf16 and fusable) or os.environ.get("PSLD_ATTN_FUSE_PROJ", "1") == "0":
+                return None
+            w3, b3, x, scale, o = proj
+            op.i[L.ATTN_PROJ] = 1
+            op.f[1] = float(scale)
+            op.inp[1] = self._w(w3, torch.bfloat16).data_ptr()
+            op.inp[2] = self._w(b3).data_ptr() if b3 is not None else None
+            op.inp[3] = x.data_ptr()
+            mg = None
+            if self.fused_stats and Cc % 32 == 0:
+                mg = self._mg_buffer(self.B, Cc)
+                op.out[1] = mg.data_ptr()
+        else:
+            o = self._acquire(*qkv.shape[:-1], Cc)
+        op.out[0] = o.data_ptr()
         if self.bf16:
             op.engine = L.ENGINE_TC
             if self.dry:
@@ -388,11 +406,18 @@ class Plan:
             else:
                 rc = self.lib.psld_op_prepare(C.byref(op))
             if rc == L.EUNSUPPORTED:
+                if proj is not None:
+                    raise RuntimeError("psld_b200: fused attention projection rejected: " +
+                                       self.lib.psld_last_error().decode(errors="replace"))
                 op.engine = L.ENGINE_SIMT
             elif rc != L.OK:
                 L.check(rc, "psld_op_prepare(attn)")
-        self.engine_count["attn_tc" if op.engine == L.ENGINE_TC else "attn_simt"] = \
-            self.engine_count.get("attn_tc" if op.engine == L.ENGINE_TC else "attn_simt", 0) + 1
+        if proj is not None and op.out[1]:
+            self.mg[o.data_ptr()] = mg
+        key = ("attn_tc_proj" if proj is not None else "attn_tc") if op.engine == L.ENGINE_TC else "attn_simt"
+        self.engine_count[key] = self.engine_count.get(key, 0) + 1
+        if proj is not None:
+            self.engine_count["attn_tc"] = self.engine_count.get("attn_tc", 0) + 1
         self._push(op)
         return o
 
@@ -492,9 +517,15 @@ class Plan:
         bqkv = torch.cat([m.NIN_0.b, m.NIN_1.b, m.NIN_2.b], dim=0)
         qkv = self.op_conv(a, None, wqkv.t().reshape(3 * Cc, Cc, 1, 1), bqkv, ks=1, want_stats=False)
         self._release(a)
+        scale = _SQRT1_2 if self.net.skip_rescale else 1.0
+        # h = (NIN_3(attention) + x) * scale inside the attention kernel where it is eligible
+        out = self.op_attn(qkv, H * W, Cc, proj=(m.NIN_3.W.t().contiguous(), m.NIN_3.b, x, scale,
+                                                 self._new(N, H, W, Cc)))
+        if out is not None:
+            self._release(qkv)
+            return out
         o = self.op_attn(qkv, H * W, Cc)
         self._release(qkv)
-        scale = _SQRT1_2 if self.net.skip_rescale else 1.0
         out = self.op_conv(o, None, m.NIN_3.W.t().reshape(Cc, Cc, 1, 1), m.NIN_3.b, ks=1,
                            residual=x, scale=scale, out=self._new(N, H, W, Cc))
         self._release(o)

@@ -165,7 +165,9 @@ def fir_op(x, taps, up, down, pad0, pad1):
     return op, out
 
 
-def attn_op(qkv, Cc, engine=L.ENGINE_SIMT):
+def attn_op(qkv, Cc, engine=L.ENGINE_SIMT, proj=None):
+    """proj = (w3 [out, in] f32, bias f32, x NHWC, scale): fused output projection + skip.
+    Returns (op, out) or (op, out, keep) when proj is given (keep[-1] = statistics accumulator)."""
     N = qkv.shape[0]
     HW = int(np.prod(qkv.shape[1:-1]))
     out = torch.full((*qkv.shape[:-1], Cc), float("nan"), dtype=qkv.dtype, device=qkv.device)
@@ -174,7 +176,17 @@ def attn_op(qkv, Cc, engine=L.ENGINE_SIMT):
     op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = N, HW, Cc, code(qkv)
     op.f[0] = float(int(Cc) ** (-0.5))
     op.inp[0], op.out[0] = qkv.data_ptr(), out.data_ptr()
-    return op, out
+    if proj is None:
+        return op, out
+    w3, b3, x, scale = proj
+    wp = w3.to(qkv.device, torch.bfloat16).contiguous()
+    bp = b3.to(qkv.device, torch.float32).contiguous()
+    mg = torch.zeros((N, Cc // 4, 2), dtype=torch.float64, device=qkv.device)
+    op.i[L.ATTN_PROJ] = 1
+    op.f[1] = scale
+    op.inp[1], op.inp[2], op.inp[3] = wp.data_ptr(), bp.data_ptr(), x.data_ptr()
+    op.out[1] = mg.data_ptr()
+    return op, out, [wp, bp, x, mg]
 
 
 def rel_l2(a, b):

@@ -156,6 +156,14 @@ def run_plan(plan, x, t):
             w = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * f[0], dim=-1)
             o = torch.einsum("bqk,bkc->bqc", w, v)
             out = g(op.out[0])
+            if i[L.ATTN_PROJ]:      # fused NIN_3 + skip connection (+ statistics of the result)
+                assert op.engine == L.ENGINE_TC and i[L.ATTN_HW] % 128 == 0
+                y = F.linear(o.to(torch.bfloat16).float(), _f(g(op.inp[1])), g(op.inp[2]))
+                y = (y + _f(g(op.inp[3])).reshape(y.shape)) * f[1]
+                if op.out[1]:
+                    v4 = y.double().reshape(B, -1, Cc // 4, 4)
+                    g(op.out[1]).add_(torch.stack([v4.sum((1, 3)), (v4 * v4).sum((1, 3))], -1))
+                o = y
             out.copy_(o.reshape(out.shape))
         else:
             raise AssertionError(f"unknown op kind {op.kind}")

@@ -503,6 +503,28 @@ def test_attention_tc(shape):
     assert err <= 8e-3, err          # P and the output are rounded to bf16
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 16, 8, 128), (5, 16, 16, 64), (1, 16, 16, 192)])
+def test_attention_tc_fused_projection(shape):
+    """Attention core + NIN_3 output projection + skip connection + GroupNorm statistics in one
+    kernel (AttnBlockpp, layerspp.py:82-91) vs the fp32 definition."""
+    N, H, W, Cc = shape
+    r = _rng(23)
+    qkv = _t(r.standard_normal((N, H, W, 3 * Cc)) * 1.5, torch.bfloat16)
+    x = _t(r.standard_normal((N, H, W, Cc)), torch.bfloat16)
+    w3 = _t(r.standard_normal((Cc, Cc)) / np.sqrt(Cc))           # [out, in]
+    b3 = _t(0.1 * r.standard_normal(Cc))
+    op, out, keep = attn_op(qkv, Cc, engine=L.ENGINE_TC, proj=(w3, b3, x, 0.7071))
+    run_op(op, prepare=True)
+    q, k, v = qkv.float().cpu().reshape(N, H * W, 3 * Cc).split(Cc, dim=-1)
+    wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
+    o = torch.einsum("bqk,bkc->bqc", wgt, v)
+    ref = (o @ w3.to(torch.bfloat16).float().cpu().t() + b3.cpu() + x.float().cpu().reshape(N, H * W, Cc)) * 0.7071
+    err = rel_l2(out.float().reshape(N, H * W, Cc), ref)
+    assert err <= 8e-3, err
+    mref = mg_ref(ref.reshape(N, H, W, Cc))
+    assert float((keep[-1].cpu() - mref).abs().max()) <= 1e-2 * float(mref.abs().max())
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_error_codes():
     lib = L.lib()
