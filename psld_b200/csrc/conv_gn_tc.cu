@@ -4,17 +4,21 @@
 //
 //   y = scale * ( conv3x3( silu( x * sc[n,c] + sh[n,c] ) ) + bias + temb + residual )
 //
-// with (sc, sh) the per-(sample, channel) affine form of GroupNorm (gn_affine_kernel) — i.e.
+// with (sc, sh) the per-(sample, channel) affine form of GroupNorm (gn_affine_micro_kernel) — i.e.
 // ResnetBlockBigGANpp's  act(GroupNorm_k(.)) -> Conv_k  pairs (reference layerspp.py:243,259,266).
 //
 // How the normalisation is applied once per element although a 3x3 conv reads every pixel 9 times:
 // per (tile, 64-channel chunk) the RAW tile plus its vertical halo ((BH+2) x W pixels, out-of-image
-// rows zero-filled by TMA) is loaded ONCE; four "transform" warps normalise it in shared memory and
+// rows zero-filled by TMA) is loaded ONCE; eight "transform" warps normalise it in shared memory and
 // write three operand tiles: centre, shifted left and shifted right by one pixel (image-edge
 // columns zeroed = the conv's horizontal padding).  The 9 taps are then plain descriptor offsets:
 // kx selects the variant, ky adds ky*W rows (a multiple of the 1024-byte swizzle atom for
 // W = 16, 32), so no tap needs its own load.  L2->SM traffic for A drops from 9 x 16 KB to 24 KB
-// per chunk; weights stream per tap through a 3-stage ring (half tile per CTA, as in conv_tc).
+// per chunk; weights stream per tap through a 4-stage ring (half tile per CTA, as in conv_tc).
+// The three centre-column taps are issued first: the centre slot (where the raw tile lands) is
+// released after a third of a chunk's MMAs, so the next-but-one raw tile is in flight early.
+// An optional 1x1 "extension" over a second, un-normalised input (the block's Conv_2 shortcut)
+// adds one-tap chunks that bypass the transform (off by default in the plan: slower than conv_tc).
 //
 // Warps (640 threads): 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator,
 // 2 = weight TMA, 3 idle, 4..11 = epilogue (shared with conv_tc), 12..19 = transform.

@@ -20,12 +20,19 @@
 //   * B operand: weights pre-packed [Cout, K] bf16 (K-major), 2-D TMA box {64, BLOCK_N}.
 //   * torch.cat([h, skip]) inputs (ncsnpp.py:374) are never materialised: the K loop walks two
 //     tensor maps.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
-//     allocator, warps 2-9 = epilogue (tcgen05.ld -> bias/temb/residual/scale -> bf16 -> global;
-//     two warps per TMEM lane quarter, each taking every other 32-column chunk, with the residual
-//     of the next chunk prefetched while the current one is processed).
-//   * 4-stage smem ring (A 16 KB + B 32 KB per stage), mbarrier full/empty pairs,
-//     tcgen05.commit releases stages and publishes accumulators.
+//   * Warp roles: warp 0 = A (activation) TMA producer, warp 10 = B (weight) TMA producer, warp 1 =
+//     MMA issuer + TMEM allocator (all three run their loops converged, one elected lane issues),
+//     warps 2-9 = epilogue (conv_tc_common.cuh: tcgen05.ld -> FFMA2 against a warp-uniform
+//     (bias + temb) * scale vector -> + residual -> bf16 through a swizzled smem tile -> full-line
+//     stores + GroupNorm statistics; two warps per TMEM lane quarter, each taking every other
+//     64-column group, with the residual of the next group prefetched).
+//   * smem ring of (A 16 KB + B 32 KB) stages, 4 deep (1-CTA) or (A 16 KB + half B 16 KB) 6 deep
+//     (2-CTA cta_group::2, the default: one M = 256 MMA stream per CTA pair), mbarrier full/empty
+//     pairs, tcgen05.commit releases stages and publishes accumulators.
+//   * Optional K-extension: a 1x1 convolution over a second input (the residual block's Conv_2
+//     shortcut) accumulated into the same tile through two more tensor maps.
+//   * Programmatic dependent launch: dependents are released at entry, the A producer and the
+//     epilogue warps execute griddepcontrol.wait before touching activations.
 
 #include <cuda.h>
 
