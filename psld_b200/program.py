@@ -12,7 +12,12 @@ Fusions relative to the reference's eager graph:
     convolution epilogue;
   * q, k, v NIN projections are one GEMM with a [C, 3C] weight;
   * the 2-layer temb MLP and all per-block ``Dense_0`` projections are computed once per call
-    (and for ONE time row when the whole batch shares t, as it does during sampling).
+    (and for ONE time row when the whole batch shares t, as it does during sampling);
+  * (bf16 plans) GroupNorm statistics are accumulated by the producing convolution's epilogue and
+    ``act(GroupNorm(.))`` is applied on load inside the consuming 3x3 convolution where the shape
+    allows (GroupNorm_0 -> Conv_0, and GroupNorm_1 -> Conv_1 of identity-shortcut blocks);
+  * (bf16 plans) the 1x1 ``Conv_2`` shortcut is appended to ``Conv_1`` as extra K-blocks, and the
+    attention block's output projection + skip connection run inside the attention kernel.
 """
 from __future__ import annotations
 
@@ -59,7 +64,7 @@ class Plan:
         self.stat_used = []
         self.fused_stats = True
         self.fuse_gn = True
-        self.fuse_gn_residual = False   # also fuse GroupNorm_1 into Conv_1 (residual epilogue)
+        self.fuse_gn_residual = False   # force GroupNorm_1 -> Conv_1 fusion (default: PSLD_TC_FUSE_GN1)
         self.fuse_shortcut = True       # Conv_2 (1x1 shortcut) as extra K-blocks of Conv_1
         self.temb_op = -1
         self._build()
