@@ -144,3 +144,42 @@ def test_checkpoint_loader(tmp_path):
     assert torch.equal(a.state_dict()[k0], ema[k0]) and torch.equal(b.state_dict()[k0], sd[k0])
     with pytest.raises(KeyError):
         select_score_fn_state({"foo.x": torch.zeros(1)}, "target")
+
+
+def test_inpaint_and_vp_tables_vs_oracle():
+    """Host coefficient tables of the two widened samplers against the oracle's scalar algebra
+    (which is pinned on the reference's outputs in test_oracle_vs_golden.py)."""
+    from _net import vp_config
+    from psld_b200.schedule import InpaintTables, VPSchedule, VPStepTables
+    # inpainting: call 0 = T, calls 1..n = T - ts[i], call n+1 = T - fl32(T - eps), mean only
+    for mode in ("hsm", "dsm"):
+        cfg = tiny_config(sampler="ip_em_sde", n_discrete_steps=12)
+        cfg.training.mode = mode
+        sch, s = PSLDSchedule(cfg), O.PSLDScalars(cfg)
+        ts, n = time_grid(cfg)
+        tab = InpaintTables(sch, ts, n, True, cfg.evaluation.eval_eps, mode == "hsm")
+        taus = [1.0] + [1.0 - float(t) for t in ts[:n]] + \
+               [float(np.float32(1.0) - np.float32(1.0 - cfg.evaluation.eval_eps))]
+        assert len(tab.steps) == n + 2
+        for k, tau in enumerate(taus):
+            st = tab.steps[k]
+            np.testing.assert_allclose([st.a_xx, st.a_xm, st.a_mx, st.a_mm], O.mean_coeffs(s, tau), rtol=1e-13)
+            cov = s.cov(0.0, s.mm_0 if mode == "hsm" else 0.0, tau)
+            np.testing.assert_allclose([st.c11, st.c12, st.c21, st.c22], s.get_coeff(cov), rtol=1e-10,
+                                       atol=1e-16)
+            assert st.m0_std == (0.0 if mode == "hsm" else s.mm_0 ** 0.5)
+            assert st.mean_only == int(k == n + 1)
+    # VP-SDE Euler-Maruyama rows
+    cfg = vp_config(n_discrete_steps=9, stride_type="quadratic")
+    v, sch = O.VPScalars(cfg), VPSchedule(cfg)
+    ts, n = time_grid(cfg)
+    tab = VPStepTables(sch, ts, n, True, cfg.evaluation.eval_eps)
+    for i in range(n):
+        tau, dt = 1.0 - float(ts[i]), float(ts[i + 1] - ts[i])
+        st = tab.steps[i]
+        beta = v.beta_t(tau)
+        np.testing.assert_allclose([st.half_beta, st.g2, st.neg_inv_std, st.dt, st.gs],
+                                   [0.5 * beta, beta, -1.0 / v.std(tau), dt, (beta * dt) ** 0.5], rtol=1e-12)
+    den = tab.steps[n]
+    assert den.gs == 0.0 and den.dt == float(np.float32(cfg.evaluation.eval_eps))
+    assert tab.tau32.numel() == n + 1
