@@ -420,10 +420,13 @@ int prepare_conv_gn_tc(psld_op& op) {
   };
   static const int env = [] { const char* e = getenv("PSLD_TC_FUSE_GN"); return e ? atoi(e) : 1; }();
   if (!env) return unsupported("disabled by PSLD_TC_FUSE_GN=0");
-  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16 || op.i[PSLD_CONV_OUT_DTYPE] != PSLD_BF16)
+  // network head (ncsnpp.py:430): fp32 NCHW output, first f[1] channels of a zero-padded Cout
+  const bool head = op.i[PSLD_CONV_OUT_LAYOUT] == PSLD_NCHW && op.i[PSLD_CONV_OUT_DTYPE] == PSLD_F32;
+  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16 || (!head && op.i[PSLD_CONV_OUT_DTYPE] != PSLD_BF16))
     return unsupported("bf16 in/out only");
-  if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC || op.i[PSLD_CONV_OUT_LAYOUT] != PSLD_NHWC)
+  if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC || (!head && op.i[PSLD_CONV_OUT_LAYOUT] != PSLD_NHWC))
     return unsupported("NHWC only");
+  if (head && (op.out[1] || op.in[2])) return unsupported("head: no statistics / residual");
   if (KS != 3 || op.i[PSLD_CONV_STRIDE] != 1 || op.i[PSLD_CONV_PAD] != 1) return unsupported("3x3 s1 p1 only");
   if (C1 % TC_BLOCK_K || C2 % TC_BLOCK_K) return unsupported("Cin %% 64 != 0");
   if (Cout % 64 || Cout > 256 && Cout % 256) return unsupported("Cout");
@@ -474,9 +477,9 @@ int prepare_conv_gn_tc(psld_op& op) {
   p.bias = (const float*)op.in[5];
   p.temb = (const float*)op.in[3];
   p.res = (const __nv_bfloat16*)op.in[2];
-  p.y = (__nv_bfloat16*)op.out[0];
-  p.y_nchw = nullptr;
-  p.cout_valid = Cout;
+  p.y = head ? nullptr : (__nv_bfloat16*)op.out[0];
+  p.y_nchw = head ? (float*)op.out[0] : nullptr;
+  p.cout_valid = head ? (int)op.f[1] : Cout;
   p.mg_stats = (double*)op.out[1];
   p.scale = op.f[0];
   p.temb_off = op.i[PSLD_CONV_TEMB_OFF];

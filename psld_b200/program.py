@@ -296,10 +296,20 @@ class Plan:
                     b32 = self._w((bias.detach().to(self.dev, torch.float32) if bias is not None else 0) +
                                   be.detach().to(self.dev, torch.float32))
                     op.inp[5] = b32.data_ptr()
+            if out_nchw_f32 and Cout % 64:          # network head: zero rows up to a 64-wide N tile
+                cpad = -(-Cout // 64) * 64
+                wt = torch.cat([wt, wt.new_zeros(cpad - Cout, wt.shape[1])], 0)
+                if b32 is not None:
+                    b32 = self._w(torch.cat([b32, b32.new_zeros(cpad - Cout)]))
+                    op.inp[5] = b32.data_ptr()
+                i[L.CONV_COUT] = cpad
+                op.f[1] = float(Cout)
+            elif out_nchw_f32:
+                op.f[1] = float(Cout)
             wt = self._w(wt, torch.bfloat16)
             op.inp[4] = wt.data_ptr()
             mg = None
-            if self.fused_stats and want_stats and (OH * OW) % 32 == 0:
+            if self.fused_stats and want_stats and not out_nchw_f32 and (OH * OW) % 32 == 0:
                 mg = self._mg_buffer(N, Cout)
                 op.out[1] = mg.data_ptr()
             if not self.dry:
@@ -633,8 +643,14 @@ class Plan:
                 m = mods[i]; i += 1
                 h = self.resblock(m, h, None, offs[id(m)])
         assert not hs
-        a = self.op_gn(h, None, mods[i], True, h.shape[1] * h.shape[2]); i += 1
-        self.eps = self.op_conv(a, None, mods[i].weight, mods[i].bias, ks=3, out_nchw_f32=True); i += 1
+        if self._gn_fusable(h, None, 64) and os.environ.get("PSLD_TC_FUSE_GN_HEAD", "1") == "1":
+            # final act(GroupNorm(h)) -> conv3x3 -> fp32 NCHW eps as one GroupNorm-on-load conv
+            aff = self.op_gn(h, None, mods[i], True, h.shape[1] * h.shape[2], affine_only=True); i += 1
+            self.eps = self.op_conv(h, None, mods[i].weight, mods[i].bias, ks=3, out_nchw_f32=True,
+                                    affine=aff); i += 1
+        else:
+            a = self.op_gn(h, None, mods[i], True, h.shape[1] * h.shape[2]); i += 1
+            self.eps = self.op_conv(a, None, mods[i].weight, mods[i].bias, ks=3, out_nchw_f32=True); i += 1
         assert i == len(mods), (i, len(mods))
         self._finish_stat_arenas(zero_ops)
 

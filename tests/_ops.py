@@ -56,7 +56,7 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
     b = bias.to(dev, torch.float32).contiguous() if bias is not None else None
     if engine in (L.ENGINE_TC, L.ENGINE_TC_GN):
         if out_nchw_f32 and Cout % 32:
-            cout_k = -(-Cout // 32) * 32
+            cout_k = -(-Cout // (64 if engine == L.ENGINE_TC_GN else 32)) * (64 if engine == L.ENGINE_TC_GN else 32)
         wt = w.permute(0, 2, 3, 1).reshape(Cout, -1)
         if cout_k != Cout:
             wt = torch.cat([wt, wt.new_zeros(cout_k - Cout, wt.shape[1])], 0)

@@ -143,7 +143,7 @@ def run_plan(plan, x, t):
                 v = y.permute(0, 2, 3, 1).double().reshape(y.shape[0], -1, cout // 4, 4)
                 g(op.out[1]).add_(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1))
             if i[L.CONV_OUT_LAYOUT] == L.NCHW:
-                valid = int(f[1]) if op.engine == L.ENGINE_TC else cout
+                valid = int(f[1]) if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN) else cout
                 out.copy_(y[:, :valid])
             else:
                 out.copy_(y.permute(0, 2, 3, 1))

@@ -450,6 +450,25 @@ def test_conv_gn_fused_with_shortcut(case):
     assert float((keep[-1].double().cpu() - mref).abs().max()) <= 5e-3 * float(mref.abs().max())
 
 
+def test_conv_gn_fused_output_head():
+    """Final act(GroupNorm(h)) -> conv3x3 -> 6 channels as fp32 NCHW through the GroupNorm-on-load
+    kernel (Cout zero-padded to one 64-wide N tile)."""
+    if os.environ.get("PSLD_TC_FUSE_GN", "1") == "0":
+        pytest.skip("fused GroupNorm conv disabled by PSLD_TC_FUSE_GN=0")
+    r = _rng(78)
+    N, H, W, Cin = 3, 32, 32, 128
+    x = _t(r.standard_normal((N, H, W, Cin)) * 1.3 + 0.1, torch.bfloat16)
+    w = _t(r.standard_normal((6, Cin, 3, 3)) / 34.0)
+    b = _t(0.1 * r.standard_normal(6))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cin)), 0.2 * r.standard_normal((N, Cin))], -1))
+    op, out, keep = conv_op(x, None, w, b, engine=L.ENGINE_TC_GN, out_nchw_f32=True, affine=aff, gn_silu=True)
+    run_op(op, prepare=True)
+    a = F.silu(x.float().cpu() * aff.cpu()[:, None, None, :, 0] + aff.cpu()[:, None, None, :, 1]).to(torch.bfloat16)
+    ref = conv_ref(a, None, w.to(torch.bfloat16), b)
+    assert out.shape == (N, 6, H, W)
+    assert rel_l2(out, ref) <= 3e-3
+
+
 def test_conv_tc_output_head():
     """3x3 conv to 6 channels written as fp32 NCHW (network output head)."""
     r = _rng(77)
