@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = workload default")
     ap.add_argument("--workload", default="cifar10", choices=["cifar10", "celeba64"],
                     help="cifar10 = BASELINE configs[1] (headline); celeba64 = configs[3]")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--state", default="float32", choices=["float32", "float64"])
     ap.add_argument("--e2e-nfe", type=int, default=NFE, help="0 disables the end-to-end run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -356,7 +356,7 @@ def main_b200(args):
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
             "config": {
                 "workload": workload_desc,
                 "batch_per_gpu": B, "batch_total": B * world, "nfe_per_sample": NFE,

@@ -40,6 +40,12 @@ extern "C" {
 #define PSLD_F32 0
 #define PSLD_BF16 1
 #define PSLD_F64 2
+/* "split bf16": every value is stored as hi + lo, two bf16 numbers (hi = rn_bf16(x), lo =
+ * rn_bf16(x - hi): 16 significand bits, fp32 range).  NHWC activations keep both halves in the
+ * pixel row: [C hi | C lo] (row stride 2C bf16 = 4C bytes, lo at +C); weights as two planes
+ * [2][Cout, K].  It is the operand format of the fp32-tolerance tensor-core tier ("bf16x3":
+ * a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi, three bf16 tcgen05 MMAs into one fp32 accumulator) */
+#define PSLD_BF16S 3
 
 /* tensor layouts */
 #define PSLD_NHWC 0

@@ -96,12 +96,12 @@ def golden_upfirdn(R):
 
 
 # ---------------------------------------------------------------- network forwards
-def golden_forward(R, cfg, fname, B, seed=0):
+def golden_forward(R, cfg, fname, B, seed=0, times=(0.731, 0.0123, 1.0, 1e-3)):
     net, _ = ref_net(R, cfg, seed)
     r = np.random.default_rng([11, seed])
     H = cfg.data.image_size
     x = torch.from_numpy((r.standard_normal((B, 6, H, H)) * 1.5).astype(np.float32))
-    t = torch.from_numpy(np.asarray([0.731, 0.0123, 1.0, 1e-3][:B], dtype=np.float32))
+    t = torch.from_numpy(np.asarray(list(times)[:B], dtype=np.float32))
     with torch.no_grad():
         y = net(x, t)
     _save(fname, x=x.numpy(), t=t.numpy(), y=y.numpy(), seed=np.asarray(seed))
@@ -205,9 +205,26 @@ def fake_score(u, t):
     return (torch.tanh(u * 0.3) * 0.7 + 0.1 * torch.sin(torch.roll(u, 1, 1))) * t.view(-1, 1, 1, 1)
 
 
+def golden_full_size(R):
+    """BASELINE.json configs[1] / configs[3] at full architecture size (``init_scale=1`` so that the
+    network is numerically visible): the SSCS trajectory of the benchmarked
+    configuration (B=2, 50 NFE, per-step probe states) and forwards at B=3 / B=2 over t in
+    {1, 0.5, 1e-3}."""
+    c = cifar10_config(n_discrete_steps=50, batch_size=2, n_samples=2)
+    c.model.score_fn.init_scale = 1.0
+    golden_sampler(R, c, "sampler_cifar10_sscs50.npz", B=2, keep=2)
+    golden_forward(R, c, "forward_cifar10_b3.npz", B=3, times=(1.0, 0.5, 1e-3))
+    c = celeba64_config(n_discrete_steps=20, batch_size=2, n_samples=2)
+    c.model.score_fn.init_scale = 1.0
+    golden_forward(R, c, "forward_celeba64_b2.npz", B=2, times=(1.0, 1e-3))
+    golden_sampler(R, c, "sampler_celeba64_sscs20.npz", B=2, keep=1)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     R = load_reference()
+    if "--only-full-size" in sys.argv:
+        return golden_full_size(R)
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
     if "--only-vp" in sys.argv:
@@ -240,6 +257,7 @@ def main():
         golden_sampler(R, cfg, f"sampler_{tag}.npz", B=3, keep=3, score="fake")
     golden_inpaint_all(R)
     golden_vp(R)
+    golden_full_size(R)
 
 
 def vp_config(**ev):

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpsld_b200.so")
 # ---- constants (keep in sync with include/psld_b200.h) --------------------------------
 VERSION = 100
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4
-F32, BF16, F64 = 0, 1, 2
+F32, BF16, F64, BF16S = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 STAGE_HALF_A, STAGE_SCORE, STAGE_HALF_B, STAGE_HALF_C = 1, 2, 4, 8
 OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN, OP_ZERO = 1, 2, 3, 4, 5, 6, 7

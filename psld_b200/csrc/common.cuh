@@ -75,38 +75,101 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- "split bf16" activations (PSLD_BF16S): value = hi + lo, both bf16; a pixel row of C
+// channels is stored as [C hi | C lo] (row stride 2C, lo at +C).  Pointers to bf16s advance in
+// bf16 units; every accessor below takes the lo offset (= the row's channel count) as `lo`.
+struct __align__(2) bf16s { __nv_bfloat16 v; };
+
+template <typename T> struct Elt { static constexpr int kMul = 1; };      // row stride = kMul * C
+template <> struct Elt<bf16s> { static constexpr int kMul = 2; };
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// (a, b) -> packed hi pair and lo pair; a - hi is exact in fp32
+__device__ __forceinline__ void split_bf2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = f2_to_bf2(a, b);
+  const float2 h = bf2_to_f2(hi);
+  lo = f2_to_bf2(a - h.x, b - h.y);
+}
+
 // ---- element-type helpers: 4-wide vector load / store with fp32 math ----------------
 template <typename T>
 struct Vec4;
 
 template <>
 struct Vec4<float> {
-  static __device__ __forceinline__ float4 load(const float* p) {
+  static __device__ __forceinline__ float4 load(const float* p, int = 0) {
     return *reinterpret_cast<const float4*>(p);
   }
-  static __device__ __forceinline__ void store(float* p, float4 v) {
+  static __device__ __forceinline__ void store(float* p, float4 v, int = 0) {
     *reinterpret_cast<float4*>(p) = v;
   }
 };
 
 template <>
 struct Vec4<__nv_bfloat16> {
-  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p, int = 0) {
     uint2 r = *reinterpret_cast<const uint2*>(p);
-    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
-    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
-    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    const float2 fa = bf2_to_f2(r.x), fb = bf2_to_f2(r.y);
     return make_float4(fa.x, fa.y, fb.x, fb.y);
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v, int = 0) {
     uint2 r;
-    r.x = *reinterpret_cast<uint32_t*>(&a);
-    r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.x = f2_to_bf2(v.x, v.y);
+    r.y = f2_to_bf2(v.z, v.w);
     *reinterpret_cast<uint2*>(p) = r;
   }
 };
+
+template <>
+struct Vec4<bf16s> {
+  static __device__ __forceinline__ float4 load(const bf16s* p, int lo) {
+    const uint2 h = *reinterpret_cast<const uint2*>(p);
+    const uint2 l = *reinterpret_cast<const uint2*>(p + lo);
+    const float2 ha = bf2_to_f2(h.x), hb = bf2_to_f2(h.y), la = bf2_to_f2(l.x), lb = bf2_to_f2(l.y);
+    return make_float4(ha.x + la.x, ha.y + la.y, hb.x + lb.x, hb.y + lb.y);
+  }
+  static __device__ __forceinline__ void store(bf16s* p, float4 v, int lo) {
+    uint2 h, l;
+    split_bf2(v.x, v.y, h.x, l.x);
+    split_bf2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(p) = h;
+    *reinterpret_cast<uint2*>(p + lo) = l;
+  }
+};
+
+// scalar element access: p points at channel c of a pixel row, `lo` = the row's channel count
+template <typename T>
+__device__ __forceinline__ float ld_elt(const T* p, int lo);
+template <>
+__device__ __forceinline__ float ld_elt<float>(const float* p, int) { return *p; }
+template <>
+__device__ __forceinline__ float ld_elt<__nv_bfloat16>(const __nv_bfloat16* p, int) {
+  return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float ld_elt<bf16s>(const bf16s* p, int lo) {
+  return __bfloat162float(p[0].v) + __bfloat162float(p[lo].v);
+}
+template <typename T>
+__device__ __forceinline__ void st_elt(T* p, float v, int lo);
+template <>
+__device__ __forceinline__ void st_elt<float>(float* p, float v, int) { *p = v; }
+template <>
+__device__ __forceinline__ void st_elt<__nv_bfloat16>(__nv_bfloat16* p, float v, int) {
+  *p = __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ void st_elt<bf16s>(bf16s* p, float v, int lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  p[0].v = h;
+  p[lo].v = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
@@ -127,6 +190,7 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
+// bytes per logical element (split bf16 = two bf16)
 static inline size_t dtype_size(int dt) { return dt == PSLD_BF16 ? 2 : (dt == PSLD_F64 ? 8 : 4); }
 
 // per-op entry points (implemented in the .cu files, dispatched from capi.cu)

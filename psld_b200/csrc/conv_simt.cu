@@ -29,8 +29,9 @@ __device__ __forceinline__ float load_in(const ConvP& p, int n, int iy, int ix, 
     return ((const float*)p.x1)[(((int64_t)n * p.C1 + c) * p.H + iy) * p.W + ix];
   }
   const int64_t pix = ((int64_t)n * p.H + iy) * p.W + ix;
-  if (c < p.C1) return to_f32<TI>(((const TI*)p.x1)[pix * p.C1 + c]);
-  return to_f32<TI>(((const TI*)p.x2)[pix * p.C2 + (c - p.C1)]);
+  constexpr int M = Elt<TI>::kMul;
+  if (c < p.C1) return ld_elt<TI>((const TI*)p.x1 + pix * (p.C1 * M) + c, p.C1);
+  return ld_elt<TI>((const TI*)p.x2 + pix * (p.C2 * M) + (c - p.C1), p.C2);
 }
 
 template <typename TI, typename TO>
@@ -127,7 +128,7 @@ conv_simt_kernel(const ConvP p) {
       if (co < p.Cout) {
         if (p.bias) v += p.bias[co];
         if (p.temb) v += p.temb[(int64_t)n * p.temb_bstride + p.temb_off + co];
-        if (p.res) v += to_f32<TO>(((const TO*)p.res)[m * p.Cout + co]);
+        if (p.res) v += ld_elt<TO>((const TO*)p.res + m * (p.Cout * Elt<TO>::kMul) + co, p.Cout);
         v *= p.scale;
       }
       o[j] = v;
@@ -139,13 +140,13 @@ conv_simt_kernel(const ConvP p) {
       for (int j = 0; j < 4; ++j)
         if (co0 + j < p.Cout) y[(((int64_t)n * p.Cout + co0 + j) * p.OH + oy) * p.OW + ox] = o[j];
     } else {
-      TO* y = (TO*)p.y + m * p.Cout + co0;
+      TO* y = (TO*)p.y + m * (p.Cout * Elt<TO>::kMul) + co0;
       if ((p.Cout & 3) == 0 && co0 + 3 < p.Cout) {
-        Vec4<TO>::store(y, make_float4(o[0], o[1], o[2], o[3]));
+        Vec4<TO>::store(y, make_float4(o[0], o[1], o[2], o[3]), p.Cout);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (co0 + j < p.Cout) y[j] = from_f32<TO>(o[j]);
+          if (co0 + j < p.Cout) st_elt<TO>(y + j, o[j], p.Cout);
       }
     }
   }
@@ -185,6 +186,12 @@ int run_conv_simt(const psld_op& op, cudaStream_t s) {
     launch_pdl(conv_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, s, 1, p);
   else if (idt == PSLD_F32 && odt == PSLD_BF16)
     launch_pdl(conv_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, p);
+  else if (idt == PSLD_BF16S && odt == PSLD_BF16S)
+    launch_pdl(conv_simt_kernel<bf16s, bf16s>, dim3(grid), dim3(256), 0, s, 1, p);
+  else if (idt == PSLD_BF16S && odt == PSLD_F32)
+    launch_pdl(conv_simt_kernel<bf16s, float>, dim3(grid), dim3(256), 0, s, 1, p);
+  else if (idt == PSLD_F32 && odt == PSLD_BF16S)
+    launch_pdl(conv_simt_kernel<float, bf16s>, dim3(grid), dim3(256), 0, s, 1, p);
   else { set_error("conv: unsupported dtypes %d -> %d", idt, odt); return PSLD_EINVAL; }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
@@ -206,7 +213,8 @@ attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int HW, int C, 
   const int n = blockIdx.y, q0 = blockIdx.x * TQ;
   const int tid = threadIdx.x;
   const int tq = tid >> 3, tk = tid & 7;
-  const int ld = 3 * C;
+  const int lo = 3 * C;                          // split-bf16 lo offset of a q|k|v row
+  const int ld = lo * Elt<T>::kMul;
   const T* base = qkv + (int64_t)n * HW * ld;
 
   // ---- phase 1: S = scale * Q K^T, key blocks of 256, channel chunks of 32
@@ -220,13 +228,13 @@ attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int HW, int C, 
       for (int e = tid; e < TQ * 32; e += 256) {
         const int r = e >> 5, cc = e & 31;
         const int q = q0 + r;
-        Qs[r * 33 + cc] = (q < HW && c0 + cc < C) ? to_f32<T>(base[(int64_t)q * ld + c0 + cc]) : 0.f;
+        Qs[r * 33 + cc] = (q < HW && c0 + cc < C) ? ld_elt<T>(base + (int64_t)q * ld + c0 + cc, lo) : 0.f;
       }
       for (int e = tid; e < 256 * 32; e += 256) {
         const int r = e >> 5, cc = e & 31;
         const int key = kb + r;
         Ks[r * 33 + cc] =
-            (key < HW && c0 + cc < C) ? to_f32<T>(base[(int64_t)key * ld + C + c0 + cc]) : 0.f;
+            (key < HW && c0 + cc < C) ? ld_elt<T>(base + (int64_t)key * ld + C + c0 + cc, lo) : 0.f;
       }
       __syncthreads();
 #pragma unroll 4
@@ -278,7 +286,7 @@ attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int HW, int C, 
       for (int e = tid; e < 32 * 256; e += 256) {
         const int r = e >> 8, cc = e & 255;
         const int key = k0 + r;
-        Vs[e] = (key < HW && cb + cc < C) ? to_f32<T>(base[(int64_t)key * ld + 2 * C + cb + cc]) : 0.f;
+        Vs[e] = (key < HW && cb + cc < C) ? ld_elt<T>(base + (int64_t)key * ld + 2 * C + cb + cc, lo) : 0.f;
       }
       __syncthreads();
 #pragma unroll 4
@@ -294,7 +302,7 @@ attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int HW, int C, 
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int c = cb + tk + 8 * i;
-        if (c < C) out[((int64_t)n * HW + q) * C + c] = from_f32<T>(acc[i]);
+        if (c < C) st_elt<T>(out + ((int64_t)n * HW + q) * (C * Elt<T>::kMul) + c, acc[i], C);
       }
     }
   }
@@ -314,6 +322,11 @@ int run_attn_simt(const psld_op& op, cudaStream_t s) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(attn_simt_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, s, 1, (const __nv_bfloat16*)op.in[0],
                                                            (__nv_bfloat16*)op.out[0], HW, C, op.f[0]);
+  } else if (dt == PSLD_BF16S) {
+    PSLD_CHECK_CUDA(cudaFuncSetAttribute(attn_simt_kernel<bf16s>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_pdl(attn_simt_kernel<bf16s>, dim3(grid), dim3(256), smem, s, 1, (const bf16s*)op.in[0],
+               (bf16s*)op.out[0], HW, C, op.f[0]);
   } else {
     PSLD_CHECK_CUDA(cudaFuncSetAttribute(attn_simt_kernel<float>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -51,6 +51,7 @@ struct ConvTcState {
   ConvTcParams p;
   int grid;
   bool pair;      // 2-CTA (cta_group::2) variant
+  bool x3;        // split-bf16 operands, three MMA groups per k-block (fp32-tolerance tier)
 };
 
 // Optional per-CTA phase timeline (build with -DPSLD_TC_TRACE; scripts/tc_trace.py reads it)
@@ -61,12 +62,12 @@ __device__ long long g_tc_trace[160 * 8];
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
-template <bool kPair>
+template <bool kPair, bool kX3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmE1,
                const __grid_constant__ CUtensorMap tmE2, const ConvTcParams p) {
-  using Cfg = TcCfg<kPair>;
+  using Cfg = TcCfg<kPair, kX3>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 0) TC_TRACE(0);
@@ -138,7 +139,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const bool is_a = warp == 0;
       if (is_a) pdl_wait();     // activations come from the previous kernel; weights do not
       const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) *
-                             (kPair ? 2u : 1u);
+                             (kPair ? 2u : 1u) * (kX3 ? 2u : 1u);
+      // one A / B tile of this stage (kX3: called for the hi half, then for the lo half)
+      auto load_a = [&](uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int x, int y, int n) {
+        if (kPair) tma_load_4d_pair(dst, tm, bar, c, x, y, n);
+        else tma_load_4d(dst, tm, bar, c, x, y, n);
+      };
+      auto load_b = [&](uint32_t dst, uint32_t bar, int k, int row) {
+        if (kPair) tma_load_2d_pair(dst, &tmB, bar, k, row);
+        else tma_load_2d(dst, &tmB, bar, k, row);
+      };
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
@@ -156,13 +166,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               if (elect_one()) {
                 if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
                 if (is_a) {
-                  const CUtensorMap* tmA = cc < p.kchunks1 ? &tmA1 : &tmA2;
-                  const int c0 = (cc < p.kchunks1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
-                  if (kPair) tma_load_4d_pair(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
-                  else tma_load_4d(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+                  const bool s1 = cc < p.kchunks1;
+                  const CUtensorMap* tmA = s1 ? &tmA1 : &tmA2;
+                  const int c0 = (s1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+                  load_a(sa, tmA, full_bar(stage), c0, kx - p.pad, y0 + ky, n0);
+                  if (kX3)
+                    load_a(sa + TC_A_BYTES, tmA, full_bar(stage), c0 + (s1 ? p.lo1 : p.lo2), kx - p.pad,
+                           y0 + ky, n0);
                 } else {
-                  if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
-                  else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                  load_b(sa + Cfg::kBOff, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                  if (kX3)
+                    load_b(sa + Cfg::kBOff + Cfg::kBBytes, full_bar(stage), kb * TC_BLOCK_K,
+                           bn0 + p.w_lo_rows);
                 }
               }
               __syncwarp();
@@ -176,13 +191,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (elect_one()) {
             if (!kPair || rank == 0) mbar_arrive_expect_tx(full_bar(stage), my_tx);
             if (is_a) {
-              const CUtensorMap* tmE = cc < p.ext_kchunks1 ? &tmE1 : &tmE2;
-              const int c0 = (cc < p.ext_kchunks1 ? cc : cc - p.ext_kchunks1) * TC_BLOCK_K;
-              if (kPair) tma_load_4d_pair(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
-              else tma_load_4d(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+              const bool s1 = cc < p.ext_kchunks1;
+              const CUtensorMap* tmE = s1 ? &tmE1 : &tmE2;
+              const int c0 = (s1 ? cc : cc - p.ext_kchunks1) * TC_BLOCK_K;
+              load_a(sa, tmE, full_bar(stage), c0, 0, y0 + p.pad, n0);
+              if (kX3)
+                load_a(sa + TC_A_BYTES, tmE, full_bar(stage), c0 + (s1 ? p.loe1 : p.loe2), 0,
+                       y0 + p.pad, n0);
             } else {
-              if (kPair) tma_load_2d_pair(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
-              else tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              load_b(sa + Cfg::kBOff, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              if (kX3)
+                load_b(sa + Cfg::kBOff + Cfg::kBBytes, full_bar(stage), kb * TC_BLOCK_K,
+                       bn0 + p.w_lo_rows);
             }
           }
           __syncwarp();
@@ -216,17 +236,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (kb == 0 && unit == unit0) TC_TRACE(2);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
-          const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+          const uint64_t bdesc = make_sw128_desc(sa + Cfg::kBOff);
           if (elect_one()) {
+            auto group = [&](uint64_t ad, uint64_t bd, bool first) {
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-              // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              if (kPair)
-                tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                 (kb > 0 || k > 0) ? 1u : 0u);
-              else
-                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                            (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+                const uint32_t accum = (!first || kb > 0 || k > 0) ? 1u : 0u;
+                if (kPair) tc_mma_bf16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accum);
+                else tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accum);
+              }
+            };
+            group(adesc, bdesc, true);                               // a_hi * w_hi
+            if (kX3) {
+              const uint64_t adesc_lo = make_sw128_desc(sa + TC_A_BYTES);
+              const uint64_t bdesc_lo = make_sw128_desc(sa + Cfg::kBOff + Cfg::kBBytes);
+              group(adesc, bdesc_lo, false);                         // a_hi * w_lo
+              group(adesc_lo, bdesc, false);                         // a_lo * w_hi
             }
             // frees the smem stage (in both CTAs) when these MMAs retire
             if (kPair) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
@@ -254,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
-      tc_epilogue_tile(
+      tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(
           p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
           stg_base + (uint32_t)(warp - 2) * 4096u, addv_base + (uint32_t)(warp - 2) * 256u,
           [&]() {
@@ -293,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 // ---------------------------------------------------------------- host side
 // Activation map over the INPUT tensor [N, H, W, C]; the box covers OW x BH x BN output positions
 // visited with element stride `stride` (TMA loads ceil(box / stride) elements per dimension).
+// (split bf16: C = 2 x channels, the row holds [hi | lo])
 static int encode_act_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int OW,
                           int BH, int BN_img, int stride) {
   EncodeTiledFn enc = get_encode_fn();
@@ -335,9 +362,12 @@ int prepare_conv_tc(psld_op& op) {
     return PSLD_EUNSUPPORTED;
   };
   const bool head = op.i[PSLD_CONV_OUT_LAYOUT] == PSLD_NCHW;   // fp32 NCHW output head
-  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16) return unsupported("input dtype must be bf16");
-  if (op.i[PSLD_CONV_OUT_DTYPE] != (head ? PSLD_F32 : PSLD_BF16))
-    return unsupported("output must be bf16 NHWC or fp32 NCHW");
+  const int adt = op.i[PSLD_CONV_IN_DTYPE];
+  if (adt != PSLD_BF16 && adt != PSLD_BF16S) return unsupported("input dtype must be bf16 or split bf16");
+  const bool x3 = adt == PSLD_BF16S;
+  const int cm = x3 ? 2 : 1;                                   // bf16 elements per channel in a row
+  if (op.i[PSLD_CONV_OUT_DTYPE] != (head ? PSLD_F32 : adt))
+    return unsupported("output must be NHWC of the input's element type, or fp32 NCHW");
   if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC) return unsupported("input layout must be NHWC");
   if (head && (op.in[2] || op.f[1] < 1.0f || (int)op.f[1] > Cout))
     return unsupported("NCHW head takes no residual and needs f[1] = valid channels");
@@ -355,7 +385,8 @@ int prepare_conv_tc(psld_op& op) {
   if (!is_pow2(OW) || !is_pow2(OH) || OW > 128 || OW < 4)
     return unsupported("output W,H must be pow2, 4..128");
   if (stride == 2 && OW * stride > 256) return unsupported("stride-2 box too wide");
-  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != PSLD_BF16) return unsupported("residual dtype");
+  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != adt) return unsupported("residual dtype");
+  if (x3 && !head && (OH * OW) % 32) return unsupported("split bf16 output needs H*W %% 32 == 0");
   if (!op.in[0] || !op.in[4] || !op.out[0] || (C2 > 0 && !op.in[1])) {
     set_error("conv_tc: null pointer");
     return PSLD_EINVAL;
@@ -394,10 +425,10 @@ int prepare_conv_tc(psld_op& op) {
   }
   ConvTcState* st = new (std::nothrow) ConvTcState();
   if (!st) { set_error("conv_tc: out of host memory"); return PSLD_ECUDA; }
-  int rc = encode_act_map(&st->a1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+  int rc = encode_act_map(&st->a1, op.in[0], N, H, W, cm * C1, OW, BH, BN_img, stride);
   if (rc == PSLD_OK)
-    rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, C2, OW, BH, BN_img, stride)
-                : encode_act_map(&st->a2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+    rc = C2 > 0 ? encode_act_map(&st->a2, op.in[1], N, H, W, cm * C2, OW, BH, BN_img, stride)
+                : encode_act_map(&st->a2, op.in[0], N, H, W, cm * C1, OW, BH, BN_img, stride);
   const int E1 = op.i[PSLD_CONV_EXT_C1], E2 = op.i[PSLD_CONV_EXT_C2];
   const bool ext = op.in[8] != nullptr && E1 > 0;
   if (ext && (stride != 1 || E1 % TC_BLOCK_K || E2 % TC_BLOCK_K || (E2 > 0 && !op.in[9]))) {
@@ -405,13 +436,14 @@ int prepare_conv_tc(psld_op& op) {
     return unsupported("1x1 extension needs stride 1 and channel counts %% 64 == 0");
   }
   if (rc == PSLD_OK)
-    rc = ext ? encode_act_map(&st->e1, op.in[8], N, OH, OW, E1, OW, BH, BN_img, 1)
-             : encode_act_map(&st->e1, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+    rc = ext ? encode_act_map(&st->e1, op.in[8], N, OH, OW, cm * E1, OW, BH, BN_img, 1)
+             : encode_act_map(&st->e1, op.in[0], N, H, W, cm * C1, OW, BH, BN_img, stride);
   if (rc == PSLD_OK)
-    rc = (ext && E2 > 0) ? encode_act_map(&st->e2, op.in[9], N, OH, OW, E2, OW, BH, BN_img, 1)
-                         : encode_act_map(&st->e2, op.in[0], N, H, W, C1, OW, BH, BN_img, stride);
+    rc = (ext && E2 > 0) ? encode_act_map(&st->e2, op.in[9], N, OH, OW, cm * E2, OW, BH, BN_img, 1)
+                         : encode_act_map(&st->e2, op.in[0], N, H, W, cm * C1, OW, BH, BN_img, stride);
   const int K = KS * KS * (C1 + C2) + (ext ? E1 + E2 : 0);
-  if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], Cout, K, pair ? block_n / 2 : block_n);
+  // split bf16 weights: two planes [2][Cout, K] seen as one [2*Cout, K] matrix
+  if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], cm * Cout, K, pair ? block_n / 2 : block_n);
   if (rc != PSLD_OK) { delete st; return rc; }
 
   ConvTcParams& p = st->p;
@@ -439,6 +471,8 @@ int prepare_conv_tc(psld_op& op) {
   p.ext_kchunks = ext ? (E1 + E2) / TC_BLOCK_K : 0;
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * OH * OW;
+  p.lo1 = C1; p.lo2 = C2; p.loe1 = E1; p.loe2 = E2; p.w_lo_rows = Cout;
+  st->x3 = x3;
   const int64_t m_tiles = (int64_t)((N + BN_img - 1) / BN_img) * p.tiles_y;
   const int64_t m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
   p.num_tiles = (int)(m_units * p.n_tiles_n);          // work units (tiles, or tile pairs)
@@ -451,12 +485,18 @@ int prepare_conv_tc(psld_op& op) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<false>::kSmemBytes);
+                                         TcCfg<false, false>::kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               TcCfg<true>::kSmemBytes);
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               TcCfg<true, false>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               TcCfg<false, true>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               TcCfg<true, true>::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -479,15 +519,16 @@ int release_conv_tc(psld_op& op) {
 int run_conv_tc(const psld_op& op, cudaStream_t s) {
   const ConvTcState* st = (const ConvTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_tc: op not prepared (call psld_op_prepare)");
+#define CONV_TC_LAUNCH(PAIR, X3)                                                               \
+  PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<PAIR, X3>, dim3((unsigned)st->grid), dim3(TC_THREADS), \
+                             TcCfg<PAIR, X3>::kSmemBytes, s, PAIR ? 2 : 1, st->a1, st->a2, st->b,  \
+                             st->e1, st->e2, st->p))
   if (st->pair) {
-    PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<true>, dim3((unsigned)st->grid), dim3(TC_THREADS),
-                               TcCfg<true>::kSmemBytes, s, 2, st->a1, st->a2, st->b, st->e1, st->e2,
-                               st->p));
+    if (st->x3) CONV_TC_LAUNCH(true, true); else CONV_TC_LAUNCH(true, false);
   } else {
-    PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<false>, dim3((unsigned)st->grid), dim3(TC_THREADS),
-                               TcCfg<false>::kSmemBytes, s, 1, st->a1, st->a2, st->b, st->e1, st->e2,
-                               st->p));
+    if (st->x3) CONV_TC_LAUNCH(false, true); else CONV_TC_LAUNCH(false, false);
   }
+#undef CONV_TC_LAUNCH
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

@@ -40,6 +40,10 @@ struct ConvTcParams {
   int block_n, n_tiles_n;
   int num_tiles;
   int64_t M;                 // N*H*W
+  // split-bf16 ("bf16x3") operands: channel offset of the lo half inside a pixel row of source
+  // 1 / 2 / shortcut 1 / shortcut 2 (= the source's channel count) and row offset of the lo plane of
+  // the weight matrix (= its padded Cout); the output / residual rows are [Cout hi | Cout lo]
+  int lo1, lo2, loe1, loe2, w_lo_rows;
 };
 
 
@@ -51,11 +55,16 @@ struct ConvTcParams {
 //   from both CTAs' shared memory.  Per CTA and k-block this cuts the L2->SM traffic from 48 KB to
 //   32 KB and frees room for a 6-deep ring (ncu on the 1-CTA kernel: tensor pipe 75 % active with
 //   the XBAR at 15.6 TB/s and only ~1.3 us of TMA lookahead).
-template <bool kPair>
+// kX3 = the fp32-tolerance tier: activations and weights are split bf16 (hi + lo); one stage holds
+//   A_hi | A_lo | B_hi | B_lo of a k-block and feeds THREE MMA groups (hi*hi, hi*lo, lo*hi) into
+//   the same fp32 accumulator: products to ~2^-17 relative instead of bf16's 2^-9, at 3x the
+//   tensor-pipe work and 2x the operand bytes per k-block (half as many, twice as long stages).
+template <bool kPair, bool kX3 = false>
 struct TcCfg {
-  static constexpr int kStages = kPair ? 6 : TC_STAGES;
+  static constexpr int kStages = kX3 ? (kPair ? 3 : 2) : (kPair ? 6 : TC_STAGES);
   static constexpr int kBBytes = kPair ? TC_B_BYTES / 2 : TC_B_BYTES;
-  static constexpr int kStageBytes = TC_A_BYTES + kBBytes;
+  static constexpr int kStageBytes = (TC_A_BYTES + kBBytes) * (kX3 ? 2 : 1);
+  static constexpr int kBOff = kX3 ? 2 * TC_A_BYTES : TC_A_BYTES;   // first B tile inside a stage
   static constexpr int kStagingBytes = 8 * 4096;   // epilogue transpose buffers, 4 KB per warp
   static constexpr int kAddvBytes = 8 * 256;       // (bias + temb) * scale, 64 columns per warp
   // 768 B of alignment slack: the kernel traps if the dynamic window starts further than that
@@ -173,12 +182,17 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 // kPrefetchRes: keep the NEXT column group's residual in registers while the current one is
 // processed (GC/2 registers); kTmemAhead (GC = 64): second TMEM chunk in flight while the first is
 // processed (32 registers).  Both off for kernels that are short of registers.
-template <bool kPrefetchRes = true, int GC = 64, bool kTmemAhead = true, class Acquire, class Release>
+// kSplit: output / residual are split bf16 ([Cout hi | Cout lo] rows): GC must be 32 and `stg` holds
+// two 2 KB tiles (hi, lo) per warp.
+template <bool kPrefetchRes = true, int GC = 64, bool kTmemAhead = true, bool kSplit = false,
+          class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
                                                  int m_tile, int n_tile, int quarter, int half,
                                                  int lane, uint32_t stg, uint32_t addv,
                                                  Acquire acquire, Release release) {
   static_assert(GC == 64 || GC == 32, "staging group = 64 or 32 columns");
+  static_assert(!kSplit || GC == 32, "split-bf16 output stages 32-column groups");
+  constexpr int NT = kSplit ? 2 : 1;                  // staging tiles / global planes (hi, lo)
   const int64_t m = (int64_t)m_tile * TC_BLOCK_M + quarter * 32 + lane;
   const bool valid = m < p.M;
   const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
@@ -202,12 +216,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     const bool full = m_base + 32 <= p.M;             // warp-uniform: no per-row bounds checks
     const int sub_row = lane / CPR, chunk = lane % CPR;
     const int ncg = p.block_n / GC;
+    constexpr uint32_t TILE = 32u * RB;               // bytes of one staging tile
+    const int64_t ldo = (int64_t)p.Cout * NT;          // output / residual row stride (elements)
     const uint32_t my_row = stg + (uint32_t)lane * RB;
     const int my_swz = swz(lane);
     const float scale = p.scale;
     const float* tembw = nullptr;
     if (p.temb) tembw = p.temb + (m_base < p.M ? m_base / p.HW : 0) * p.temb_bstride + p.temb_off;
-    uint4 rq[ITS];
+    uint4 rq[NT][ITS];
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_add = [&](int cg) {
       if (lane < GC / 4) {
@@ -219,18 +235,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         }
       }
     };
-    const int64_t rowstep = (int64_t)RPI * p.Cout;    // RPI rows (elements)
+    const int64_t rowstep = (int64_t)RPI * ldo;       // RPI rows (elements)
     auto load_res = [&](int cg) {
-      const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * GC + chunk * 8 +
-                                (m_base + sub_row) * p.Cout;
-      if (full) {
 #pragma unroll
-        for (int it = 0; it < ITS; ++it) rq[it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
-      } else {
+      for (int pl = 0; pl < NT; ++pl) {
+        const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * GC + chunk * 8 +
+                                  (m_base + sub_row) * ldo + pl * p.Cout;
+        if (full) {
 #pragma unroll
-        for (int it = 0; it < ITS; ++it)
-          if (m_base + RPI * it + sub_row < p.M)
-            rq[it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
+          for (int it = 0; it < ITS; ++it) rq[pl][it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
+        } else {
+#pragma unroll
+          for (int it = 0; it < ITS; ++it)
+            if (m_base + RPI * it + sub_row < p.M)
+              rq[pl][it] = *reinterpret_cast<const uint4*>(rp + it * rowstep);
+        }
       }
     };
     // one 32-column chunk: r = accumulator row fragment -> bf16 into this thread's row of the
@@ -248,15 +267,24 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
               scale, scale, __uint_as_float(ad[q].z), __uint_as_float(ad[q].w));
       }
       if (p.res) {
-        uint4 wq[4];
+        uint4 wq[4], wl[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) wq[q] = lds128(my_row + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4));
+        for (int q = 0; q < 4; ++q) {
+          wq[q] = lds128(my_row + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4));
+          if (kSplit) wl[q] = lds128(my_row + TILE + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4));
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t w[4] = {wq[q].x, wq[q].y, wq[q].z, wq[q].w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+            float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+            if (kSplit) {
+              const uint32_t wlo[4] = {wl[q].x, wl[q].y, wl[q].z, wl[q].w};
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wlo[t]));
+              f.x += g.x;
+              f.y += g.y;
+            }
             ffma2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], f.x, f.y, scale, scale, v[q * 8 + 2 * t],
                   v[q * 8 + 2 * t + 1]);
           }
@@ -264,13 +292,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t o[4];
+        uint32_t o[4], ol[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
-          o[t] = *reinterpret_cast<uint32_t*>(&h);
+          if (kSplit) {
+            split_bf2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1], o[t], ol[t]);
+          } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+            o[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
         }
         sts128(my_row + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4), o[0], o[1], o[2], o[3]);
+        if (kSplit)
+          sts128(my_row + TILE + (uint32_t)(((sub * 4 + q) ^ my_swz) << 4), ol[0], ol[1], ol[2], ol[3]);
       }
       if (stats) {
         // GroupNorm statistics of the tensor being written, at 4-channel ("micro-group")
@@ -320,11 +354,13 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       if (p.res) {
         if (!kPrefetchRes && cg != half) load_res(cg);
 #pragma unroll
-        for (int it = 0; it < ITS; ++it) {
-          const int row = RPI * it + sub_row;
-          sts128(stg + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4),
-                 rq[it].x, rq[it].y, rq[it].z, rq[it].w);
-        }
+        for (int pl = 0; pl < NT; ++pl)
+#pragma unroll
+          for (int it = 0; it < ITS; ++it) {
+            const int row = RPI * it + sub_row;
+            sts128(stg + pl * TILE + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4),
+                   rq[pl][it].x, rq[pl][it].y, rq[pl][it].z, rq[pl][it].w);
+          }
       }
       __syncwarp();
       if (more) {
@@ -361,13 +397,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
         }
       }
       __syncwarp();
-      {
-        __nv_bfloat16* yp = p.y + co_base + chunk * 8 + (m_base + sub_row) * p.Cout;
+#pragma unroll
+      for (int pl = 0; pl < NT; ++pl) {
+        __nv_bfloat16* yp = p.y + co_base + chunk * 8 + (m_base + sub_row) * ldo + pl * p.Cout;
         uint4 q[ITS];
 #pragma unroll
         for (int it = 0; it < ITS; ++it) {
           const int row = RPI * it + sub_row;
-          q[it] = lds128(stg + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4));
+          q[it] = lds128(stg + pl * TILE + (uint32_t)row * RB + (uint32_t)((chunk ^ swz(row)) << 4));
         }
         if (full) {
 #pragma unroll
@@ -381,6 +418,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
       __syncwarp();
     }
   } else {
+  if (kSplit && p.y != nullptr) __trap();     // split-bf16 NHWC output exists only on the staged path
   acquire();
   const int img = valid ? (int)(m / p.HW) : 0;
   const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;

@@ -32,7 +32,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, in
     const int64_t r = i / CW;
     const int p = (int)(r % HW);
     const int n = (int)(r / HW);
-    out[r * CP + c] = c < C ? from_f32<T>(in[((int64_t)n * C + c) * HW + p]) : from_f32<T>(0.f);
+    st_elt<T>(out + r * (CP * Elt<T>::kMul) + c, c < C ? in[((int64_t)n * C + c) * HW + p] : 0.f, CP);
   }
 }
 
@@ -47,7 +47,7 @@ nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int N, in
     const int64_t r = i / HW;
     const int c = (int)(r % C);
     const int n = (int)(r / C);
-    out[i] = to_f32<T>(in[((int64_t)n * HW + p) * C + c]);
+    out[i] = ld_elt<T>(in + ((int64_t)n * HW + p) * (C * Elt<T>::kMul) + c, C);
   }
 }
 
@@ -72,6 +72,9 @@ int run_layout(const psld_op& op, cudaStream_t s) {
     if (dt == PSLD_BF16)
       launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
                                                             (__nv_bfloat16*)op.out[0], N, C, HW, CP, CW);
+    else if (dt == PSLD_BF16S)
+      launch_pdl(nchw_to_nhwc_kernel<bf16s>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
+                 (bf16s*)op.out[0], N, C, HW, CP, CW);
     else
       launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0],
                                                     N, C, HW, CP, CW);
@@ -79,6 +82,9 @@ int run_layout(const psld_op& op, cudaStream_t s) {
     if (dt == PSLD_BF16)
       launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, (const __nv_bfloat16*)op.in[0],
                                                             (float*)op.out[0], N, C, HW);
+    else if (dt == PSLD_BF16S)
+      launch_pdl(nhwc_to_nchw_kernel<bf16s>, dim3(grid), dim3(256), 0, s, 1, (const bf16s*)op.in[0],
+                 (float*)op.out[0], N, C, HW);
     else
       launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0],
                                                     N, C, HW);
@@ -175,19 +181,19 @@ template <typename T>
 struct Vec8;
 template <>
 struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8], int = 0) {
     const float4 a = *reinterpret_cast<const float4*>(p);
     const float4 b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8], int = 0) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
 };
 template <>
 struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8], int = 0) {
     const uint4 r = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -197,7 +203,7 @@ struct Vec8<__nv_bfloat16> {
       v[2 * t + 1] = f.y;
     }
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8], int = 0) {
     uint32_t w[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -205,6 +211,28 @@ struct Vec8<__nv_bfloat16> {
       w[t] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <>
+struct Vec8<bf16s> {
+  static __device__ __forceinline__ void load(const bf16s* p, float (&v)[8], int lo) {
+    const uint4 h = *reinterpret_cast<const uint4*>(p);
+    const uint4 l = *reinterpret_cast<const uint4*>(p + lo);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 a = bf2_to_f2(hw[t]), b = bf2_to_f2(lw[t]);
+      v[2 * t] = a.x + b.x;
+      v[2 * t + 1] = a.y + b.y;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16s* p, const float (&v)[8], int lo) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) split_bf2(v[2 * t], v[2 * t + 1], hw[t], lw[t]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(p + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 };
 
@@ -242,7 +270,8 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
     const int c = tv * VW;
     const bool first = c < C1;
     const T* src = first ? x1 + c : x2 + (c - C1);
-    const int ld = first ? C1 : C2;
+    const int lo = first ? C1 : C2;              // channels of the source = split-bf16 lo offset
+    const int ld = lo * Elt<T>::kMul;            // pixel row stride
     float s[VW], q[VW];
     double ds[VW], dq[VW];
 #pragma unroll
@@ -254,8 +283,8 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u) {
         const T* ptr = src + ((int64_t)n * HW + p + u * rows_per_iter) * ld;
-        if (VW == 8) Vec8<T>::load(ptr, v[u]);
-        else { const float4 t = Vec4<T>::load(ptr); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
+        if (VW == 8) Vec8<T>::load(ptr, v[u], lo);
+        else { const float4 t = Vec4<T>::load(ptr, lo); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
       }
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u)
@@ -271,8 +300,8 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
     for (; p < p1; p += rows_per_iter) {
       float v[8];
       const T* ptr = src + ((int64_t)n * HW + p) * ld;
-      if (VW == 8) Vec8<T>::load(ptr, v);
-      else { const float4 t = Vec4<T>::load(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+      if (VW == 8) Vec8<T>::load(ptr, v, lo);
+      else { const float4 t = Vec4<T>::load(ptr, lo); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 #pragma unroll
       for (int k = 0; k < VW; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
     }
@@ -357,7 +386,9 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
   const int c = tv * VW;
   const bool first = c < C1;
   const TI* src = first ? x1 + c : x2 + (c - C1);
-  const int ld = first ? C1 : C2;
+  const int lo = first ? C1 : C2;                // split-bf16 lo offset of the source
+  const int ld = lo * Elt<TI>::kMul;
+  constexpr int MO = Elt<TO>::kMul;
   float sc[VW], bi[VW];
 #pragma unroll
   for (int k = 0; k < VW; ++k) {
@@ -371,8 +402,8 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
       const TI* ptr = src + ((int64_t)n * HW + p + u * rows_per_iter) * ld;
-      if (VW == 8) Vec8<TI>::load(ptr, v[u]);
-      else { const float4 t = Vec4<TI>::load(ptr); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
+      if (VW == 8) Vec8<TI>::load(ptr, v[u], lo);
+      else { const float4 t = Vec4<TI>::load(ptr, lo); v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w; }
     }
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
@@ -381,24 +412,24 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
         float o = fmaf(v[u][k], sc[k], bi[k]);
         v[u][k] = silu ? silu_t<kFast>(o) : o;
       }
-      TO* dst = y + ((int64_t)n * HW + p + u * rows_per_iter) * C + c;
-      if (VW == 8) Vec8<TO>::store(dst, v[u]);
-      else Vec4<TO>::store(dst, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+      TO* dst = y + ((int64_t)n * HW + p + u * rows_per_iter) * (C * MO) + c;
+      if (VW == 8) Vec8<TO>::store(dst, v[u], C);
+      else Vec4<TO>::store(dst, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]), C);
     }
   }
   for (; p < p1; p += rows_per_iter) {
     float v[8];
     const TI* ptr = src + ((int64_t)n * HW + p) * ld;
-    if (VW == 8) Vec8<TI>::load(ptr, v);
-    else { const float4 t = Vec4<TI>::load(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    if (VW == 8) Vec8<TI>::load(ptr, v, lo);
+    else { const float4 t = Vec4<TI>::load(ptr, lo); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 #pragma unroll
     for (int k = 0; k < VW; ++k) {
       float o = fmaf(v[k], sc[k], bi[k]);
       v[k] = silu ? silu_t<kFast>(o) : o;
     }
-    TO* dst = y + ((int64_t)n * HW + p) * C + c;
-    if (VW == 8) Vec8<TO>::store(dst, v);
-    else Vec4<TO>::store(dst, make_float4(v[0], v[1], v[2], v[3]));
+    TO* dst = y + ((int64_t)n * HW + p) * (C * MO) + c;
+    if (VW == 8) Vec8<TO>::store(dst, v, C);
+    else Vec4<TO>::store(dst, make_float4(v[0], v[1], v[2], v[3]), C);
   }
 }
 
@@ -492,6 +523,7 @@ int run_gn(const psld_op& op, cudaStream_t s) {
   launch_pdl(gn_stats_kernel<T, VW>, dim3(grid), dim3(256), sh1, s, 1, (const T*)op.in[0], (const T*)op.in[1], part, HW, \
                                                 C1, C2, G, nchunk)
     if (idt == PSLD_BF16) { if (v8) GN_STATS(__nv_bfloat16, 8); else GN_STATS(__nv_bfloat16, 4); }
+    else if (idt == PSLD_BF16S) { if (v8) GN_STATS(bf16s, 8); else GN_STATS(bf16s, 4); }
     else { if (v8) GN_STATS(float, 8); else GN_STATS(float, 4); }
 #undef GN_STATS
   }
@@ -520,6 +552,7 @@ int run_gn(const psld_op& op, cudaStream_t s) {
              eps, silu)
 #define GN_APPLY2(T, VW, FAST) do { if (fused) GN_APPLY(T, VW, FAST, true); else GN_APPLY(T, VW, FAST, false); } while (0)
   if (idt == PSLD_BF16) { if (v8) GN_APPLY2(__nv_bfloat16, 8, true); else GN_APPLY2(__nv_bfloat16, 4, true); }
+  else if (idt == PSLD_BF16S) { if (v8) GN_APPLY2(bf16s, 8, false); else GN_APPLY2(bf16s, 4, false); }
   else { if (v8) GN_APPLY2(float, 8, false); else GN_APPLY2(float, 4, false); }
 #undef GN_APPLY2
 #undef GN_APPLY
@@ -565,22 +598,22 @@ fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int 
         const int ix = ux / up;
         if (ix >= W) continue;
         const float w = taps.k[(KH - 1 - ky) * KH + (KH - 1 - kx)];   // true convolution: flipped
-        const T* src = x + (((int64_t)n * H + iy) * W + ix) * C + cv * VW;
+        const T* src = x + (((int64_t)n * H + iy) * W + ix) * (C * Elt<T>::kMul) + cv * VW;
         float v[8];
-        if (VW == 8) Vec8<T>::load(src, v);
-        else { const float4 t = Vec4<T>::load(src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        if (VW == 8) Vec8<T>::load(src, v, C);
+        else { const float4 t = Vec4<T>::load(src, C); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 #pragma unroll
         for (int k = 0; k < VW; ++k) acc[k] = fmaf(w, v[k], acc[k]);
       }
     }
-    T* dst = y + (((int64_t)n * OH + oy) * OW + ox) * C + cv * VW;
+    T* dst = y + (((int64_t)n * OH + oy) * OW + ox) * (C * Elt<T>::kMul) + cv * VW;
     if (VW == 8) {
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = acc[k < VW ? k : 0];
-      Vec8<T>::store(dst, o);
+      Vec8<T>::store(dst, o, C);
     } else {
-      Vec4<T>::store(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      Vec4<T>::store(dst, make_float4(acc[0], acc[1], acc[2], acc[3]), C);
     }
   }
 }
@@ -591,7 +624,7 @@ __global__ void __launch_bounds__(256)
 fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W,
                   int C, int OH, int OW, int up_x, int up_y, int down_x, int down_y, int pad_x0,
                   int pad_y0, int KH, int KW, int64_t sn, int64_t sy, int64_t sx, int64_t sc,
-                  int64_t on, int64_t oyS, int64_t oxS, int64_t oc) {
+                  int64_t on, int64_t oyS, int64_t oxS, int64_t oc, int lo) {
   pdl_wait();
   const int64_t total = (int64_t)N * OH * OW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -613,10 +646,10 @@ fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int 
         const int ix = ux / up_x;
         if (ix >= W) continue;
         const float w = taps.k[(KH - 1 - ky) * KW + (KW - 1 - kx)];
-        acc = fmaf(w, to_f32<T>(x[n * sn + iy * sy + ix * sx + c * sc]), acc);
+        acc = fmaf(w, ld_elt<T>(x + n * sn + iy * sy + ix * sx + c * sc, lo), acc);
       }
     }
-    y[n * on + oy * oyS + ox * oxS + c * oc] = from_f32<T>(acc);
+    st_elt<T>(y + n * on + oy * oyS + ox * oxS + c * oc, acc, lo);
   }
 }
 
@@ -653,7 +686,7 @@ fir_up2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, 
         const int ix = qx + rx;
         if (ix < 0 || ix >= W) continue;
         float v[8];
-        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * C + cv * 8, v);
+        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * (C * Elt<T>::kMul) + cv * 8, v, C);
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const int ky = 2 * ry + 2 - dy;
@@ -673,8 +706,8 @@ fir_up2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, 
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx)
-        Vec8<T>::store(y + (((int64_t)n * 2 * H + 2 * qy + dy) * OW + 2 * qx + dx) * C + cv * 8,
-                       acc[dy * 2 + dx]);
+        Vec8<T>::store(y + (((int64_t)n * 2 * H + 2 * qy + dy) * OW + 2 * qx + dx) * (C * Elt<T>::kMul) + cv * 8,
+                       acc[dy * 2 + dx], C);
   }
 }
 
@@ -710,7 +743,7 @@ fir_down2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N
         const int ix = 4 * qx - 1 + c;
         if (ix < 0 || ix >= W) continue;
         float v[8];
-        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * C + cv * 8, v);
+        Vec8<T>::load(x + (((int64_t)n * H + iy) * W + ix) * (C * Elt<T>::kMul) + cv * 8, v, C);
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const int ky = r - 2 * dy;
@@ -730,8 +763,8 @@ fir_down2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx)
-        Vec8<T>::store(y + (((int64_t)n * OH + 2 * qy + dy) * OW + 2 * qx + dx) * C + cv * 8,
-                       acc[dy * 2 + dx]);
+        Vec8<T>::store(y + (((int64_t)n * OH + 2 * qy + dy) * OW + 2 * qx + dx) * (C * Elt<T>::kMul) + cv * 8,
+                       acc[dy * 2 + dx], C);
   }
 }
 
@@ -755,6 +788,9 @@ int run_fir(const psld_op& op, cudaStream_t s) {
     if (dt == PSLD_BF16)
       launch_pdl(fir_up2_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1,
                  (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C);
+    else if (dt == PSLD_BF16S)
+      launch_pdl(fir_up2_kernel<bf16s>, dim3(grid), dim3(256), 0, s, 1, (const bf16s*)op.in[0],
+                 (bf16s*)op.out[0], taps, N, H, W, C);
     else
       launch_pdl(fir_up2_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
                  (float*)op.out[0], taps, N, H, W, C);
@@ -764,6 +800,9 @@ int run_fir(const psld_op& op, cudaStream_t s) {
     if (dt == PSLD_BF16)
       launch_pdl(fir_down2_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1,
                  (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C);
+    else if (dt == PSLD_BF16S)
+      launch_pdl(fir_down2_kernel<bf16s>, dim3(grid), dim3(256), 0, s, 1, (const bf16s*)op.in[0],
+                 (bf16s*)op.out[0], taps, N, H, W, C);
     else
       launch_pdl(fir_down2_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0],
                  (float*)op.out[0], taps, N, H, W, C);
@@ -781,21 +820,27 @@ int run_fir(const psld_op& op, cudaStream_t s) {
     else FIR_LAUNCH2(T, VW, 0, 0);                                 \
   } while (0)
     if (dt == PSLD_BF16) { if (vw == 8) FIR_LAUNCH(__nv_bfloat16, 8); else FIR_LAUNCH(__nv_bfloat16, 4); }
+    else if (dt == PSLD_BF16S) { if (vw == 8) FIR_LAUNCH(bf16s, 8); else FIR_LAUNCH(bf16s, 4); }
     else { if (vw == 8) FIR_LAUNCH(float, 8); else FIR_LAUNCH(float, 4); }
 #undef FIR_LAUNCH
 #undef FIR_LAUNCH2
   } else {
     const int grid = ew_grid((int64_t)N * OH * OW * C);
-    const int64_t sn = (int64_t)H * W * C, sy = (int64_t)W * C, sx = C, sc = 1;
-    const int64_t on = (int64_t)OH * OW * C, oyS = (int64_t)OW * C, oxS = C, oc = 1;
+    const int64_t rs = dt == PSLD_BF16S ? 2 * C : C;      // pixel row stride in elements
+    const int64_t sn = (int64_t)H * W * rs, sy = (int64_t)W * rs, sx = rs, sc = 1;
+    const int64_t on = (int64_t)OH * OW * rs, oyS = (int64_t)OW * rs, oxS = rs, oc = 1;
     if (dt == PSLD_BF16)
       launch_pdl(fir_scalar_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 1, 
           (const __nv_bfloat16*)op.in[0], (__nv_bfloat16*)op.out[0], taps, N, H, W, C, OH, OW, up,
-          up, down, down, pad0, pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc);
+          up, down, down, pad0, pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc, C);
+    else if (dt == PSLD_BF16S)
+      launch_pdl(fir_scalar_kernel<bf16s>, dim3(grid), dim3(256), 0, s, 1, (const bf16s*)op.in[0],
+                 (bf16s*)op.out[0], taps, N, H, W, C, OH, OW, up, up, down, down, pad0, pad0, KH, KH,
+                 sn, sy, sx, sc, on, oyS, oxS, oc, C);
     else
       launch_pdl(fir_scalar_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)op.in[0], (float*)op.out[0], taps,
                                                   N, H, W, C, OH, OW, up, up, down, down, pad0,
-                                                  pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc);
+                                                  pad0, KH, KH, sn, sy, sx, sc, on, oyS, oxS, oc, C);
   }
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
@@ -823,7 +868,7 @@ extern "C" int psld_upfirdn2d(const float* input, float* output, const float* ta
   // planes-as-batch, C = 1, contiguous W
   launch_pdl(fir_scalar_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, 
       input, output, taps, (int)planes, in_h, in_w, 1, OH, OW, up_x, up_y, down_x, down_y, pad_x0,
-      pad_y0, kh, kw, (int64_t)in_h * in_w, in_w, 1, 0, (int64_t)OH * OW, OW, 1, 0);
+      pad_y0, kh, kw, (int64_t)in_h * in_w, in_w, 1, 0, (int64_t)OH * OW, OW, 1, 0, 0);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

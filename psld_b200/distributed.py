@@ -38,6 +38,44 @@ def rank_seed(seed: int, rank: int) -> int:
     return int(seed) + int(rank)
 
 
+def current_rank() -> int:
+    """Global rank of this process AT CALL TIME: ``torch.distributed`` when initialised (Lightning's
+    DDP launcher initialises it but exports only LOCAL_RANK / NODE_RANK / WORLD_SIZE to the children,
+    not RANK), else RANK, else NODE_RANK x local world + LOCAL_RANK, else 0."""
+    if dist.is_available() and dist.is_initialized():
+        return int(dist.get_rank())
+    if "RANK" in os.environ:
+        return int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    node = int(os.environ.get("NODE_RANK", os.environ.get("GROUP_RANK", "0")))
+    per_node = int(os.environ.get("LOCAL_WORLD_SIZE", "0")) or 1
+    return node * per_node + local
+
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def call_seed(seed: int, rank: int, call: int) -> int:
+    """64-bit Philox key of the ``call``-th ``sample()`` of a sampler on ``rank``.
+
+    The reference draws its noise from the global torch generator, seeded once per process with
+    ``seed + global_rank`` (wrapper.py:93-99) and ADVANCING from batch to batch, so every
+    ``predict_step`` sees fresh noise.  A counter-based generator has no state to advance: the key
+    must change per call or every batch would reuse the same injected noise.  Deterministic in
+    (seed, rank, call); call 0 of rank r keeps the reference's ``seed + r`` key."""
+    base = rank_seed(seed, rank) & _M64
+    if call == 0:
+        return base
+    return _splitmix64(base ^ _splitmix64(int(call) & _M64))
+
+
 def gather_samples(u_local: torch.Tensor, n_total: int | None = None, group=None):
     """All-gathers the position half x of the local states ``[b, 2C, H, W]`` -> ``[B, C, H, W]``
     (the momentum half is dropped exactly like the reference's image writer does,

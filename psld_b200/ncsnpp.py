@@ -30,6 +30,13 @@ from . import _lib as L
 
 _SQRT1_2 = float(1.0 / np.sqrt(2.0))
 
+# Precision tiers of the contractions (convolutions, NIN, attention):
+#   "bf16x3"  split-bf16 operands, three tcgen05 MMAs per product (a_hi w_hi + a_hi w_lo + a_lo w_hi),
+#             fp32 accumulation, split-bf16 activations: fp32-tolerance results on the tensor cores
+#   "bf16"    bf16 operands and activations, fp32 accumulation (throughput tier, ~1e-2 per forward)
+#   "fp32"    true fp32 FFMA on the CUDA cores (reference-faithful arithmetic)
+PRECISIONS = ("fp32", "bf16", "bf16x3")
+
 
 # ----------------------------------------------------------------------------------------
 # Parameter containers (names/shapes = reference state-dict contract)
@@ -167,7 +174,7 @@ class NCSNpp(nn.Module):
         dropout = float(sf.dropout)
         prec = getattr(sf, "precision", None) if not isinstance(sf, dict) else sf.get("precision")
         self.precision = str(prec or os.environ.get("PSLD_B200_PRECISION", "bf16")).lower()
-        assert self.precision in ("fp32", "bf16")
+        assert self.precision in PRECISIONS, self.precision
 
         mods = []
         if self.embedding_type == "fourier":
@@ -250,19 +257,36 @@ class NCSNpp(nn.Module):
         return new
 
     def set_precision(self, precision: str):
-        assert precision in ("fp32", "bf16")
+        assert precision in PRECISIONS, precision
         if precision != self.precision:
             self.precision = precision
             self._drop_plans()
         return self
 
     # -- public call surface -----------------------------------------------------------
+    def _fingerprint(self):
+        """Cheap identity of the live parameter values: (storage pointer, in-place version counter)
+        of every parameter.  Plans hold RE-PACKED copies of the weights (bf16 K-major, concatenated
+        Dense_0, fused biases); an in-place update (``p.data.copy_``, an EMA step, an optimizer
+        step, ``nn.init``) bumps ``_version`` and a re-assignment changes the pointer, so a stale
+        plan is detected and rebuilt instead of silently running with old weights."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate(self):
+        """Drop every compiled plan (they are rebuilt, with re-packed weights, on next use)."""
+        self._drop_plans()
+
     def plan(self, batch: int, nt: int, logged: bool):
         key = (int(batch), int(nt), bool(logged), self.precision)
         p = self._plans.get(key)
+        fp = self._fingerprint()
+        if p is not None and p.fingerprint != fp:
+            p.release()
+            p = None
         if p is None:
             from .program import build_plan
             p = build_plan(self, batch, nt, logged)
+            p.fingerprint = fp
             self._plans[key] = p
         return p
 

@@ -53,8 +53,13 @@ class Plan:
         if self.dev.type != "cuda" and not self.dry:
             raise RuntimeError("psld_b200: parameters must be on a CUDA device (no CPU path)")
         self.bf16 = net.precision == "bf16"
+        # "bf16x3": split-bf16 activations / weights (value = hi + lo, [C hi | C lo] pixel rows = 4
+        # bytes per element, so the buffers are ALLOCATED as float32 of the logical shape) and
+        # three tcgen05 MMA groups per k-block: fp32-tolerance results on the tensor cores
+        self.x3 = net.precision == "bf16x3"
+        self.tc = self.bf16 or self.x3
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
-        self.acode = L.BF16 if self.bf16 else L.F32
+        self.acode = L.BF16 if self.bf16 else (L.BF16S if self.x3 else L.F32)
         self.keep = []          # tensors referenced by raw pointers
         self.ops = []
         self.pool = {}
@@ -103,7 +108,7 @@ class Plan:
 
     def _ext_fusable(self, b, e1, e2, cout):
         """Can Conv_2 (1x1 shortcut over e = cat(e1, e2)) ride along Conv_1's MMA stream?"""
-        if not self.bf16 or not self.fuse_shortcut:
+        if not self.tc or not self.fuse_shortcut:
             return False
         N, H, W, Cb = b.shape
         E1 = e1.shape[-1]
@@ -182,7 +187,7 @@ class Plan:
         else:
             y = self._acquire(*x1.shape[:-1], Cc)
         # stats pass: ~64 KB of input per CTA, but enough CTAs to fill 148 SMs at small batch
-        per_img = HW * Cc * (2 if self.bf16 else 4)
+        per_img = HW * Cc * (2 if self.bf16 else 4)      # (split bf16 = 4 bytes per element too)
         nchunk = max(-(-per_img // 65536), -(-592 // self.B))
         nchunk = int(max(1, min(nchunk, max(1, HW // 32))))
         op = self._op(L.OP_GN)
@@ -318,7 +323,7 @@ class Plan:
                 self.mg[out.data_ptr()] = mg
             self.engine_count["tc_gn"] = self.engine_count.get("tc_gn", 0) + 1
             done = True
-        elif self.bf16 and allow_tc and not in_nchw:
+        elif self.tc and allow_tc and not in_nchw:
             op.engine = L.ENGINE_TC
             cout_pad = Cout
             if out_nchw_f32 and Cout % 32:
@@ -342,6 +347,9 @@ class Plan:
                 if b32 is not None:
                     b32 = self._w(torch.cat([b32, b32.new_zeros(cout_pad - Cout)]))
                     op.inp[5] = b32.data_ptr()
+            if self.x3:      # weight planes [2][Cout, K]: hi = rn(w), lo = rn(w - hi)
+                hi = wt.to(torch.bfloat16)
+                wt = torch.cat([hi, (wt - hi.to(torch.float32)).to(torch.bfloat16)], 0)
             wt = self._w(wt, torch.bfloat16)
             op.inp[4] = wt.data_ptr()
             i[L.CONV_COUT] = cout_pad
@@ -385,9 +393,11 @@ class Plan:
         ks = i[L.CONV_KS]
         same = i[L.CONV_STRIDE] == 1 and ks in (1, 3) and i[L.CONV_PAD] == ks // 2
         down2 = i[L.CONV_STRIDE] == 2 and i[L.CONV_PAD] == 0 and ks == 3 and i[L.CONV_C2] == 0
-        ok = (i[L.CONV_IN_DTYPE] == L.BF16 and i[L.CONV_IN_LAYOUT] == L.NHWC and (same or down2)
+        ok = (i[L.CONV_IN_DTYPE] in (L.BF16, L.BF16S) and i[L.CONV_IN_LAYOUT] == L.NHWC and (same or down2)
               and i[L.CONV_C1] % 64 == 0 and i[L.CONV_C2] % 64 == 0 and i[L.CONV_COUT] % 32 == 0
               and pow2(i[L.CONV_OW]) and pow2(i[L.CONV_OH]) and 4 <= i[L.CONV_OW] <= 128)
+        if i[L.CONV_IN_DTYPE] == L.BF16S and i[L.CONV_OUT_LAYOUT] == L.NHWC:
+            ok = ok and (i[L.CONV_OH] * i[L.CONV_OW]) % 32 == 0
         return L.OK if ok else L.EUNSUPPORTED
 
     def op_attn(self, qkv, HW, Cc, proj=None):
@@ -592,7 +602,7 @@ class Plan:
         # ---- input: NCHW fp32 -> NHWC activations
         # bf16 plans zero-pad the 6 input channels to 64 so that the input conv and the first
         # pyramid conv are tensor-core eligible (K chunks are 64 channels)
-        cpad = 64 if (self.bf16 and net.in_ch < 64) else net.in_ch
+        cpad = 64 if (self.tc and net.in_ch < 64) else net.in_ch
         if cpad > net.in_ch:     # padding channels: zeroed once here, never written again
             x = torch.zeros(B, H, H, cpad, dtype=self.adt, device=self.dev)
             self.keep.append(x)

@@ -15,7 +15,9 @@ Two execution paths, both on the GPU, neither with a CPU/eager fallback for the 
 
 Noise: ``sampler.noise`` may hold pre-drawn N(0,1) tensors ``[draws,B,2C,H,W]`` (fp32) in the
 reference's ``randn_like`` draw order for parity runs; otherwise the kernels
-draw from Philox4x32-10 (seed = ``config.evaluation.seed`` + rank, cf. wrapper.py:93-99).
+draw from Philox4x32-10; the key is a function of (``config.evaluation.seed``, global rank at call
+time, index of the ``sample()`` call on this sampler): every call gets fresh noise, like the
+reference's advancing torch generator seeded with seed + rank (wrapper.py:93-99).
 """
 from __future__ import annotations
 
@@ -26,6 +28,7 @@ import os
 import torch
 
 from . import _lib as L
+from .distributed import call_seed, current_rank
 from .ncsnpp import NCSNpp
 from .registry import register_module
 from .schedule import InpaintTables, PSLDSchedule, StepTables, VPSchedule, VPStepTables
@@ -88,7 +91,9 @@ class _FusedSampler(Sampler):
         self.fuse_halves = bool(_opt(config, "fuse_halves", True))
         self.merge_noise = bool(_opt(config, "merge_noise", True))   # Philox mode only
         self.use_graph = bool(_opt(config, "cuda_graph", True))       # replay one captured step
-        self.seed = int(getattr(config.evaluation, "seed", 0)) + int(os.environ.get("RANK", "0"))
+        self.base_seed = int(getattr(config.evaluation, "seed", 0))
+        self.calls = 0             # sample() calls so far: folded into the Philox key
+        self.seed = call_seed(self.base_seed, current_rank(), 0)
         self.noise = None          # optional pre-drawn noise bank (parity mode)
         self.record = None         # optional [n, B,2C,H,W] buffer filled with per-step states
         self.nfe = 0
@@ -99,6 +104,12 @@ class _FusedSampler(Sampler):
 
     def _embedding(self):
         return getattr(self.score_fn, "embedding_type", "fourier")
+
+    def _next_seed(self):
+        """Philox key of THIS sample() call (rank resolved now, call counter advanced)."""
+        self.seed = call_seed(self.base_seed, current_rank(), self.calls)
+        self.calls += 1
+        return self.seed
 
     def _sample_vp(self, batch, ts, n, denoise, eps):
         """Euler-Maruyama on the VP-SDE (state [B,C,H,W]): score_fn + one fused update per step."""
@@ -149,6 +160,7 @@ class _FusedSampler(Sampler):
         lib = L.lib()
         n = int(n_discrete_steps)
         self.nfe = n
+        self._next_seed()
         if self.vp is not None:
             return self._sample_vp(batch, ts, n, denoise, eps)
         native = isinstance(self.score_fn, NCSNpp)
@@ -331,6 +343,7 @@ class InpaintEulerMaruyamaSampler(_FusedSampler):
         x_0, mask = batch
         n = int(n_discrete_steps)
         self.nfe = n
+        self._next_seed()
         if isinstance(self.score_fn, NCSNpp):
             dev = next(self.score_fn.parameters()).device
         else:

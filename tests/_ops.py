@@ -9,8 +9,37 @@ import torch
 from psld_b200 import _lib as L
 
 
+class Split(torch.Tensor):
+    """Marker subclass: a float32-typed tensor whose BYTES are split bf16 ([C hi | C lo] per pixel
+    row, include/psld_b200.h PSLD_BF16S); its logical shape is the float32 shape."""
+
+
+def to_split(x):
+    """fp32 [..., C] -> split-bf16 storage (returned as a float32-typed ``Split`` of the same shape)."""
+    x = x.to(torch.float32)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.cat([hi, lo], -1).contiguous().view(torch.float32).as_subclass(Split)
+
+
+def from_split(t):
+    """split-bf16 storage -> fp32 values (hi + lo)."""
+    b = t.as_subclass(torch.Tensor).contiguous().view(torch.bfloat16)
+    Cc = b.shape[-1] // 2
+    return b[..., :Cc].to(torch.float32) + b[..., Cc:].to(torch.float32)
+
+
+def split_like(shape, device):
+    return torch.full(shape, float("nan"), dtype=torch.float32, device=device).as_subclass(Split)
+
+
+def val(t):
+    """Logical fp32/fp64-able values of a tensor in any activation format."""
+    return from_split(t) if isinstance(t, Split) else t.as_subclass(torch.Tensor)
+
+
 def code(t):
-    return L.dtype_code(t.dtype)
+    return L.BF16S if isinstance(t, Split) else L.dtype_code(t.dtype)
 
 
 def run_op(op, prepare=False):
@@ -70,6 +99,9 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
             i[L.CONV_EXT_C1] = e1.shape[-1]
             i[L.CONV_EXT_C2] = e2.shape[-1] if e2 is not None else 0
             keep += [e1, e2]
+        if isinstance(x1, Split):      # weight planes [2][Cout, K]
+            hi = wt.to(torch.bfloat16)
+            wt = torch.cat([hi.to(torch.float32), wt - hi.to(torch.float32)], 0)
         wp = wt.to(torch.bfloat16).contiguous()
         i[L.CONV_COUT] = cout_k
         op.f[1] = float(Cout)
@@ -81,6 +113,8 @@ def conv_op(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=Non
             out = torch.full((N, Cout, OH, OW), float("nan"), dtype=torch.float32, device=dev)
         else:
             out = torch.full((N, OH, OW, Cout), float("nan"), dtype=x1.dtype, device=dev)
+            if isinstance(x1, Split):
+                out = out.as_subclass(Split)
     op.inp[0] = x1.data_ptr()
     op.inp[1] = x2.data_ptr() if x2 is not None else None
     op.inp[2] = residual.data_ptr() if residual is not None else None
@@ -105,6 +139,7 @@ def conv_ref(x1, x2, w_oihw, bias, *, stride=1, pad=None, residual=None, temb=No
     import torch.nn.functional as F
     ks = w_oihw.shape[-1]
     pad = ks // 2 if pad is None else pad
+    x1, x2, residual = val(x1), (val(x2) if x2 is not None else None), (val(residual) if residual is not None else None)
     xx = x1.double().cpu() if x2 is None else torch.cat([x1.double().cpu(), x2.double().cpu()], -1)
     y = F.conv2d(xx.permute(0, 3, 1, 2), w_oihw.double().cpu(),
                  bias.double().cpu() if bias is not None else None, stride=stride, padding=pad)
@@ -131,6 +166,8 @@ def gn_op(x1, x2, gamma, beta, G, silu, eps=1e-6, nchunk=4, out_dtype=None, mg1=
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     out = torch.full((*x1.shape[:-1], C1 + C2), float("nan"), dtype=out_dtype or x1.dtype, device=x1.device)
+    if isinstance(x1, Split):
+        out = out.as_subclass(Split)
     scratch = torch.zeros(N * nchunk * G * 2 + 16, dtype=torch.float64, device=x1.device)
     op = L.Op()
     op.kind = L.OP_GN
@@ -153,6 +190,8 @@ def fir_op(x, taps, up, down, pad0, pad1):
     OH = (H * up + pad0 + pad1 - KH) // down + 1
     OW = (W * up + pad0 + pad1 - KH) // down + 1
     out = torch.full((N, OH, OW, Cc), float("nan"), dtype=x.dtype, device=x.device)
+    if isinstance(x, Split):
+        out = out.as_subclass(Split)
     op = L.Op()
     op.kind = L.OP_FIR
     i = op.i
@@ -171,6 +210,8 @@ def attn_op(qkv, Cc, engine=L.ENGINE_SIMT, proj=None):
     N = qkv.shape[0]
     HW = int(np.prod(qkv.shape[1:-1]))
     out = torch.full((*qkv.shape[:-1], Cc), float("nan"), dtype=qkv.dtype, device=qkv.device)
+    if isinstance(qkv, Split):
+        out = out.as_subclass(Split)
     op = L.Op()
     op.kind, op.engine = L.OP_ATTN, engine
     op.i[L.ATTN_N], op.i[L.ATTN_HW], op.i[L.ATTN_C], op.i[L.ATTN_DTYPE] = N, HW, Cc, code(qkv)
@@ -190,10 +231,10 @@ def attn_op(qkv, Cc, engine=L.ENGINE_SIMT, proj=None):
 
 
 def rel_l2(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = val(a).double().cpu(), val(b).double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
 
 
 def max_rel(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = val(a).double().cpu(), val(b).double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))

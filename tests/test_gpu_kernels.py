@@ -166,6 +166,57 @@ def test_philox_noise_and_prior():
     assert abs(float((ox * om).mean()) - (-0.21)) < 0.01
 
 
+def test_philox_normal_quality():
+    """The in-kernel generator (Philox4x32-10 + Box-Muller) that produces every noise sample of a
+    throughput run, on 2.5e7 draws per stream: Kolmogorov-Smirnov distance against N(0,1), moments
+    up to the 6th, tail mass beyond 3/4/5 sigma, and independence between step streams, between
+    the x and m halves, between neighbouring elements and between seeds."""
+    from math import erfc, sqrt
+    lib = L.lib()
+    B, chw = 4096, 3072
+    n = B * chw * 2                                     # 2.5e7 normals per launch
+    co = L.SscsCoeffs()
+    co.half_a.c11, co.half_a.c22 = 1.0, 1.0             # u = z: a pure-noise half step
+    z0 = torch.zeros(B, 6, 32, 32, dtype=torch.float32, device=DEV)
+
+    def draw(seed, step):
+        out = torch.empty_like(z0)
+        L.check(lib.psld_sscs_update(L.ptr(out), L.ptr(z0), L.F32, None, None, None, None, None,
+                                     C.byref(co), 1, seed, step, B, chw, L.stream_ptr()), "sscs")
+        return out
+
+    a = draw(2024, 0)
+    v = a.double().flatten()
+    # moments: E z^k = 0, 1, 0, 3, 0, 15 with standard errors sqrt(Var(z^k) / n)
+    se = {1: 1.0, 2: sqrt(2.0), 3: sqrt(15.0), 4: sqrt(96.0), 5: sqrt(945.0), 6: sqrt(10170.0)}
+    want = {1: 0.0, 2: 1.0, 3: 0.0, 4: 3.0, 5: 0.0, 6: 15.0}
+    for k in range(1, 7):
+        mk = float((v ** k).mean())
+        assert abs(mk - want[k]) <= 5.0 * se[k] / sqrt(n), (k, mk)
+    # KS distance on a 4e6 subsample (stride keeps every stream position): D_crit(1e-3) = 1.95/sqrt(m)
+    sub = v[::6].sort().values.cpu()
+    m = sub.numel()
+    cdf = 0.5 * (1.0 + torch.erf(sub / sqrt(2.0)))
+    i = torch.arange(1, m + 1, dtype=torch.float64)
+    D = float(torch.max(torch.max(i / m - cdf), torch.max(cdf - (i - 1) / m)))
+    assert D <= 1.95 / sqrt(m), D
+    # tails: two-sided mass beyond k sigma, binomial 5-sigma band
+    for k in (3.0, 4.0, 5.0):
+        p = erfc(k / sqrt(2.0))
+        cnt = float((v.abs() > k).sum())
+        assert abs(cnt - n * p) <= 5.0 * sqrt(n * p) + 1.0, (k, cnt, n * p)
+    assert float(v.abs().max()) < 6.8
+    # independence: correlation of two standard normals over n pairs has std 1/sqrt(n)
+    lim = 5.0 / sqrt(n)
+    b = draw(2024, 1).double().flatten()                 # next step's stream
+    c = draw(2025, 0).double().flatten()                 # another seed
+    assert abs(float((v * b).mean())) <= lim and abs(float((v * c).mean())) <= lim
+    x, mm = torch.chunk(a.double(), 2, 1)
+    assert abs(float((x * mm).mean())) <= lim * sqrt(2.0)
+    assert abs(float((v[1:] * v[:-1]).mean())) <= lim    # neighbours (same Philox counter block)
+    assert abs(float((v[4:] * v[:-4]).mean())) <= lim
+
+
 # ------------------------------------------------------------------ GroupNorm
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 0), (3, 8, 8, 256, 128), (2, 32, 32, 32, 64),

@@ -84,6 +84,26 @@ def test_module_contract():
         net(x.cpu(), t.cpu())
 
 
+def test_in_place_weight_update_invalidates_plans():
+    """A plan snapshots re-packed weights; an in-place parameter update (EMA / optimizer step /
+    ``p.data.copy_``) must be picked up by the next call, as the reference module would."""
+    cfg = tiny_config()
+    net, sd = make_net(cfg, "bf16")
+    x = torch.randn(2, 6, 32, 32, device="cuda")
+    t = torch.tensor([0.5, 0.2], device="cuda")
+    y0 = net(x, t).clone()
+    assert torch.equal(net(x, t), y0)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 4:
+                p.mul_(1.05)                       # in place: same storage, new version
+    y1 = net(x, t).clone()
+    assert not torch.equal(y1, y0)
+    twin, _ = make_net(cfg, "bf16")
+    twin.load_state_dict(net.state_dict())
+    assert torch.equal(twin(x, t), y1)
+
+
 @pytest.mark.parametrize("sf,B,precision,tol", [
     (dict(nf=96, ch_mult=[1, 2], num_res_blocks=1), 3, "bf16", 3e-2),     # channels 96/192/288: SIMT fallbacks, odd group sizes
     (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 5, "bf16", 3e-2),  # 8x8 level, 2 images per tile, odd batch

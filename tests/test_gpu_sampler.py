@@ -156,6 +156,29 @@ def test_philox_mode_runs_and_is_reproducible():
     assert torch.isfinite(m1).all() and torch.equal(m1, m2)
 
 
+def test_consecutive_sample_calls_draw_fresh_noise():
+    """One sampler instance serves every dataloader batch of a run (reference wrapper.py:101-122):
+    each sample() call must inject different noise (the reference's torch generator advances), while
+    a given (seed, rank, call index) stays reproducible."""
+    cfg = tiny_config(sampler="sscs_sde", n_discrete_steps=6)
+    net, _ = make_net(cfg, "bf16")
+    u0, _ = sampler_inputs(cfg, 4, 5, "sscs_sde")
+    ts, n = time_grid(cfg)
+    for kind in ("sscs_sde", "em_sde"):
+        S = SAMPLERS[kind](cfg, PSLD(cfg), net)
+        S.state_dtype = torch.float32
+        outs = [S.sample(u0.cuda(), ts.cuda(), n).clone() for _ in range(3)]
+        assert S.calls == 3
+        for i in range(3):
+            for j in range(i + 1, 3):
+                d = (outs[i] - outs[j]).abs().max().item()
+                assert d > 1e-3, (kind, i, j, d)
+        S2 = SAMPLERS[kind](cfg, PSLD(cfg), net)
+        S2.state_dtype = torch.float32
+        S2.calls = 2
+        assert torch.equal(S2.sample(u0.cuda(), ts.cuda(), n), outs[2])
+
+
 def test_merged_noise_is_exact_in_law():
     """Merging half B of step i with half A of step i+1 into one draw keeps the law of the chain:
     with a zero score network the end state is Gaussian with a known 2x2 covariance per pair."""
@@ -246,8 +269,10 @@ def test_inpaint_sampler_philox_keeps_known_region():
     x_0, mask = inpaint_inputs(4, 8, 5)
     S = InpaintEulerMaruyamaSampler(cfg, sde, fake_score)
     a = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()
-    b = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()
-    assert torch.equal(a, b) and torch.isfinite(a).all()
+    c = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()      # next call: fresh prior and noise
+    S.calls = 0
+    b = S.sample((x_0.cuda(), mask.cuda()), ts, n).cpu()      # same (seed, rank, call) -> same draws
+    assert torch.equal(a, b) and torch.isfinite(a).all() and not torch.equal(a, c)
     s = O.PSLDScalars(cfg)
     axx = O.mean_coeffs(s, float(np.float32(1.0) - np.float32(1.0 - cfg.evaluation.eval_eps)))[0]
     known = mask == 1
@@ -302,8 +327,10 @@ def test_vp_sampler_with_network_vs_oracle():
     assert e <= 1e-5
     # Philox noise: reproducible and finite
     S.noise = None
-    a, b = S.sample(x0.cuda(), ts, n), S.sample(x0.cuda(), ts, n)
-    assert torch.equal(a, b) and torch.isfinite(a).all()
+    a, c = S.sample(x0.cuda(), ts, n), S.sample(x0.cuda(), ts, n)
+    S.calls -= 2
+    b = S.sample(x0.cuda(), ts, n)
+    assert torch.equal(a, b) and torch.isfinite(a).all() and not torch.equal(a, c)
 
 
 def test_native_sampler_celeba64_vs_oracle():

@@ -183,3 +183,24 @@ def test_inpaint_and_vp_tables_vs_oracle():
     den = tab.steps[n]
     assert den.gs == 0.0 and den.dt == float(np.float32(cfg.evaluation.eval_eps))
     assert tab.tau32.numel() == n + 1
+
+
+def test_call_seed_per_call_and_rank(monkeypatch):
+    """Philox key derivation (psld_b200/distributed.py): call 0 keeps the reference's seed + rank
+    (wrapper.py:93-99); later calls and other ranks get distinct 64-bit keys; the rank is resolved
+    at call time from RANK, else NODE_RANK/LOCAL_RANK (Lightning's launcher does not export RANK)."""
+    from psld_b200.distributed import call_seed, current_rank
+    assert call_seed(7, 0, 0) == 7 and call_seed(7, 3, 0) == 10
+    keys = {call_seed(7, r, c) for r in range(8) for c in range(64)}
+    assert len(keys) == 8 * 64 and all(0 <= k < 2 ** 64 for k in keys)
+    assert call_seed(7, 1, 5) == call_seed(7, 1, 5)
+    for k in ("RANK", "LOCAL_RANK", "NODE_RANK", "GROUP_RANK", "LOCAL_WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    assert current_rank() == 0
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    assert current_rank() == 3
+    monkeypatch.setenv("NODE_RANK", "1")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert current_rank() == 11
+    monkeypatch.setenv("RANK", "5")
+    assert current_rank() == 5
