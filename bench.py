@@ -54,7 +54,13 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = workload default")
     ap.add_argument("--workload", default="cifar10", choices=["cifar10", "celeba64"],
                     help="cifar10 = BASELINE configs[1] (headline); celeba64 = configs[3]")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
+    ap.add_argument("--batch-total", type=int, default=0,
+                    help="fixed TOTAL batch sharded over the GPUs (strong scaling; BASELINE configs[2]: 2048, "
+                         "configs[3]: 512); overrides --batch")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
+                    help="tier on the main line (the other tensor-core tier is reported as <tier>_path)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other tensor-core tier")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager GPU context baseline")
     ap.add_argument("--state", default="float32", choices=["float32", "float64"])
     ap.add_argument("--e2e-nfe", type=int, default=NFE, help="0 disables the end-to-end run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,48 +195,35 @@ def main_reference(args):
 
 
 # ======================================================================== B200 arm
-def main_b200(args):
+TIER_DTYPE = {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}
+TIER_NOTE = {
+    "bf16x3": "fp32-tolerance tier: split-bf16 operands, three tcgen05 MMAs per product, fp32 accumulation",
+    "bf16": "throughput tier: bf16 operands and activations, fp32 accumulation (~5e-3 trajectory error)",
+    "fp32": "true fp32 FFMA on the CUDA cores",
+}
+
+
+def measure_tier(args, precision, ctx):
+    """Device-timed steps + per-op roofline + (optionally) the end-to-end run of ONE precision tier."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from psld_b200 import NCSNpp, PSLD, SSCSSampler, time_grid
+    from psld_b200 import SSCSSampler, time_grid
     from psld_b200 import _lib as L
-    from psld_b200.distributed import env_rank, gather_samples, max_over_ranks
+    from psld_b200.distributed import gather_samples, max_over_ranks
     from psld_b200.profiling import profile_plan
     from psld_b200.schedule import StepTables
-    import ctypes as C
 
-    rank, world, local = env_rank()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    pk = peaks()
-    import psld_b200
-    cfg_name, flop_per_sample_nfe, default_batch, workload_desc = WORKLOADS[args.workload]
-    make_cfg = getattr(psld_b200, cfg_name)
-    if args.batch <= 0:
-        args.batch = default_batch
-    cfg = make_cfg(batch_size=args.batch, n_samples=args.batch * world)
-    cfg.evaluation.sampler["state_dtype"] = args.state
-    torch.manual_seed(1234)
-    net = NCSNpp(cfg).eval().set_precision(args.precision).to(dev)   # random-init weights
-    sde = PSLD(cfg)
-    S = SSCSSampler(cfg, sde, net)
-    B = args.batch
-    H = cfg.data.image_size
-    chw = 3 * H * H
-    ts, n = time_grid(cfg)
+    net, sde, cfg, dev, rank, world, local, pk = (ctx[k] for k in
+                                                  ("net", "sde", "cfg", "dev", "rank", "world", "local", "pk"))
+    B, H, chw, ts = ctx["B"], ctx["H"], ctx["chw"], ctx["ts"]
+    net.set_precision(precision)
     plan = net.plan(B, 1, True)
     lib = L.lib()
-    stream = L.stream_ptr(dev)
-
-    # ---- device-resident loop pieces: K predictor steps of the real 1000-step schedule
     state_dtype = torch.float32 if args.state == "float32" else torch.float64
     state = sde.prior_sampling_device((B, 3, H, H), seed=1 + rank, device=dev).to(state_dtype)
     plan.x_in.copy_(state)
-
-    side = torch.cuda.Stream(dev)          # CUDA-graph capture needs a non-default stream
+    side = ctx["side"]
 
     def run_steps(first, count):
         tabs = StepTables(sde, ts[first:first + count + 1], count, "sscs_sde", False, 1e-3,
@@ -277,54 +270,59 @@ def main_b200(args):
     launches = 1 + args.steps * (plan.launches + 1 + (1 if args.graph else 0))
     finite = bool(torch.isfinite(state).all().item())
 
-    # ---- per-kernel roofline from CUDA-event timing of every op
+    # ---- per-kernel roofline: per-op CUDA-event times give every kernel's SHARE of a step; the
+    # achieved rate is the algorithmic work over (share x the graph-replayed step time), so it can
+    # never exceed what the driver-checked step time allows
     prof = profile_plan(plan, iters=max(1, args.profile_ops)) if args.profile_ops > 0 else {}
     conv_classes = prof.pop("_conv_classes", {})
     roof = None
+    total_ms = sum(v["ms"] for v in prof.values()) if prof else 0.0
     tc_names = [k for k in ("conv_tc", "conv_tc_gn") if k in prof]
+    mult = 3 if precision == "bf16x3" else 1       # bf16 MMAs executed per algorithmic product
     if tc_names:
-        # the tcgen05 implicit-GEMM convolution family (plain + GroupNorm-on-load variant)
-        c = {"flops": sum(prof[k]["flops"] for k in tc_names), "ms": sum(prof[k]["ms"] for k in tc_names),
-             "n": sum(prof[k]["n"] for k in tc_names)}
-        c["launch_ms"] = c["ms"] / c["n"]
-        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        flops = sum(prof[k]["flops"] for k in tc_names)         # algorithmic, zero padding excluded
+        ev_ms = sum(prof[k]["ms"] for k in tc_names)
+        nl = sum(prof[k]["n"] for k in tc_names)
+        share = ev_ms / total_ms
+        ms_in_step = share * ms_per_step
+        ach = flops / (ms_in_step * 1e-3) / 1e12
         traffic, tsrc = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and B == 256 and args.workload == "cifar10":
-            tj = json.load(open(tp))
-            ks = [tj["kernels"][k] for k in ("conv_tc_kernel", "conv_gn_tc_kernel") if k in tj["kernels"]]
+            tj = json.load(open(tp)).get(precision, {})
+            ks = [tj["kernels"][k] for k in ("conv_tc_kernel", "conv_gn_tc_kernel") if k in tj.get("kernels", {})]
             if ks:
                 traffic = sum(k["traffic_bytes_per_launch"] * k["launches"] for k in ks) / sum(k["launches"] for k in ks)
                 tsrc = tj["source"]
         roof = {"bound": "tensor",
-                "kernel": "conv_tc_kernel + conv_gn_tc_kernel (tcgen05 implicit-GEMM convolutions, bf16)",
+                "kernel": "conv_tc_kernel" + (" + conv_gn_tc_kernel" if "conv_tc_gn" in prof else "") +
+                          " (tcgen05 implicit-GEMM convolutions, " + TIER_DTYPE[precision] + ")",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": traffic,
-                "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
-                "traffic_source": tsrc, "algorithmic_flop_per_launch": c["flops"] / c["n"],
-                "peak_source": pk["src"] + ", sustained",
-                "launches_per_step": c["n"], "avg_launch_ms": c["launch_ms"],
-                "share_of_step": c["ms"] / sum(v["ms"] for v in prof.values()),
+                "frac": ach / pk["tf_sustained"],
+                "executed_mma_per_product": mult, "achieved_executed": ach * mult,
+                "frac_executed": ach * mult / pk["tf_sustained"],
+                "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                "traffic_source": tsrc, "algorithmic_flop_per_launch": flops / nl,
+                "peak_source": pk["src"] + ", sustained cuBLAS bf16",
+                "launches_per_step": nl, "avg_launch_ms": ms_in_step / nl,
+                "share_of_step": share, "time_basis": "per-op CUDA-event share x graph-replayed ms_per_step",
                 "per_kernel": {k: {"ms": round(prof[k]["ms"], 3), "launches": prof[k]["n"],
                                    "tflops": round(prof[k]["flops"] / (prof[k]["ms"] * 1e-3) / 1e12, 1)}
                                for k in tc_names}}
+        tpj = os.path.join(ROOT, "profiles", "tensor_pipe.json")
+        if os.path.exists(tpj):        # ncu sm__pipe_tensor_cycles_active captures (committed evidence)
+            roof["ncu_tensor_pipe"] = json.load(open(tpj)).get(precision)
     elif "conv_simt" in prof:
         c = prof["conv_simt"]
-        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        ach = c["flops"] / (c["ms"] / total_ms * ms_per_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_simt_kernel (fp32 FFMA)", "achieved": ach,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "traffic": None, "peak_source": pk["src"]}
-    # fused phase-space update alone (HBM-bound), timed at this batch
-    upd = time_update(lib, state, plan, B, chw, stream, dev, state_dtype, sde, ts)
-    upd["peak"] = pk["hbm"]
-    upd["frac"] = upd["achieved"] / pk["hbm"]
-    if "achieved" in upd.get("large", {}):
-        upd["large"]["frac"] = upd["large"]["achieved"] / pk["hbm"]
 
     # ---- end to end through the public API: pinned host prior -> HOST samples
     e2e = None
     if args.e2e_nfe > 0:
-        cfg_e = make_cfg(batch_size=B, n_samples=B * world, n_discrete_steps=args.e2e_nfe)
+        cfg_e = ctx["make_cfg"](batch_size=B, n_samples=B * world, n_discrete_steps=args.e2e_nfe)
         cfg_e.evaluation.sampler["state_dtype"] = args.state
         Se = SSCSSampler(cfg_e, sde, net)
         ts_e, n_e = time_grid(cfg_e)
@@ -344,36 +342,146 @@ def main_b200(args):
                "d2h_bytes_per_step": int(host.numel() * host.element_size()),
                "seconds": dt, "nfe": args.e2e_nfe, "api": "SSCSSampler.sample + gather_samples",
                "finite": bool(torch.isfinite(host).all().item())}
+    return {"precision": precision, "dtype": TIER_DTYPE[precision], "note": TIER_NOTE[precision],
+            "value": value, "ms_per_step": ms_per_step, "e2e": e2e, "roofline": roof, "clocks": clk,
+            "gpu_launches": launches, "finite": finite, "engines": dict(plan.engine_count),
+            "tensor_frac_of_step": (ctx["flop"] * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
+            "per_kernel_ms": {k: round(v["ms"] / total_ms * ms_per_step, 4) for k, v in prof.items()},
+            "conv_classes": {k: {"n": v["n"], "ms": round(v["ms"], 4), "tflops": round(v["tflops"], 1)}
+                             for k, v in sorted(conv_classes.items(), key=lambda kv: -kv[1]["ms"])},
+            "_state": state, "_plan": plan}
 
-    cpu = None
+
+def gpu_eager_baseline(cfg, sde_cfg_B, dev, steps=2):
+    """Context, never the target: the reference's algorithm as PLAIN PyTorch-eager CUDA code on the same
+    B200 (the oracle port's ``ncsnpp_forward`` + SSCS algebra with ``.cuda()`` tensors: cuDNN / cuBLAS
+    through ATen, FIR through the pure-ATen ``upfirdn2d``), fp32, device-timed."""
+    import torch
+    from oracle import psld_oracle as O
+    from oracle.weights import fill_state_dict, noise_bank, prior
+    from psld_b200 import NCSNpp
+    B = sde_cfg_B
+    H = cfg.data.image_size
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    sd = {k: v.to(dev) for k, v in fill_state_dict(shapes, 0).items()}
+    score = lambda u, t: O.ncsnpp_forward(cfg, sd, u, t)
+    ts, n = O.time_grid(cfg)
+    u0 = prior((B, 3, H, H), 0.5, 1).to(dev)
+    out = {}
+    for name, tf32 in (("tf32_convs_torch_default", True), ("strict_fp32", False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        nb = [z.to(dev) for z in noise_bank(2 * (steps + 1), (B, 6, H, H), 2)]
+        with torch.no_grad():
+            O.sscs_sample(cfg, score, u0, ts, 1, nb, denoise=False)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            O.sscs_sample(cfg, score, u0, ts, steps, nb, denoise=False)
+            b.record()
+            torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / steps
+        out[name] = {"value": B / (NFE * ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+    torch.backends.cudnn.allow_tf32 = True
+    out["what"] = (f"oracle port (plain PyTorch eager, fp32) of NCSN++ forward + SSCS algebra on cuda, batch {B}, "
+                   f"{steps} steps after 1 warm-up, extrapolated linearly to {NFE} NFE")
+    return out
+
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from psld_b200 import NCSNpp, PSLD, time_grid
+    from psld_b200 import _lib as L
+    from psld_b200.distributed import env_rank
+
+    rank, world, local = env_rank()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    import psld_b200
+    cfg_name, flop_per_sample_nfe, default_batch, workload_desc = WORKLOADS[args.workload]
+    make_cfg = getattr(psld_b200, cfg_name)
+    scaling = "weak"
+    if args.batch_total > 0:             # fixed total batch sharded over the ranks (BASELINE configs[2]/[3])
+        if args.batch_total % world:
+            raise SystemExit(f"--batch-total {args.batch_total} is not divisible by {world} GPUs")
+        args.batch = args.batch_total // world
+        scaling = "strong"
+    elif args.batch <= 0:
+        args.batch = default_batch
+    cfg = make_cfg(batch_size=args.batch, n_samples=args.batch * world)
+    cfg.evaluation.sampler["state_dtype"] = args.state
+    torch.manual_seed(1234)
+    net = NCSNpp(cfg).eval().to(dev)   # random-init weights
+    sde = PSLD(cfg)
+    B = args.batch
+    H = cfg.data.image_size
+    ts, n = time_grid(cfg)
+    ctx = dict(net=net, sde=sde, cfg=cfg, dev=dev, rank=rank, world=world, local=local, pk=pk, B=B, H=H,
+               chw=3 * H * H, ts=ts, side=torch.cuda.Stream(dev), make_cfg=make_cfg, flop=flop_per_sample_nfe)
+
+    main = measure_tier(args, args.precision, ctx)
+    lib = L.lib()
+    state_dtype = torch.float32 if args.state == "float32" else torch.float64
+    # fused phase-space update alone (HBM-bound), timed at this batch
+    upd = time_update(lib, main["_state"], main["_plan"], B, 3 * H * H, L.stream_ptr(dev), dev, state_dtype,
+                      sde, ts)
+    upd["peak"] = pk["hbm"]
+    upd["frac"] = upd["achieved"] / pk["hbm"]
+    if "achieved" in upd.get("large", {}):
+        upd["large"]["frac"] = upd["large"]["achieved"] / pk["hbm"]
+
+    # ---- the other tensor-core tier, stated separately (north_star: "the bf16 score_fn path stated
+    # separately"): same workload, same measurement, its own roofline and end-to-end number
+    other = None
+    sec = {"bf16x3": "bf16", "bf16": "bf16x3"}.get(args.precision)
+    if sec and not args.no_secondary:
+        o = measure_tier(args, sec, ctx)
+        other = {k: o[k] for k in ("precision", "dtype", "note", "value", "ms_per_step", "e2e", "roofline",
+                                   "gpu_launches", "finite", "tensor_frac_of_step", "per_kernel_ms",
+                                   "conv_classes", "clocks")}
+
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu_port(make_cfg(), args.cpu_batch, args.cpu_steps, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        try:
+            eager = gpu_eager_baseline(make_cfg(), min(B, 64), dev)
+        except Exception as e:      # context only: never fail the bench line on it
+            eager = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
 
     if rank == 0:
         line = {
             "metric": METRIC if args.workload == "cifar10" else METRIC.replace("CIFAR-10", "CelebA-64"),
-            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
+            "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None,
+            "dtype": main["dtype"], "data": "synthetic",
             "config": {
                 "workload": workload_desc,
                 "batch_per_gpu": B, "batch_total": B * world, "nfe_per_sample": NFE,
+                "precision_tier": args.precision + ": " + main["note"],
                 "state_dtype": args.state, "noise": "in-kernel Philox4x32-10",
                 "step": "one SSCS predictor step = 1 score_fn call + 1 fused update",
                 "cuda_graph": bool(args.graph),
                 "l2": "activations per step (GBs at B=256) exceed the 126 MB L2; no flush needed",
-                "parallelism": f"batch-sharded x{world}, no per-step communication",
+                "parallelism": f"batch-sharded x{world}, no per-step communication, one final NCCL all-gather",
             },
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "roofline_update": upd, "cpu_baseline": cpu,
-            "tensor_frac_of_step": (flop_per_sample_nfe * B / (ms_per_step * 1e-3) / 1e12) / pk["tf_sustained"],
-            "per_kernel_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
-            "engines": plan.engine_count, "finite": finite,
-            "conv_classes": {k: {"n": v["n"], "ms": round(v["ms"], 4), "tflops": round(v["tflops"], 1)}
-                             for k, v in sorted(conv_classes.items(), key=lambda kv: -kv[1]["ms"])},
+            "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+            "roofline": main["roofline"], "roofline_update": upd, "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
+            "tensor_frac_of_step": main["tensor_frac_of_step"],
+            "per_kernel_ms": main["per_kernel_ms"],
+            "engines": main["engines"], "finite": main["finite"],
+            "conv_classes": main["conv_classes"],
         }
+        if other is not None:
+            line[other["precision"] + "_path"] = other
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

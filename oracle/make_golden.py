@@ -220,11 +220,26 @@ def golden_full_size(R):
     golden_sampler(R, c, "sampler_celeba64_sscs20.npz", B=2, keep=1)
 
 
+def golden_state_dict_contract(R):
+    """Names and shapes of the REFERENCE module's state dict for the shipped architectures: the
+    checkpoint contract (``ema_score_fn.all_modules.<i>...``, wrapper.py:30-31) the drop-in must keep."""
+    import json
+    out = {}
+    for name, mk in (("tiny", tiny_config), ("cifar10", cifar10_config), ("celeba64", celeba64_config)):
+        net = R.NCSNpp(mk())
+        out[name] = {k: list(v.shape) for k, v in net.state_dict().items()}
+        print(name, len(out[name]), "tensors", sum(int(np.prod(v)) for v in out[name].values()), "elements")
+    with open(os.path.join(OUT, "state_dict_contract.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     R = load_reference()
     if "--only-full-size" in sys.argv:
         return golden_full_size(R)
+    if "--only-contract" in sys.argv:
+        return golden_state_dict_contract(R)
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
     if "--only-vp" in sys.argv:
@@ -258,6 +273,7 @@ def main():
     golden_inpaint_all(R)
     golden_vp(R)
     golden_full_size(R)
+    golden_state_dict_contract(R)
 
 
 def vp_config(**ev):

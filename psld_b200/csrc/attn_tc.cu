@@ -24,13 +24,25 @@
 
 namespace psld {
 
-constexpr int AT_SLOT_BYTES = 16384 + 32768;   // Q chunk [128 x 64] + K chunk / V group [<=256 x 64]
-constexpr int AT_SLOTS = 3;
-constexpr int AT_P_BYTES = 128 * 256 * 2;      // P as 4 K-major tiles of [128 x 64] bf16
-constexpr int AT_SMEM_BYTES = AT_SLOTS * AT_SLOT_BYTES + AT_P_BYTES + 1024 + 256;
-// fused output projection: + 4 KB staging and 256 B additive vector per softmax/epilogue warp
-constexpr int AT_SMEM_BYTES_PROJ = AT_SMEM_BYTES + 4 * 4096 + 4 * 256;
+constexpr int AT_P_TILE = 128 * 256 * 2;       // P (or normalised O) as 4 K-major tiles of [128 x 64] bf16
 constexpr int AT_THREADS = 192;
+
+// kX3 = split-bf16 operands (the fp32-tolerance tier): q|k|v rows are [3C hi | 3C lo], every GEMM
+// (S = Q K^T, O = P V, Y = O W3^T) is three MMA groups hi*hi + hi*lo + lo*hi, P and the normalised
+// O are written to shared memory as hi and lo tiles, the output is split bf16.  Operand tiles are
+// twice as large, so the ring has ONE slot (96 KB) next to the 128 KB of P; the projection
+// epilogue's staging tiles alias the slot (every MMA has retired by then).
+template <bool kX3>
+struct AtCfg {
+  static constexpr int kQBytes = 16384 * (kX3 ? 2 : 1);      // Q chunk [128 x 64] (hi | lo)
+  static constexpr int kKVBytes = 32768 * (kX3 ? 2 : 1);     // K chunk / V group / W3 chunk [<=256 x 64]
+  static constexpr int kSlotBytes = kQBytes + kKVBytes;
+  static constexpr int kSlots = kX3 ? 1 : 3;
+  static constexpr int kPBytes = AT_P_TILE * (kX3 ? 2 : 1);
+  static constexpr int kSmem = kSlots * kSlotBytes + kPBytes + 1024 + 256;
+  // fused output projection: 4 KB staging and 256 B additive vector per softmax/epilogue warp
+  static constexpr int kSmemProj = kSmem + (kX3 ? 0 : 4 * 4096 + 4 * 256);
+};
 
 struct AttnTcParams {
   __nv_bfloat16* out;
@@ -42,7 +54,7 @@ struct AttnTcParams {
 
 struct AttnTcState {
   CUtensorMap tq, tkv, tw;
-  bool proj;
+  bool proj, x3;
   AttnTcParams p;
   dim3 grid;
 };
@@ -53,14 +65,21 @@ struct AttnTcState {
 //   product accumulates in the TMEM columns S occupied, and the conv epilogue (bias, residual,
 //   scale, bf16 store, GroupNorm statistics) finishes the tile: no O round trip through HBM and
 //   no separate 1x1 convolution launch.
-template <bool kProj>
+template <bool kProj, bool kX3>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmW, const AttnTcParams p) {
+  using Cfg = AtCfg<kX3>;
+  constexpr int AT_SLOTS = Cfg::kSlots;
+  constexpr int AT_SLOT_BYTES = Cfg::kSlotBytes;
+  constexpr uint32_t QB = Cfg::kQBytes;              // offset of the K / V / W3 tile inside a slot
+  constexpr uint32_t A_LO = 16384u;                  // lo half of the Q chunk (kX3)
+  constexpr uint32_t B_LO = 32768u;                  // lo half of the K / V / W3 tile (kX3)
+  constexpr uint32_t P_LO = AT_P_TILE;               // lo tiles of P / normalised O (kX3)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t p_base = base + AT_SLOTS * AT_SLOT_BYTES;
-  const uint32_t bar_base = p_base + AT_P_BYTES;
+  const uint32_t bar_base = p_base + Cfg::kPBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (AT_SLOTS + s); };
   const uint32_t s_full = bar_base + 8u * (2 * AT_SLOTS);
@@ -69,8 +88,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t o_ready = s_full + 24u;
   const uint32_t y_full = s_full + 32u;
   const uint32_t tmem_slot = s_full + 40u;
-  const uint32_t stg_base = bar_base + 256u;             // kProj only
+  // kProj only; kX3: aliases the (by then idle) operand slot
+  const uint32_t stg_base = kX3 ? base : bar_base + 256u;
   const uint32_t addv_base = stg_base + 4u * 4096u;
+  const int lo_c = 3 * p.C;                              // kX3: lo half of a q|k|v row
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -113,25 +134,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // Q/K channel chunks
       for (int c = 0; c < nck; ++c) {
         mbar_wait(empty_bar(slot), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(p.q_rows + p.HW) * 128u);
+        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(p.q_rows + p.HW) * 128u * (kX3 ? 2u : 1u));
         const uint32_t sq = base + slot * AT_SLOT_BYTES;
         tma_load_3d(sq, &tmQ, full_bar(slot), c * 64, q0, n);
-        tma_load_3d(sq + 16384, &tmKV, full_bar(slot), p.C + c * 64, 0, n);
+        tma_load_3d(sq + QB, &tmKV, full_bar(slot), p.C + c * 64, 0, n);
+        if (kX3) {
+          tma_load_3d(sq + A_LO, &tmQ, full_bar(slot), lo_c + c * 64, q0, n);
+          tma_load_3d(sq + QB + B_LO, &tmKV, full_bar(slot), lo_c + p.C + c * 64, 0, n);
+        }
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       }
       // V channel groups
       for (int g = 0; g < nck; ++g) {
         mbar_wait(empty_bar(slot), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.HW * 128u);
-        const uint32_t sv = base + slot * AT_SLOT_BYTES + 16384;
+        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.HW * 128u * (kX3 ? 2u : 1u));
+        const uint32_t sv = base + slot * AT_SLOT_BYTES + QB;
         tma_load_3d(sv, &tmKV, full_bar(slot), 2 * p.C + g * 64, 0, n);
+        if (kX3) tma_load_3d(sv + B_LO, &tmKV, full_bar(slot), lo_c + 2 * p.C + g * 64, 0, n);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       }
       if (kProj) {       // W3 [C out rows x 64 input channels] per chunk
         for (int c = 0; c < nck; ++c) {
           mbar_wait(empty_bar(slot), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.C * 128u);
-          tma_load_2d(base + slot * AT_SLOT_BYTES + 16384, &tmW, full_bar(slot), c * 64, 0);
+          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.C * 128u * (kX3 ? 2u : 1u));
+          tma_load_2d(base + slot * AT_SLOT_BYTES + QB, &tmW, full_bar(slot), c * 64, 0);
+          if (kX3) tma_load_2d(base + slot * AT_SLOT_BYTES + QB + B_LO, &tmW, full_bar(slot), c * 64, p.C);
           if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
         }
       }
@@ -148,11 +175,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         const uint32_t sq = base + slot * AT_SLOT_BYTES;
         const uint64_t adesc = make_sw128_desc(sq);
-        const uint64_t bdesc = make_sw128_desc(sq + 16384);
+        const uint64_t bdesc = make_sw128_desc(sq + QB);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s,
                       (c > 0 || k > 0) ? 1u : 0u);
+        if (kX3) {
+          const uint64_t adesc_lo = make_sw128_desc(sq + A_LO);
+          const uint64_t bdesc_lo = make_sw128_desc(sq + QB + B_LO);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc_s, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_S, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, 1u);
+        }
         tc_commit(empty_bar(slot));
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       }
@@ -165,12 +202,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int g = 0; g < nck; ++g) {
         mbar_wait(full_bar(slot), phase);
         tc_fence_after();
-        const uint32_t sv = base + slot * AT_SLOT_BYTES + 16384;
+        const uint32_t sv = base + slot * AT_SLOT_BYTES + QB;
         for (int ks = 0; ks < p.HW / 16; ++ks) {
           const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)(ks >> 2) * 16384u) +
                                  (uint64_t)(2 * (ks & 3));
           const uint64_t bdesc = make_sw128_desc(sv + (uint32_t)ks * 2048u);   // 16 keys x 128 B
           tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+          if (kX3) {
+            const uint64_t adesc_lo = make_sw128_desc(p_base + P_LO + (uint32_t)(ks >> 2) * 16384u) +
+                                      (uint64_t)(2 * (ks & 3));
+            const uint64_t bdesc_lo = make_sw128_desc(sv + B_LO + (uint32_t)ks * 2048u);
+            tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc, bdesc_lo, idesc_o, 1u);
+            tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc_lo, bdesc, idesc_o, 1u);
+          }
         }
         tc_commit(empty_bar(slot));
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
@@ -187,11 +231,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)c * 16384u);
-          const uint64_t bdesc = make_sw128_desc(base + slot * AT_SLOT_BYTES + 16384);
+          const uint64_t bdesc = make_sw128_desc(base + slot * AT_SLOT_BYTES + QB);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_y,
                         (c > 0 || k > 0) ? 1u : 0u);
+          if (kX3) {
+            const uint64_t adesc_lo = make_sw128_desc(p_base + P_LO + (uint32_t)c * 16384u);
+            const uint64_t bdesc_lo = make_sw128_desc(base + slot * AT_SLOT_BYTES + QB + B_LO);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc_y, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tmem_S, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_y, 1u);
+          }
           tc_commit(empty_bar(slot));
           if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
         }
@@ -224,20 +278,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int cbase = (ch & 63) >> 3;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t w[4];
+        uint32_t w[4], wl[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float e0 = exp2f(fmaf(__uint_as_float(r[q * 8 + 2 * t]), p.scale_log2, -mxs));
           const float e1 = exp2f(fmaf(__uint_as_float(r[q * 8 + 2 * t + 1]), p.scale_log2, -mxs));
-          __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-          // accumulate the sum from the ROUNDED values so that P / sum is a true softmax of P
-          const float2 f = __bfloat1622float2(h);
-          sum += f.x + f.y;
-          w[t] = *reinterpret_cast<uint32_t*>(&h);
+          if (kX3) {
+            split_bf2(e0, e1, w[t], wl[t]);
+            sum += e0 + e1;
+          } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+            // accumulate the sum from the ROUNDED values so that P / sum is a true softmax of P
+            const float2 f = __bfloat1622float2(h);
+            sum += f.x + f.y;
+            w[t] = *reinterpret_cast<uint32_t*>(&h);
+          }
         }
         const uint32_t dst = tile + (uint32_t)(((cbase + q) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                      ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        if (kX3) sts128(dst + P_LO, wl[0], wl[1], wl[2], wl[3]);
       }
     }
     // make the generic-proxy smem writes visible to the tensor-core (async) proxy
@@ -259,14 +319,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int cbase = (ch & 63) >> 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t w[4];
+          uint32_t w[4], wl[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * t]) * inv,
-                                                     __uint_as_float(r[j * 8 + 2 * t + 1]) * inv);
-            w[t] = *reinterpret_cast<uint32_t*>(&h);
+            const float o0 = __uint_as_float(r[j * 8 + 2 * t]) * inv;
+            const float o1 = __uint_as_float(r[j * 8 + 2 * t + 1]) * inv;
+            if (kX3) split_bf2(o0, o1, w[t], wl[t]);
+            else w[t] = f2_to_bf2(o0, o1);
           }
           sts128(tile + (uint32_t)(((cbase + j) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+          if (kX3)
+            sts128(tile + P_LO + (uint32_t)(((cbase + j) ^ (row & 7)) << 4), wl[0], wl[1], wl[2], wl[3]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -278,11 +341,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5
 #pragma unroll 1
       for (int half = 0; half < 2; ++half)
-        tc_epilogue_tile<true, 64, true>(p.ep, tmem_S, 0, m_tile, 0, quarter, half, lane,
-                                         stg_base + (uint32_t)ew * 4096u,
-                                         addv_base + (uint32_t)ew * 256u, []() {}, []() {});
+        tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_S, 0, m_tile, 0, quarter, half, lane,
+                                                         stg_base + (uint32_t)ew * 4096u,
+                                                         addv_base + (uint32_t)ew * 256u, []() {}, []() {});
     } else {
-    __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * p.C;
+    __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * (p.C * (kX3 ? 2 : 1));
     for (int ch = 0; ch < p.C; ch += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_O + lane_addr + (uint32_t)ch, r);
@@ -290,14 +353,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          uint32_t w[4];
+          uint32_t w[4], wl[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]) * inv,
-                                                     __uint_as_float(r[j + 2 * t + 1]) * inv);
-            w[t] = *reinterpret_cast<uint32_t*>(&h);
+            const float o0 = __uint_as_float(r[j + 2 * t]) * inv;
+            const float o1 = __uint_as_float(r[j + 2 * t + 1]) * inv;
+            if (kX3) split_bf2(o0, o1, w[t], wl[t]);
+            else w[t] = f2_to_bf2(o0, o1);
           }
           *reinterpret_cast<uint4*>(orow + ch + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (kX3) *reinterpret_cast<uint4*>(orow + p.C + ch + j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
       }
       __syncwarp();
@@ -335,15 +400,19 @@ int prepare_attn_tc(psld_op& op) {
     set_error("attn_tc: not eligible (%s): N=%d HW=%d C=%d", why, N, HW, C);
     return PSLD_EUNSUPPORTED;
   };
-  if (op.i[PSLD_ATTN_DTYPE] != PSLD_BF16) return unsupported("dtype must be bf16");
+  const int adt = op.i[PSLD_ATTN_DTYPE];
+  if (adt != PSLD_BF16 && adt != PSLD_BF16S) return unsupported("dtype must be bf16 or split bf16");
+  const bool x3 = adt == PSLD_BF16S;
+  const int cm = x3 ? 2 : 1;
   if (C % 64 || C < 64 || C > 256) return unsupported("C must be 64..256, multiple of 64");
   if (HW != 64 && HW != 128 && HW != 256) return unsupported("HW must be 64, 128 or 256");
   if (!op.in[0] || !op.out[0]) { set_error("attn_tc: null pointer"); return PSLD_EINVAL; }
   AttnTcState* st = new (std::nothrow) AttnTcState();
   if (!st) { set_error("attn_tc: out of host memory"); return PSLD_ECUDA; }
   const int q_rows = HW < 128 ? HW : 128;
-  int rc = encode_qkv_map(&st->tq, op.in[0], N, HW, 3 * C, q_rows);
-  if (rc == PSLD_OK) rc = encode_qkv_map(&st->tkv, op.in[0], N, HW, 3 * C, HW);
+  st->x3 = x3;
+  int rc = encode_qkv_map(&st->tq, op.in[0], N, HW, cm * 3 * C, q_rows);
+  if (rc == PSLD_OK) rc = encode_qkv_map(&st->tkv, op.in[0], N, HW, cm * 3 * C, HW);
   if (rc != PSLD_OK) { delete st; return rc; }
   st->p.out = (__nv_bfloat16*)op.out[0];
   st->p.HW = HW; st->p.C = C; st->p.N = N; st->p.q_rows = q_rows;
@@ -354,7 +423,7 @@ int prepare_attn_tc(psld_op& op) {
   if (st->proj) {
     if (HW % 128 || !op.in[1] || !op.in[3]) { delete st; return unsupported("fused projection needs HW %% 128 == 0, weight and residual"); }
     EncodeTiledFn enc = get_encode_fn();
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)C};
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(cm * C)};      // split: planes [2][C out, C in]
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)C};
     cuuint32_t estr[2] = {1, 1};
@@ -381,11 +450,17 @@ int prepare_attn_tc(psld_op& op) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         AT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::kSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               AT_SMEM_BYTES_PROJ);
+      e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AtCfg<false>::kSmemProj);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AtCfg<true>::kSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AtCfg<true>::kSmemProj);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -408,12 +483,13 @@ int release_attn_tc(psld_op& op) {
 int run_attn_tc(const psld_op& op, cudaStream_t s) {
   const AttnTcState* st = (const AttnTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
-  if (st->proj)
-    PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES_PROJ, s, 1,
-                               st->tq, st->tkv, st->tw, st->p));
-  else
-    PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, st->grid, dim3(AT_THREADS), AT_SMEM_BYTES, s, 1,
-                               st->tq, st->tkv, st->tw, st->p));
+#define ATTN_LAUNCH(PROJ, X3)                                                                  \
+  PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<PROJ, X3>, st->grid, dim3(AT_THREADS),                \
+                             PROJ ? AtCfg<X3>::kSmemProj : AtCfg<X3>::kSmem, s, 1, st->tq, st->tkv, \
+                             st->tw, st->p))
+  if (st->proj) { if (st->x3) ATTN_LAUNCH(true, true); else ATTN_LAUNCH(true, false); }
+  else { if (st->x3) ATTN_LAUNCH(false, true); else ATTN_LAUNCH(false, false); }
+#undef ATTN_LAUNCH
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

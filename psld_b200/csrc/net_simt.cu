@@ -239,14 +239,19 @@ struct Vec8<bf16s> {
 // accurate SiLU for the fp32 path, fast-intrinsic SiLU when the result is rounded to bf16 anyway
 // fast path: silu(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2 : ONE MUFU op (tanh.approx.f32,
 // |err| ~ 5e-4 absolute at most, well under the bf16 rounding of the result) instead of ex2 + rcp
-template <bool kFast>
+// kFast = 2 (split-bf16 tier): x * rcp(1 + ex2(-x log2 e)) with the MUFU ex2 / rcp approximations
+// (2 ulp each; the argument scaling adds |x| 2^-24): ~1e-6 relative for |x| < 16, an order of
+// magnitude under the tier's 16-bit operand precision, at a third of the instructions of the
+// IEEE expf + division form (the apply pass of this tier is instruction-bound, not HBM-bound).
+template <int kFast>
 __device__ __forceinline__ float silu_t(float x) {
-  if (kFast) {
+  if (kFast == 1) {
     const float h = 0.5f * x;
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
     return fmaf(h, t, h);
   }
+  if (kFast == 2) return __fdividef(x, 1.0f + __expf(-x));
   return x / (1.0f + expf(-x));
 }
 
@@ -348,7 +353,7 @@ __device__ __forceinline__ void gn_group_sums(const double* __restrict__ mg1,
 
 // kMicro: group statistics come straight from the producers' accumulators (mg1, mg2); otherwise
 // from the `part` chunks written by gn_stats_kernel.
-template <typename TI, typename TO, int VW, bool kFast, bool kMicro>
+template <typename TI, typename TO, int VW, int kFast, bool kMicro>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
                 const double* __restrict__ part, const double* __restrict__ mg1,
@@ -551,9 +556,9 @@ int run_gn(const psld_op& op, cudaStream_t s) {
              (const T*)op.in[1], part, m1, m2, ga, be, (T*)op.out[0], HW, C1, C2, G, nchunk_eff, nca, \
              eps, silu)
 #define GN_APPLY2(T, VW, FAST) do { if (fused) GN_APPLY(T, VW, FAST, true); else GN_APPLY(T, VW, FAST, false); } while (0)
-  if (idt == PSLD_BF16) { if (v8) GN_APPLY2(__nv_bfloat16, 8, true); else GN_APPLY2(__nv_bfloat16, 4, true); }
-  else if (idt == PSLD_BF16S) { if (v8) GN_APPLY2(bf16s, 8, false); else GN_APPLY2(bf16s, 4, false); }
-  else { if (v8) GN_APPLY2(float, 8, false); else GN_APPLY2(float, 4, false); }
+  if (idt == PSLD_BF16) { if (v8) GN_APPLY2(__nv_bfloat16, 8, 1); else GN_APPLY2(__nv_bfloat16, 4, 1); }
+  else if (idt == PSLD_BF16S) { if (v8) GN_APPLY2(bf16s, 8, 2); else GN_APPLY2(bf16s, 4, 2); }
+  else { if (v8) GN_APPLY2(float, 8, 0); else GN_APPLY2(float, 4, 0); }
 #undef GN_APPLY2
 #undef GN_APPLY
   PSLD_CHECK_LAUNCH();

@@ -24,11 +24,22 @@ def select_score_fn_state(state_dict: dict, sample_from: str = "target") -> dict
     return out
 
 
-def load_checkpoint(net, path: str, sample_from: str = "target", map_location="cpu"):
+def load_checkpoint(net, path: str, sample_from: str = "target", map_location="cpu", trust: bool = False):
     """Loads a reference ``.ckpt`` (Lightning: ``{"state_dict": ...}``) or a bare state dict into a
     :class:`psld_b200.NCSNpp`.  Parameter names/shapes are the reference's, so this is a plain
-    ``load_state_dict`` (strict)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    ``load_state_dict`` (strict).
+
+    Only tensors are needed, so the file is read with ``weights_only=True`` (no arbitrary pickle
+    code runs).  A checkpoint that also pickles non-tensor objects (Lightning hyper-parameters,
+    callbacks) needs ``trust=True`` to fall back to the unrestricted loader."""
+    try:
+        ckpt = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception as e:
+        if not trust:
+            raise RuntimeError(
+                f"{path}: not loadable with weights_only=True ({type(e).__name__}: {str(e)[:200]}); "
+                "pass trust=True to unpickle it without restrictions if you trust its origin") from e
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
     sd = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
     if any(k.startswith(("score_fn.", "ema_score_fn.")) for k in sd):
         sd = select_score_fn_state(sd, sample_from)

@@ -19,15 +19,17 @@ def op_name(op):
     return KIND_NAMES.get(op.kind, "?")
 
 
-def op_flops(op) -> float:
-    """Algorithmic FLOPs (2*MAC) of dense-contraction ops; 0 for memory-bound ops."""
+def op_flops(op, cin_valid=None) -> float:
+    """Algorithmic FLOPs (2*MAC) of dense-contraction ops; 0 for memory-bound ops.  Zero padding is
+    not work: ``cin_valid`` = real input channels of a conv over a channel-padded input, and the
+    output head counts its valid output channels only."""
     i = op.i
     if op.kind == L.OP_CONV:
         M = i[L.CONV_N] * i[L.CONV_OH] * i[L.CONV_OW]
-        K = i[L.CONV_KS] ** 2 * (i[L.CONV_C1] + i[L.CONV_C2])
+        K = i[L.CONV_KS] ** 2 * (cin_valid if cin_valid else i[L.CONV_C1] + i[L.CONV_C2])
         if op.engine == L.ENGINE_TC:
             K += i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]      # fused 1x1 shortcut
-        cout = int(op.f[1]) if (op.engine == L.ENGINE_TC and op.f[1] >= 1) else i[L.CONV_COUT]
+        cout = int(op.f[1]) if (op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN) and op.f[1] >= 1) else i[L.CONV_COUT]
         return 2.0 * M * K * cout
     if op.kind == L.OP_ATTN:
         return 4.0 * i[L.ATTN_N] * i[L.ATTN_HW] ** 2 * i[L.ATTN_C]
@@ -69,7 +71,7 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
             for k in range(n):
                 acc[k] += evs[k].elapsed_time(evs[k + 1])
     out = {}
-    elt = 2 if plan.bf16 else 4
+    elt = 2 if plan.bf16 else 4      # (split bf16 = 4 bytes per element)
     classes = {}
     for k in range(n):
         op = plan.op_array[k]
@@ -82,11 +84,11 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
             c = classes.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
             c["ms"] += acc[k] / iters
             c["n"] += 1
-            c["flops"] += op_flops(op)
+            c["flops"] += op_flops(op, plan.cin_valid.get(k))
         d = out.setdefault(op_name(op), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += acc[k] / iters
         d["n"] += 1
-        d["flops"] += op_flops(op)
+        d["flops"] += op_flops(op, plan.cin_valid.get(k))
         d["bytes"] += op_bytes(op, elt)
     for d in out.values():
         d["launch_ms"] = d["ms"] / max(d["n"], 1)

@@ -64,6 +64,7 @@ class Plan:
         self.ops = []
         self.pool = {}
         self.engine_count = {"tc": 0, "simt": 0}
+        self.cin_valid = {}     # op index -> real input channels of convs over a zero-padded input
         self.mg = {}            # data_ptr of an activation -> its GroupNorm statistics accumulator
         self.stat_chunks = []   # f64 arenas the accumulators are carved from (zeroed by OP_ZERO)
         self.stat_used = []
@@ -252,7 +253,9 @@ class Plan:
             N, H, W, C1 = x1.shape
         C2 = x2.shape[-1] if x2 is not None else 0
         Cout = w_oihw.shape[0]
+        cin_real = None
         if x2 is None and w_oihw.shape[1] < C1:       # zero-padded input channels (6 -> 64)
+            cin_real = int(w_oihw.shape[1])
             w_oihw = torch.cat([w_oihw.detach(), w_oihw.new_zeros(
                 Cout, C1 - w_oihw.shape[1], *w_oihw.shape[2:])], 1)
         assert w_oihw.shape[1] == C1 + C2, (tuple(w_oihw.shape), C1, C2)
@@ -382,7 +385,9 @@ class Plan:
             ws = self._w(w.permute(2, 3, 1, 0).reshape(-1, Cout))     # [K, Cout] fp32
             op.inp[4] = ws.data_ptr()
             self.engine_count["simt"] += 1
-        self._push(op)
+        idx = self._push(op)
+        if cin_real is not None:
+            self.cin_valid[idx] = cin_real
         return out
 
     @staticmethod
@@ -409,11 +414,15 @@ class Plan:
         op.inp[0] = qkv.data_ptr()
         fusable = Cc % 64 == 0 and 64 <= Cc <= 256 and HW in (128, 256)
         if proj is not None:
-            if not (self.bf16 and fusable) or os.environ.get("PSLD_ATTN_FUSE_PROJ", "1") == "0":
+            if not (self.tc and fusable) or os.environ.get("PSLD_ATTN_FUSE_PROJ", "1") == "0":
                 return None
             w3, b3, x, scale, o = proj
             op.i[L.ATTN_PROJ] = 1
             op.f[1] = float(scale)
+            w3 = w3.detach().to(self.dev, torch.float32)
+            if self.x3:          # weight planes [2][C out, C in]
+                hi = w3.to(torch.bfloat16)
+                w3 = torch.cat([hi, (w3 - hi.to(torch.float32)).to(torch.bfloat16)], 0)
             op.inp[1] = self._w(w3, torch.bfloat16).data_ptr()
             op.inp[2] = self._w(b3).data_ptr() if b3 is not None else None
             op.inp[3] = x.data_ptr()
@@ -424,7 +433,7 @@ class Plan:
         else:
             o = self._acquire(*qkv.shape[:-1], Cc)
         op.out[0] = o.data_ptr()
-        if self.bf16:
+        if self.tc:
             op.engine = L.ENGINE_TC
             if self.dry:
                 rc = L.OK if (Cc % 64 == 0 and 64 <= Cc <= 256 and HW in (64, 128, 256)) else L.EUNSUPPORTED

@@ -98,9 +98,84 @@ class _FusedSampler(Sampler):
         self.record = None         # optional [n, B,2C,H,W] buffer filled with per-step states
         self.nfe = 0
 
-    # the reference exposes this name; the fused kernels implement it
-    def predictor_update_fn(self, *a, **k):
-        raise NotImplementedError("psld_b200 samplers fuse the predictor step into sample()")
+    # ------------------------------------------------------------------ reference-named single steps
+    # ``sample()`` never calls these (it runs the fused native loop); they exist so that code written
+    # against the reference's sampler API (custom loops, correctors, notebooks) keeps working, and
+    # they run on the same fused kernels.
+    def _scalar(self, v):
+        return float(v.reshape(-1)[0]) if torch.is_tensor(v) else float(v)
+
+    def _single(self, u, t, dt):
+        if self.vp is not None:
+            raise NotImplementedError("single-step API is implemented for the PSLD SDE")
+        if not u.is_cuda:
+            raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
+        if u.dim() != 4 or u.shape[1] % 2 or (u.shape[1] // 2 * u.shape[2] * u.shape[3]) % 4:
+            raise ValueError(f"expected a [B,2C,H,W] phase-space batch, got {tuple(u.shape)}")
+        t, dt = self._scalar(t), self._scalar(dt)
+        tabs = StepTables(self.schedule, torch.tensor([t], dtype=torch.float64), 1, self.KIND, False,
+                          1e-3, self._embedding(), dt=torch.tensor([dt], dtype=torch.float64))
+        sdt = torch.float64 if u.dtype == torch.float64 else torch.float32
+        state = u.to(sdt).contiguous().clone()
+        net_in = state.to(torch.float32)
+        B = u.shape[0]
+        chw = u.shape[1] // 2 * u.shape[2] * u.shape[3]
+        self._single_calls = getattr(self, "_single_calls", 0) + 1
+        return tabs, state, net_in, B, chw, L.dtype_code(sdt), L.stream_ptr(u.device)
+
+    def _score(self, net_in, tabs, B):
+        with torch.no_grad():
+            return self.score_fn(net_in, tabs.tau32[0].to(net_in.device).expand(B)).to(torch.float32).contiguous()
+
+    def predictor_update_fn(self, u, t, dt, z=None):
+        """One predictor step from time ``t`` with step ``dt`` (reference sde.py:16-26 for ``em_sde``:
+        returns ``(x, x_mean)``; sde.py:331-336 for ``sscs_sde``: returns ``u``).  ``z`` optionally
+        supplies the pre-drawn N(0,1) noise (``em_sde``: one ``[B,2C,H,W]`` tensor; ``sscs_sde``: a pair,
+        first and second half-step); otherwise the in-kernel Philox generator draws it."""
+        lib = L.lib()
+        with torch.cuda.device(u.device):
+            tabs, state, net_in, B, chw, sdt, stream = self._single(u, t, dt)
+            step = (1 << 40) + self._single_calls          # Philox stream ids disjoint from sample()'s
+            f32 = lambda v: None if v is None else v.to(u.device, torch.float32).contiguous()
+            if self.KIND == "sscs_sde":
+                za, zb = (f32(z[0]), f32(z[1])) if z is not None else (None, None)
+                L.check(lib.psld_sscs_update(L.ptr(state), L.ptr(state), sdt, L.ptr(net_in), None, L.ptr(za),
+                                             None, None, C.byref(tabs.sscs[0]), L.STAGE_HALF_A, self.seed,
+                                             step, B, chw, stream), "psld_sscs_update")
+                e = self._score(net_in, tabs, B)
+                L.check(lib.psld_sscs_update(L.ptr(state), L.ptr(state), sdt, None, L.ptr(e), None,
+                                             L.ptr(zb), None, C.byref(tabs.sscs[0]),
+                                             L.STAGE_SCORE | L.STAGE_HALF_B, self.seed, step, B, chw,
+                                             stream), "psld_sscs_update")
+                self._keep = (za, zb, e, tabs)
+                return state
+            e = self._score(net_in, tabs, B)
+            zz = f32(z)
+            mean = torch.empty_like(state)
+            L.check(lib.psld_em_update(L.ptr(mean), L.ptr(state), sdt, None, L.ptr(e), None, 0,
+                                       C.byref(tabs.em[0]), self.seed, step, B, chw, stream),
+                    "psld_em_update")
+            L.check(lib.psld_em_update(L.ptr(state), L.ptr(state), sdt, None, L.ptr(e), L.ptr(zz),
+                                       0 if zz is not None else 1, C.byref(tabs.em[0]), self.seed, step,
+                                       B, chw, stream), "psld_em_update")
+            self._keep = (zz, e, tabs)
+            return state, mean
+
+    def denoising_fn(self, x, t, dt):
+        """``x + fbar(x, t) * dt`` without noise (reference sde.py:28-36, 338-348; ``sample()`` calls
+        it with ``t = T - eps, dt = eps``)."""
+        lib = L.lib()
+        with torch.cuda.device(x.device):
+            kind, self.KIND = self.KIND, "em_sde"
+            try:
+                tabs, state, net_in, B, chw, sdt, stream = self._single(x, t, dt)
+            finally:
+                self.KIND = kind
+            e = self._score(net_in, tabs, B)
+            L.check(lib.psld_em_update(L.ptr(state), L.ptr(state), sdt, None, L.ptr(e), None, 0,
+                                       C.byref(tabs.em[0]), self.seed, 0, B, chw, stream), "psld_em_update")
+            self._keep = (e, tabs)
+            return state
 
     def _embedding(self):
         return getattr(self.score_fn, "embedding_type", "fourier")

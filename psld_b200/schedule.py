@@ -236,12 +236,14 @@ class StepTables:
     """ctypes tables for one ``sample()`` call."""
 
     def __init__(self, sch: PSLDSchedule, ts, n: int, sampler: str, denoise: bool, eps: float,
-                 embedding: str = "fourier", merge_noise: bool = False):
+                 embedding: str = "fourier", merge_noise: bool = False, dt=None):
+        """``dt`` (optional f64 [n]) overrides ``ts[i+1] - ts[i]``: a standalone
+        ``predictor_update_fn(u, t, dt)`` call passes its step verbatim."""
         ts = torch.as_tensor(ts, dtype=_F64).cpu()
-        assert ts.numel() >= n + 1
+        assert ts.numel() >= n + 1 or (dt is not None and ts.numel() >= n)
         self.n = n
         t = ts[:n]
-        dt = ts[1:n + 1] - ts[:n]
+        dt = ts[1:n + 1] - ts[:n] if dt is None else torch.as_tensor(dt, dtype=_F64).cpu().reshape(-1)[:n]
         tau = sch.T - t
         self.sscs = self.em = None
         if n > 0:

@@ -7,7 +7,7 @@ PT="python -m pytest -q -rA --no-header -p no:cacheprovider --timeout 900 -m gpu
 run() { local name=$1; shift; local to=$1; shift
   echo "=== $name"; timeout "$to" "$@" > "gpurun_out/$name.log" 2>&1
   echo "rc=$? $(tail -n 1 gpurun_out/$name.log)"; }
-run x3_kernels 900 $PT tests/test_gpu_x3.py -k "split or conv_tc_x3 or memory_bound"
+run x3_kernels 900 $PT tests/test_gpu_x3.py -k "split or conv_tc_x3 or memory_bound or attention"
 run x3_net 1500 $PT tests/test_gpu_x3.py -k "forward or sampler or trajectory or full_batch"
 grep -h -E "rel-L2|PASSED|FAILED|ERROR|Error|error" gpurun_out/x3_kernels.log gpurun_out/x3_net.log | cut -c1-220 | tail -n 70
 if [ "${BENCH:-1}" = "1" ]; then

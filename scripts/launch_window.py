@@ -11,7 +11,7 @@ from psld_b200 import NCSNpp, cifar10_config  # noqa: E402
 from psld_b200.program import build_plan  # noqa: E402
 
 net = NCSNpp(cifar10_config()).eval()
-net.precision = "bf16"
+net.precision = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 L = build_plan(net, 2, 1, True, dry=True).launches
 pre = 3                      # prior_kernel + dtype cast + copy into the network input
 warm = 1 + 3 * (L + 1)       # first half-step + 3 warm-up steps (program + fused update)

@@ -14,6 +14,7 @@ from psld_b200 import _lib as L  # noqa: E402
 import _ops  # noqa: E402
 
 B = int(os.environ.get("ONE_OP_B", "256"))
+X3 = os.environ.get("ONE_OP_X3", "0") == "1"       # split-bf16 operands (bf16x3 tier)
 SHAPES = {   # name: (HW, C1, C2, Cout, ks, residual, temb, stats, gn)
     "qkv16": (16, 256, 0, 768, 1, False, False, False, False),
     "proj16": (16, 256, 0, 256, 1, True, False, True, False),
@@ -37,11 +38,12 @@ def main():
     reps = int(os.environ.get("ONE_OP_REPS", "20"))
     for name in sys.argv[1:]:
         hw, c1, c2, cout, ks, res, temb, stats, gn = SHAPES[name]
-        x1 = torch.randn(B, hw, hw, c1, generator=g).to(dev, torch.bfloat16)
-        x2 = torch.randn(B, hw, hw, c2, generator=g).to(dev, torch.bfloat16) if c2 else None
+        act = (lambda t: _ops.to_split(t.to(dev))) if X3 else (lambda t: t.to(dev, torch.bfloat16))
+        x1 = act(torch.randn(B, hw, hw, c1, generator=g))
+        x2 = act(torch.randn(B, hw, hw, c2, generator=g)) if c2 else None
         w = torch.randn(cout, c1 + c2, ks, ks, generator=g) * 0.05
         bias = torch.randn(cout, generator=g)
-        r = torch.randn(B, hw, hw, cout, generator=g).to(dev, torch.bfloat16) if res else None
+        r = act(torch.randn(B, hw, hw, cout, generator=g)) if res else None
         t = torch.randn(B, cout, generator=g).to(dev) if temb else None
         aff = torch.randn(B, c1 + c2, 2, generator=g).to(dev) if gn else None
         op, out, keep = _ops.conv_op(x1, x2, w, bias, residual=r, temb=t, temb_bstride=cout if temb else 0,
@@ -62,7 +64,7 @@ def main():
         flops = 2.0 * B * hw * hw * (c1 + c2) * ks * ks * cout
         med = ts[len(ts) // 2]
         print(f"{name}: median {med:.1f} us  min {ts[0]:.1f} us  {flops / med * 1e-6:.0f} TFLOP/s  "
-              f"finite={bool(torch.isfinite(out.float()).all())}", flush=True)
+              f"finite={bool(torch.isfinite(_ops.val(out).float()).all())}{' (x3: 3 MMAs per product)' if X3 else ''}", flush=True)
         L.lib().psld_op_release(op)
 
 

@@ -220,7 +220,11 @@ def attn_op(qkv, Cc, engine=L.ENGINE_SIMT, proj=None):
     if proj is None:
         return op, out
     w3, b3, x, scale = proj
-    wp = w3.to(qkv.device, torch.bfloat16).contiguous()
+    w3 = w3.to(qkv.device, torch.float32)
+    if isinstance(qkv, Split):          # weight planes [2][C out, C in]
+        hi = w3.to(torch.bfloat16)
+        w3 = torch.cat([hi.to(torch.float32), w3 - hi.to(torch.float32)], 0)
+    wp = w3.to(torch.bfloat16).contiguous()
     bp = b3.to(qkv.device, torch.float32).contiguous()
     mg = torch.zeros((N, Cc // 4, 2), dtype=torch.float64, device=qkv.device)
     op.i[L.ATTN_PROJ] = 1

@@ -84,6 +84,34 @@ def test_module_contract():
         net(x.cpu(), t.cpu())
 
 
+def test_checkpoint_to_samples_cifar10(golden_dir, tmp_path):
+    """Real-size checkpoint path on the GPU (sample.py:62-69): a Lightning-style .ckpt holding the
+    749-tensor CIFAR-10 state dict under ``score_fn.`` / ``ema_score_fn.`` -> ``load_checkpoint`` into
+    a module already on the GPU -> forward equals the reference's output for those weights ->
+    ``samples_to_uint8`` image writer arithmetic."""
+    from oracle.weights import fill_state_dict
+    from psld_b200 import NCSNpp, load_checkpoint, samples_to_uint8
+    cfg = _full(cifar10_config())
+    net = NCSNpp(cfg).eval().cuda()                 # default precision tier
+    assert net.precision == "bf16x3"
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 0)
+    assert len(sd) == 749
+    other = {k: v + 1.0 for k, v in list(sd.items())[:3]}
+    path = tmp_path / "cifar10_psld.ckpt"
+    torch.save({"state_dict": {**{"ema_score_fn." + k: v for k, v in sd.items()},
+                               **{"score_fn." + k: other.get(k, v) for k, v in sd.items()}},
+                "epoch": 2500, "global_step": 1}, path)
+    load_checkpoint(net, str(path), sample_from="target")
+    g = np.load(f"{golden_dir}/forward_cifar10_b3.npz")
+    y = net(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda())
+    err = rel_l2(y, torch.from_numpy(g["y"]))
+    print(f"checkpoint -> forward (CIFAR-10, {net.precision}): rel-L2 {err:.3e}")
+    assert err <= 5e-5
+    img = samples_to_uint8(torch.cat([y[:, :3] * 0.4, y[:, 3:]], 1).double())
+    ref = ((y[:, :3].double().cpu() * 0.4 * 0.5 + 0.5).permute(0, 2, 3, 1).numpy() * 255).clip(0, 255).astype(np.uint8)
+    assert img.shape == (3, 32, 32, 3) and np.array_equal(img.cpu().numpy(), ref)
+
+
 def test_in_place_weight_update_invalidates_plans():
     """A plan snapshots re-packed weights; an in-place parameter update (EMA / optimizer step /
     ``p.data.copy_``) must be picked up by the next call, as the reference module would."""

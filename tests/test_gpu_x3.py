@@ -101,7 +101,7 @@ def test_conv_tc_x3(case):
     # fp32 NCHW head output (no epilogue terms)
     op, out2, keep2 = conv_op(x1, x2, w, None, engine=L.ENGINE_TC, out_nchw_f32=True)
     run_op(op, prepare=True)
-    assert rel_l2(out2, conv_ref(x1, x2, w, None)) <= 1e-5
+    assert rel_l2(out2, conv_ref(x1, x2, w, None)) <= 2e-5
 
 
 @pytest.mark.parametrize("case", [(2, 17, 17, 256, 256), (3, 33, 33, 64, 256), (5, 9, 9, 128, 64)])
@@ -171,6 +171,46 @@ def test_memory_bound_kernels_on_split_tensors():
     q, kk, v = val(qkv).double().cpu().reshape(2, 256, 3 * Ca).split(Ca, -1)
     wgt = torch.softmax(q @ kk.transpose(1, 2) * Ca ** -0.5, -1)
     assert rel_l2(val(o).reshape(2, 256, Ca), wgt @ v) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 8, 8, 256), (2, 16, 16, 64), (1, 8, 16, 128),
+                                   (4, 8, 8, 64)])
+def test_attention_tc_x3(shape):
+    """tcgen05 attention core with split-bf16 q|k|v, P and output: three MMA groups per GEMM."""
+    N, H, W, Cc = shape
+    r = _rng(19)
+    qkv = _s(r.standard_normal((N, H, W, 3 * Cc)) * 1.5)
+    op, out = attn_op(qkv, Cc, engine=L.ENGINE_TC)
+    run_op(op, prepare=True)
+    q, k, v = val(qkv).double().cpu().reshape(N, H * W, 3 * Cc).split(Cc, dim=-1)
+    wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
+    ref = torch.einsum("bqk,bkc->bqc", wgt, v)
+    err = rel_l2(val(out).reshape(N, H * W, Cc), ref)
+    print(f"x3 attention {shape}: rel-L2 {err:.2e}")
+    assert err <= 2e-5, err
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 16, 8, 128), (5, 16, 16, 64), (1, 16, 16, 192)])
+def test_attention_tc_x3_fused_projection(shape):
+    """Attention core + NIN_3 projection + skip connection + GroupNorm statistics in one kernel
+    (AttnBlockpp, layerspp.py:82-91), split-bf16 tier, vs the fp64 definition."""
+    N, H, W, Cc = shape
+    r = _rng(23)
+    qkv = _s(r.standard_normal((N, H, W, 3 * Cc)) * 1.5)
+    x = _s(r.standard_normal((N, H, W, Cc)))
+    w3 = _t(r.standard_normal((Cc, Cc)) / np.sqrt(Cc))          # [out, in]
+    b3 = _t(0.1 * r.standard_normal(Cc))
+    op, out, keep = attn_op(qkv, Cc, engine=L.ENGINE_TC, proj=(w3, b3, x, 0.7071))
+    run_op(op, prepare=True)
+    q, k, v = val(qkv).double().cpu().reshape(N, H * W, 3 * Cc).split(Cc, dim=-1)
+    wgt = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * (int(Cc) ** -0.5), dim=-1)
+    o = torch.einsum("bqk,bkc->bqc", wgt, v)
+    ref = (o @ w3.double().cpu().t() + b3.double().cpu() + val(x).double().cpu().reshape(N, H * W, Cc)) * 0.7071
+    err = rel_l2(val(out).reshape(N, H * W, Cc), ref)
+    print(f"x3 attention+proj {shape}: rel-L2 {err:.2e}")
+    assert err <= 2e-5, err
+    mref = mg_ref(ref.reshape(N, H, W, Cc))
+    assert float((keep[-1].double().cpu() - mref).abs().max()) <= 2e-5 * float(mref.abs().max())
 
 
 # ------------------------------------------------------------------ whole network

@@ -146,6 +146,39 @@ def test_checkpoint_loader(tmp_path):
         select_score_fn_state({"foo.x": torch.zeros(1)}, "target")
 
 
+def test_checkpoint_loader_refuses_untrusted_pickles(tmp_path):
+    """Tensors-only checkpoints load with weights_only=True; one that pickles an arbitrary object
+    is refused unless the caller passes trust=True."""
+    from psld_b200 import load_checkpoint
+    cfg = tiny_config()
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}, 2)
+
+    class Hparams:          # what Lightning's save_hyperparameters can leave in a .ckpt
+        pass
+
+    path = tmp_path / "lightning_like.ckpt"
+    torch.save({"state_dict": {"ema_score_fn." + k: v for k, v in sd.items()}, "hyper_parameters": Hparams()},
+               path)
+    with pytest.raises(RuntimeError, match="trust=True"):
+        load_checkpoint(NCSNpp(cfg), str(path))
+    net = load_checkpoint(NCSNpp(cfg), str(path), trust=True)
+    assert torch.equal(net.state_dict()["all_modules.3.weight"], sd["all_modules.3.weight"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "cifar10", "celeba64"])
+def test_state_dict_contract_vs_reference(golden_dir, name):
+    """Checkpoint contract (wrapper.py:30-31, sample.py:62-69): same tensor names, shapes and ORDER as
+    the reference module for the shipped architectures (749 tensors for CIFAR-10, 571 for CelebA-64;
+    fixture written from the reference's own modules by oracle/make_golden.py)."""
+    import json
+    from psld_b200 import celeba64_config, cifar10_config
+    want = json.load(open(f"{golden_dir}/state_dict_contract.json"))[name]
+    cfg = {"tiny": tiny_config, "cifar10": cifar10_config, "celeba64": celeba64_config}[name]()
+    got = {k: list(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    assert list(got.keys()) == list(want.keys())
+    assert got == want
+
+
 def test_inpaint_and_vp_tables_vs_oracle():
     """Host coefficient tables of the two widened samplers against the oracle's scalar algebra
     (which is pinned on the reference's outputs in test_oracle_vs_golden.py)."""
