@@ -146,6 +146,10 @@ def test_checkpoint_loader(tmp_path):
         select_score_fn_state({"foo.x": torch.zeros(1)}, "target")
 
 
+class _Hparams:          # what Lightning's save_hyperparameters can leave in a .ckpt
+    pass
+
+
 def test_checkpoint_loader_refuses_untrusted_pickles(tmp_path):
     """Tensors-only checkpoints load with weights_only=True; one that pickles an arbitrary object
     is refused unless the caller passes trust=True."""
@@ -153,11 +157,8 @@ def test_checkpoint_loader_refuses_untrusted_pickles(tmp_path):
     cfg = tiny_config()
     sd = fill_state_dict({k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}, 2)
 
-    class Hparams:          # what Lightning's save_hyperparameters can leave in a .ckpt
-        pass
-
     path = tmp_path / "lightning_like.ckpt"
-    torch.save({"state_dict": {"ema_score_fn." + k: v for k, v in sd.items()}, "hyper_parameters": Hparams()},
+    torch.save({"state_dict": {"ema_score_fn." + k: v for k, v in sd.items()}, "hyper_parameters": _Hparams()},
                path)
     with pytest.raises(RuntimeError, match="trust=True"):
         load_checkpoint(NCSNpp(cfg), str(path))
