@@ -134,6 +134,16 @@ PSLD_API int psld_em_update(void* u_out, const void* u_in, int state_dtype, floa
                    const psld_score_step* coeffs /* host */, uint64_t seed, uint64_t step,
                    int64_t B, int64_t chw, psld_stream_t stream);
 
+/* Classifier-guided Euler-Maruyama step, ClassCondEulerMaruyamaSampler.predictor_update_fn
+ * (main/samplers/sde.py:73-100): fbar = -f + g^2 score + g^2 (guide * guide_scale), where guide is
+ * d/du log p(y | u, t) as fp32 [B,2C,H,W] (the caller's classifier gradient) and guide_scale the
+ * classifier temperature clf_temp; guide = NULL is psld_em_update.  z = NULL and use_philox = 0
+ * gives the guided mean x + fbar dt the reference uses for its denoising call (sde.py:112-117). */
+PSLD_API int psld_em_update_guided(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                          const float* eps, const float* guide, double guide_scale, const float* z,
+                          int use_philox, const psld_score_step* coeffs /* host */, uint64_t seed,
+                          uint64_t step, int64_t B, int64_t chw, psld_stream_t stream);
+
 /* One Split-Perturb-Combine step of the inpainting sampler ES3EulerMaruyamaInpainter
  * (main/samplers/sde.py:134-186; perturbation kernel PSLD._mean / cond_marginal_prob /
  * perturb_data, main/models/sde/psld.py:62-84,222-228,262-287), fused into one pass:

@@ -240,6 +240,8 @@ def main():
         return golden_full_size(R)
     if "--only-contract" in sys.argv:
         return golden_state_dict_contract(R)
+    if "--only-cc" in sys.argv:
+        return golden_cc(R)
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
     if "--only-vp" in sys.argv:
@@ -274,6 +276,7 @@ def main():
     golden_vp(R)
     golden_full_size(R)
     golden_state_dict_contract(R)
+    golden_cc(R)
 
 
 def vp_config(**ev):
@@ -299,6 +302,34 @@ def golden_vp(R):
         with NoiseBank(nb):
             out = S.sample(x0.clone(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
         _save(f"sampler_vp_em_fake_{tag}.npz", final=out.double().numpy(), ts=ts.numpy(), n=np.asarray(n),
+              B=np.asarray(B))
+
+
+def cc_config(**ev):
+    e = dict(sampler="cc_em_sde", n_discrete_steps=40)
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.data.image_size = 8
+    cfg["clf"] = dict(evaluation=dict(label_to_sample=3, clf_temp=2.5))
+    from psld_b200.config import Cfg
+    return Cfg(cfg)
+
+
+def golden_cc(R):
+    """Classifier-guided EM (cc_em_sde, sde.py:61-122): sampler algebra with the stand-in score network
+    and a stand-in differentiable classifier, uniform and quadratic stride."""
+    from oracle.weights import fake_classifier
+    for tag, kw in [("uniform", {}), ("quad_nodenoise", dict(stride_type="quadratic", denoise=False))]:
+        cfg = cc_config(**kw)
+        sde = R.PSLD(cfg)
+        ts, n = reference_time_grid(cfg)
+        B = 3
+        nb = noise_bank(n, (B, 6, 8, 8), 2)
+        u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+        S = R.get_module("samplers", "cc_em_sde")(cfg, sde, fake_score, fake_classifier)
+        with NoiseBank(nb):
+            out = S.sample(u0.clone(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+        _save(f"sampler_cc_em_fake_{tag}.npz", final=out.double().numpy(), ts=ts.numpy(), n=np.asarray(n),
               B=np.asarray(B))
 
 

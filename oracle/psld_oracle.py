@@ -14,6 +14,7 @@ reference repo (mandt-lab/PSLD, ``/root/reference``):
   * score from eps (fp32 coefficient cast) .... ``main/models/sde/psld.py:230-260``
   * forward / reverse drift, EM step, denoise . ``main/models/sde/psld.py:330-364``,
                                                 ``main/samplers/sde.py:16-58,338-370``
+  * classifier-guided EM (cc_em_sde) .......... ``main/samplers/sde.py:61-122``
   * time grid ................................. ``main/models/wrapper.py:51-54,101-114``
   * NCSN++ forward ............................ ``main/models/score_fn/song_sde/ncsnpp.py:287-438``
   * ResnetBlockBigGANpp / AttnBlockpp / NIN ... ``.../layerspp.py:75-91,242-274``, ``.../layers.py:531-540``
@@ -217,6 +218,42 @@ def em_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, record
                 record(i, u)
         if denoise:                                                # sde.py:28-36,52-57
             u = _denoise(sde, score_fn, u, eps)
+    return u
+
+
+def cc_em_sample(config, score_fn, clf_fn, u0, ts, n, noise, y, clf_temp, denoise=True, eps=1e-3,
+                 record=None):
+    """``ClassCondEulerMaruyamaSampler.sample`` (``sde.py:61-122``): Euler-Maruyama whose reverse
+    drift gets the classifier-guidance term ``g^2 * clf_temp * d/du log p(y | u, t)``
+    (``sde.py:82-93``; the classifier sees the REVERSE time ``t`` as float32, ``sde.py:84-87``).  The
+    denoising call is a predictor step at fl32(T - eps) whose MEAN (guidance included) is kept
+    (``sde.py:112-117``); its noise draw is discarded.  ``noise``: n tensors [B,2C,H,W]."""
+    sde = PSLDScalars(config)
+    u = u0.to(torch.float64)
+    C = u.shape[1] // 2
+    idx = torch.as_tensor(y).expand(u.shape[0]) if not torch.is_tensor(y) or y.dim() == 0 else y
+
+    def guided_drift(u, t):
+        fbar, (gx, gm) = reverse_drift(sde, score_fn, u, t)
+        with torch.enable_grad():
+            x_in = u.clone().requires_grad_()
+            logits = clf_fn(x_in.to(torch.float32), _tvec(u, float(np.float32(t))))
+            sel = F.log_softmax(logits, dim=-1)[range(len(logits)), idx]
+            grad = torch.autograd.grad(sel.sum(), x_in)[0] * clf_temp
+        g2 = torch.cat([torch.full_like(u[:, :C], gx ** 2), torch.full_like(u[:, C:], gm ** 2)], dim=1)
+        return fbar + g2 * grad, (gx, gm)
+
+    with torch.no_grad():
+        for i in range(n):
+            t, dt = float(ts[i]), float(ts[i + 1] - ts[i])
+            f, (gx, gm) = guided_drift(u, t)
+            g = torch.cat([torch.full_like(u[:, :C], gx), torch.full_like(u[:, C:], gm)], dim=1)
+            u = (u + f * dt) + g * math.sqrt(dt) * noise[i].to(torch.float64)
+            if record is not None:
+                record(i, u)
+        if denoise:
+            f, _ = guided_drift(u, float(np.float32(sde.T - eps)))
+            u = u + f * float(np.float32(eps))
     return u
 
 

@@ -15,7 +15,8 @@ from .registry import get_module, install, register_module
 from .schedule import PSLDSchedule, StepTables, time_grid
 from .sde import PSLD, VPSDE
 from .ncsnpp import NCSNpp
-from .samplers import EulerMaruyamaSampler, InpaintEulerMaruyamaSampler, Sampler, SSCSSampler
+from .samplers import (ClassCondEulerMaruyamaSampler, EulerMaruyamaSampler, InpaintEulerMaruyamaSampler, Sampler,
+                       SSCSSampler)
 from .io import load_checkpoint, samples_to_uint8, select_score_fn_state
 
 register_module(category="score_fn", name="ncsnpp_b200")(NCSNpp)
@@ -23,7 +24,8 @@ register_module(category="score_fn", name="ncsnpp_b200")(NCSNpp)
 __all__ = [
     "Cfg", "make_config", "tiny_config", "mid_config", "cifar10_config", "celeba64_config",
     "register_module", "get_module", "install", "PSLDSchedule", "StepTables", "time_grid",
-    "PSLD", "VPSDE", "NCSNpp", "SSCSSampler", "EulerMaruyamaSampler", "InpaintEulerMaruyamaSampler", "Sampler",
+    "PSLD", "VPSDE", "NCSNpp", "SSCSSampler", "EulerMaruyamaSampler", "InpaintEulerMaruyamaSampler",
+    "ClassCondEulerMaruyamaSampler", "Sampler",
     "load_checkpoint", "samples_to_uint8", "select_score_fn_state",
 ]
 __version__ = "0.1.0"

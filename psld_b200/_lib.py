@@ -93,6 +93,10 @@ EXPORTS = {
     "psld_em_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.POINTER(ScoreStep), C.c_uint64, C.c_uint64,
                                  C.c_int64, C.c_int64, C.c_void_p]),
+    "psld_em_update_guided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                        C.POINTER(ScoreStep), C.c_uint64, C.c_uint64, C.c_int64,
+                                        C.c_int64, C.c_void_p]),
     "psld_inpaint_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(InpaintStep), C.c_uint64,
                                        C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),

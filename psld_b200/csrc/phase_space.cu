@@ -37,11 +37,14 @@ struct Philox {
     }
     return c;
   }
-  // 4 standard normals from one draw (Box-Muller on two uniform pairs).  Full-accuracy logf and
-  // sincospif (not the MUFU approximations __logf / __sincosf, whose absolute error in the angle
-  // grows with the argument): this generator produces every injected-noise sample of a throughput
-  // run, and its cost is invisible next to the network.  The radius uniform is (n + 0.5) 2^-32 in
-  // (0, 1): tail reaches sqrt(-2 ln 2^-33) = 6.76 sigma.
+  // 4 standard normals from one draw (Box-Muller on two uniform pairs).  The radius uses the
+  // full-accuracy logf (the tail is where a relative error of the logarithm would show); the angle
+  // is drawn on [-pi, pi), the interval on which sin.approx / cos.approx are specified to 2^-21.4
+  // absolute error, i.e. below the fp32 rounding of the state the noise is added to
+  // (-DPSLD_RNG_EXACT_TRIG switches to sincospif; it costs 96 more instructions per 4 pairs and
+  // takes the fused update at 2^24 pairs from bandwidth-bound to issue-bound).  The radius uniform
+  // is (n + 0.5) 2^-32 in (0, 1): the tail reaches sqrt(-2 ln 2^-33) = 6.76 sigma.  Statistical
+  // checks on 2.5e7 draws per stream: tests/test_gpu_kernels.py::test_philox_normal_quality.
   static __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t stream, uint64_t index) {
     uint4 r = draw(seed, stream, index);
     const float k = 2.3283064365386963e-10f;  // 2^-32
@@ -51,8 +54,15 @@ struct Philox {
     u2 = fminf(u2, 0.99999994f);
     float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
     float sa, ca, sb, cb;
+#ifdef PSLD_RNG_EXACT_TRIG
     sincospif(2.0f * u1, &sa, &ca);
     sincospif(2.0f * u3, &sb, &cb);
+#else
+    // angle uniform on [-pi, pi): the range where sin.approx / cos.approx are specified to
+    // 2^-21.4 ABSOLUTE error (the former code fed them [0, 2 pi), outside that range)
+    __sincosf(6.283185307179586f * (u1 - 0.5f), &sa, &ca);
+    __sincosf(6.283185307179586f * (u3 - 0.5f), &sb, &cb);
+#endif
     return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
   }
 };
@@ -248,6 +258,8 @@ struct EmParams {
   uint64_t seed, step;
   int64_t B, chw;
   int use_philox;
+  const float* guide;      // optional [B,2C,H,W]: fbar += g^2 * (guide * guide_scale)   (sde.py:86-93)
+  double guide_scale;
 };
 
 template <typename S>
@@ -258,6 +270,8 @@ __device__ __forceinline__ void em_update_body(S* __restrict__ u_out, const S* _
   const S g2x = (S)p.c.g2_x, g2m = (S)p.c.g2_m, dt = (S)p.c.dt;
   const S gsx = (S)p.c.gs_x, gsm = (S)p.c.gs_m;
   const bool noisy = (p.z != nullptr) || p.use_philox;
+  const bool guided = p.guide != nullptr;
+  const S gsc = (S)p.guide_scale;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = v / (p.chw >> 2);
@@ -269,6 +283,13 @@ __device__ __forceinline__ void em_update_body(S* __restrict__ u_out, const S* _
     if (noisy) get_noise(p.z, p.seed, p.step, b, j, p.chw, zx, zm);
     const float exa[4] = {ex.x, ex.y, ex.z, ex.w}, ema[4] = {em.x, em.y, em.z, em.w};
     const float zxa[4] = {zx.x, zx.y, zx.z, zx.w}, zma[4] = {zm.x, zm.y, zm.z, zm.w};
+    float gxa[4] = {0.f, 0.f, 0.f, 0.f}, gma[4] = {0.f, 0.f, 0.f, 0.f};
+    if (guided) {
+      const float4 a = *reinterpret_cast<const float4*>(p.guide + ox);
+      const float4 c = *reinterpret_cast<const float4*>(p.guide + ox + p.chw);
+      gxa[0] = a.x; gxa[1] = a.y; gxa[2] = a.z; gxa[3] = a.w;
+      gma[0] = c.x; gma[1] = c.y; gma[2] = c.z; gma[3] = c.w;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const S x = xs.v[i], m = ms.v[i];
@@ -276,8 +297,12 @@ __device__ __forceinline__ void em_update_body(S* __restrict__ u_out, const S* _
       score_from_eps(p.c, exa[i], ema[i], sx, sm);
       const S fx = hb * (mi * m - ga * x);              // psld.py:336
       const S fm = hb * (-nu * m - x);                  // psld.py:337
-      const S fbx = -fx + g2x * (S)sx;                  // psld.py:359
-      const S fbm = -fm + g2m * (S)sm;
+      S fbx = -fx + g2x * (S)sx;                        // psld.py:359
+      S fbm = -fm + g2m * (S)sm;
+      if (guided) {                                     // classifier guidance, sde.py:93
+        fbx = fbx + g2x * ((S)gxa[i] * gsc);
+        fbm = fbm + g2m * ((S)gma[i] * gsc);
+      }
       S nx = x + fbx * dt, nm = m + fbm * dt;           // sde.py:23
       if (noisy) {
         nx = nx + gsx * (S)zxa[i];                      // sde.py:24-25
@@ -317,6 +342,7 @@ em_update_table_kernel(S* __restrict__ u_out, const S* __restrict__ u_in, const 
   if (threadIdx.x == 0) {
     p.eps = pp.eps; p.z = pp.z; p.net_in = pp.net_in; p.seed = pp.seed; p.step = (uint64_t)step;
     p.B = pp.B; p.chw = pp.chw; p.use_philox = pp.use_philox;
+    p.guide = pp.guide; p.guide_scale = pp.guide_scale;
   }
   __syncthreads();
   em_update_body<S>(u_out, u_in, p);
@@ -445,6 +471,15 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
                               const float* eps, const float* z, int use_philox,
                               const psld_score_step* coeffs, uint64_t seed, uint64_t step,
                               int64_t B, int64_t chw, psld_stream_t stream) {
+  return psld_em_update_guided(u_out, u_in, state_dtype, net_in, eps, nullptr, 0.0, z, use_philox, coeffs,
+                               seed, step, B, chw, stream);
+}
+
+extern "C" int psld_em_update_guided(void* u_out, const void* u_in, int state_dtype, float* net_in,
+                                     const float* eps, const float* guide, double guide_scale,
+                                     const float* z, int use_philox, const psld_score_step* coeffs,
+                                     uint64_t seed, uint64_t step, int64_t B, int64_t chw,
+                                     psld_stream_t stream) {
   PSLD_CHECK_ARG(u_out && u_in && coeffs && eps, "psld_em_update: null pointer");
   PSLD_CHECK_ARG(B > 0 && chw > 0 && chw % 4 == 0, "psld_em_update: need chw %% 4 == 0");
   PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32,
@@ -454,6 +489,7 @@ extern "C" int psld_em_update(void* u_out, const void* u_in, int state_dtype, fl
   p.table = nullptr; p.step_ptr = nullptr;
   p.eps = eps; p.z = z; p.net_in = net_in; p.seed = seed; p.step = step;
   p.B = B; p.chw = chw; p.use_philox = use_philox;
+  p.guide = guide; p.guide_scale = guide_scale;
   const int grid = grid_for(B * (chw / 4));
   cudaStream_t s = (cudaStream_t)stream;
   if (state_dtype == PSLD_F64)

@@ -392,6 +392,96 @@ class EulerMaruyamaSampler(_FusedSampler):
     KIND = "em_sde"
 
 
+@register_module(category="samplers", name="cc_em_sde_b200")
+class ClassCondEulerMaruyamaSampler(_FusedSampler):
+    """Classifier-guided Euler-Maruyama sampler (reference ``ClassCondEulerMaruyamaSampler``,
+    sde.py:61-122): ``cls(config, sde, score_fn, clf_fn, corrector_fn=None)``; every predictor step adds
+    ``g^2 * clf_temp * d/du log p(y | u, t)`` to the reverse drift, with
+    ``y = config.clf.evaluation.label_to_sample`` and ``clf_temp = config.clf.evaluation.clf_temp``.
+
+    The classifier is the caller's differentiable module (the reference's ``NCSNppClassifier`` is
+    outside the hot-path scope); its input gradient is taken with
+    ``torch.autograd.grad`` exactly as the reference does (sde.py:82-90: float32 input, REVERSE time
+    ``t`` as float32, ``log_softmax`` then the selected class).  The score network call and the guided
+    update (``psld_em_update_guided``: drift + guidance + diffusion in one pass) run on this library.
+    The denoising call keeps the guided MEAN of one more predictor step (sde.py:112-117)."""
+    KIND = "em_sde"
+
+    def __init__(self, config, sde, score_fn, clf_fn, corrector_fn=None):
+        super().__init__(config, sde, score_fn, corrector_fn=corrector_fn)
+        if self.vp is not None:
+            raise ValueError("cc_em_sde is defined for the PSLD SDE")
+        self.clf_fn = clf_fn
+        ev = config.clf.evaluation
+        self.y = ev.label_to_sample
+        self.clf_temp = float(ev.clf_temp)
+
+    def _guidance(self, state, t):
+        """d/du log p(y | u, t) as fp32 (sde.py:82-90)."""
+        B = state.shape[0]
+        with torch.inference_mode(False), torch.enable_grad():
+            x_in = state.detach().clone().requires_grad_()
+            tt = torch.full((B,), float(t), dtype=torch.float32, device=state.device)
+            logits = self.clf_fn(x_in.to(torch.float32), tt)
+            log_probs = torch.nn.functional.log_softmax(logits, dim=-1)
+            selected = log_probs[range(len(logits)), self.y]
+            grad = torch.autograd.grad(selected.sum(), x_in)[0]
+        return grad.detach().to(torch.float32).contiguous()
+
+    def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
+        lib = L.lib()
+        n = int(n_discrete_steps)
+        self.nfe = n
+        self._next_seed()
+        if isinstance(self.score_fn, NCSNpp):
+            dev = next(self.score_fn.parameters()).device
+        else:
+            dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
+        if batch.dim() != 4 or batch.shape[1] % 2:
+            raise ValueError(f"expected a [B,2C,H,W] phase-space batch, got {tuple(batch.shape)}")
+        B, C2, H, W = batch.shape
+        chw = (C2 // 2) * H * W
+        if chw % 4:
+            raise ValueError("C*H*W must be a multiple of 4")
+        with torch.no_grad(), torch.cuda.device(dev):
+            state = batch.to(device=dev, dtype=self.state_dtype).contiguous().clone()
+            ts64 = ts.detach().to("cpu", torch.float64)
+            tabs = StepTables(self.schedule, ts64, n, "em_sde", bool(denoise), float(eps), self._embedding())
+            noise = None
+            if self.noise is not None:
+                noise = self.noise.to(device=dev, dtype=torch.float32).contiguous()
+                if noise.shape[0] < n or tuple(noise.shape[1:]) != (B, C2, H, W):
+                    raise ValueError(f"noise bank must be [{n},{B},{C2},{H},{W}], got {tuple(noise.shape)}")
+            record = None
+            if self.record is not None:
+                record = torch.empty(n, B, C2, H, W, dtype=self.state_dtype, device=dev)
+            net_in = state.to(torch.float32)
+            tau32 = tabs.tau32.to(dev)
+            sdt = L.dtype_code(self.state_dtype)
+            stream = L.stream_ptr(dev)
+            sp, ip = L.ptr(state), L.ptr(net_in)
+            # reverse times the classifier sees: ts[i], then fl32(T - eps) for the denoising call
+            t_den = float(torch.tensor(self.schedule.T - float(eps), dtype=torch.float32))
+            for i in range(n + (1 if denoise else 0)):
+                e = self.score_fn(net_in, tau32[i].expand(B)).to(torch.float32).contiguous()
+                g = self._guidance(state, float(ts64[i]) if i < n else t_den)
+                last = i == n
+                z = L.ptr(noise[i]) if (noise is not None and not last) else None
+                philox = 1 if (noise is None and not last) else 0
+                co = tabs.em[i] if not last else tabs.den
+                L.check(lib.psld_em_update_guided(sp, sp, sdt, ip, L.ptr(e), L.ptr(g), self.clf_temp, z,
+                                                  philox, C.byref(co), self.seed, i, B, chw, stream),
+                        "psld_em_update_guided")
+                if not last:
+                    self._post_step(state, net_in, record, i, ts)
+            if record is not None:
+                self.record = record
+            self._keep = (tabs, noise, net_in)
+        return state
+
+
 @register_module(category="samplers", name="ip_em_sde_b200")
 class InpaintEulerMaruyamaSampler(_FusedSampler):
     """Euler-Maruyama inpainting sampler (reference ``ES3EulerMaruyamaInpainter``,

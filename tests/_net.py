@@ -43,3 +43,16 @@ def vp_config(**ev):
     cfg.model.score_fn.update(in_ch=3, out_ch=3)
     cfg.data.image_size = 8
     return cfg
+
+
+def cc_config(**ev):
+    """Classifier-guidance config of oracle/make_golden.py::cc_config (``config.clf.evaluation`` keys of
+    the reference's class_cond_sample.py)."""
+    from psld_b200 import tiny_config
+    from psld_b200.config import Cfg
+    e = dict(sampler="cc_em_sde", n_discrete_steps=40)
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.data.image_size = 8
+    cfg["clf"] = dict(evaluation=dict(label_to_sample=3, clf_temp=2.5))
+    return Cfg(cfg)

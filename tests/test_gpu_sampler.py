@@ -298,6 +298,36 @@ def test_inpaint_sampler_vs_reference_golden(golden_dir, mode):
     assert rel_l2(out32, ref) <= 2e-5
 
 
+@pytest.mark.parametrize("tag,kw", [("uniform", {}), ("quad_nodenoise", dict(stride_type="quadratic", denoise=False))])
+def test_class_conditional_sampler_vs_reference_golden(golden_dir, tag, kw):
+    """cc_em_sde (sde.py:61-122): guided drift + EM update in one fused pass, classifier gradient by
+    autograd through the caller's classifier, vs the reference's own output; then Philox noise."""
+    from _net import cc_config
+    from oracle.weights import fake_classifier
+    from psld_b200 import ClassCondEulerMaruyamaSampler
+    g = np.load(f"{golden_dir}/sampler_cc_em_fake_{tag}.npz")
+    cfg = cc_config(**kw)
+    ts, n = time_grid(cfg)
+    assert n == int(g["n"])
+    B = int(g["B"])
+    u0, nb = sampler_inputs(cfg, B, n, "em_sde")
+    S = ClassCondEulerMaruyamaSampler(cfg, PSLD(cfg), fake_score, fake_classifier)
+    S.state_dtype = torch.float64
+    S.noise = torch.stack(nb)
+    out = S.sample(u0.cuda(), ts.cuda(), n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["final"])
+    e, m = rel_l2(out, ref), max_rel(out, ref)
+    print(f"cc_em_sde {tag}: rel-L2 {e:.3e} max-abs/max|ref| {m:.3e}")
+    assert e <= 1e-6 and m <= 1e-6
+    S.noise = None
+    a = S.sample(u0.cuda(), ts.cuda(), n)
+    assert torch.isfinite(a).all()
+    with torch.inference_mode():          # Lightning's predict loop runs under inference_mode
+        b = S.sample(u0.cuda(), ts.cuda(), n)
+    assert torch.isfinite(b).all()
+
+
 def test_inpaint_sampler_philox_keeps_known_region():
     """Device-drawn prior and noise: reproducible, and the known region of the denoised result is
     the perturbation mean of x_0 (HSM), i.e. x_0 scaled by the mean coefficient at tau = eps."""

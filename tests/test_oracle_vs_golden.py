@@ -188,3 +188,28 @@ def test_vp_sampler_algebra(golden_dir, tag, kw):
                          denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
     ref = g["final"]
     assert np.abs(out.numpy() - ref).max() <= 5e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag,kw", [("uniform", {}), ("quad_nodenoise", dict(stride_type="quadratic", denoise=False))])
+def test_cc_sampler_algebra(golden_dir, tag, kw):
+    """Oracle restatement of ClassCondEulerMaruyamaSampler (sde.py:61-122) vs the reference's output
+    (stand-in score network and stand-in differentiable classifier)."""
+    from _net import cc_config
+    from oracle.weights import fake_classifier
+    g = np.load(f"{golden_dir}/sampler_cc_em_fake_{tag}.npz")
+    cfg = cc_config(**kw)
+    ts, n = O.time_grid(cfg)
+    assert n == int(g["n"])
+    B = int(g["B"])
+    sde = O.PSLDScalars(cfg)
+    u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+    ev = cfg.clf.evaluation
+    out = O.cc_em_sample(cfg, fake_score, fake_classifier, u0, ts, n, noise_bank(n, (B, 6, 8, 8), 2),
+                         ev.label_to_sample, ev.clf_temp, denoise=cfg.evaluation.denoise,
+                         eps=cfg.evaluation.eval_eps)
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-7 * np.abs(ref).max()
+    # the guidance term matters: without it the end state differs visibly
+    plain = O.em_sample(cfg, fake_score, u0, ts, n, noise_bank(n, (B, 6, 8, 8), 2),
+                        denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
+    assert np.abs(plain.numpy() - ref).max() >= 1e-3 * np.abs(ref).max()
