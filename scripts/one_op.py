@@ -20,6 +20,7 @@ SHAPES = {   # name: (HW, C1, C2, Cout, ks, residual, temb, stats, gn)
     "proj16": (16, 256, 0, 256, 1, True, False, True, False),
     "c32": (32, 256, 0, 256, 3, True, False, True, False),
     "c32t": (32, 256, 0, 256, 3, False, True, True, False),
+    "c32cat": (32, 256, 256, 256, 3, False, True, True, False),
     "c16": (16, 256, 0, 256, 3, True, False, True, False),
     "c8": (8, 256, 0, 256, 3, True, False, True, False),
     "c8cat": (8, 256, 256, 256, 3, False, True, True, False),
