@@ -364,7 +364,7 @@ def gpu_eager_baseline(cfg, sde_cfg_B, dev, steps=2):
     H = cfg.data.image_size
     shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
     sd = {k: v.to(dev) for k, v in fill_state_dict(shapes, 0).items()}
-    score = lambda u, t: O.ncsnpp_forward(cfg, sd, u, t)
+    score = lambda u, t: O.ncsnpp_forward(cfg, sd, u, t.to(u.device))
     ts, n = O.time_grid(cfg)
     u0 = prior((B, 3, H, H), 0.5, 1).to(dev)
     out = {}

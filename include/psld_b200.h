@@ -182,6 +182,29 @@ PSLD_API int psld_vp_em_update(void* x_out, const void* x_in, int state_dtype, f
                                const psld_vp_step* coeffs /* host */, uint64_t seed, uint64_t step,
                                int64_t n, psld_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * 1b. Probability-flow ODE sampler BBODESampler (main/samplers/ode.py:41-76): the reference hands
+ * ode_fn = reverse_sde(..., probability_flow=True) (psld.py:345-364) to torchdiffeq==0.2.3
+ * odeint(method="scipy_solver") = scipy.integrate.solve_ivp(RK45) (Dormand-Prince 5(4) with scipy's
+ * step-size control), which is absent from the reference tree; psld_b200/ode.py restates that driver
+ * on the host and runs every vector operation on the device through these three kernels.
+ * ---------------------------------------------------------------------------------- */
+/* fbar = -f + g^2 (score_scale * score), float64 out [B,2C,H,W]; u in state_dtype (f64 | f32). */
+PSLD_API int psld_reverse_drift(double* out, const void* u, int state_dtype, const float* eps,
+                                const psld_score_step* coeffs /* host */, double score_scale,
+                                int64_t B, int64_t chw, psld_stream_t stream);
+/* out = y + h * sum_{j < terms} coef[j] K[j]; K = [terms, n] float64, coef on the HOST (terms <= 8);
+ * out32 (optional) receives the float32 rounding of the same values (the float32-batch view of the
+ * state = the next network input); out may be NULL when only out32 is wanted. */
+PSLD_API int psld_rk_combine(double* out, float* out32, const double* y, const double* K,
+                             const double* coef /* host */, int terms, double h, int64_t n,
+                             psld_stream_t stream);
+/* *sum_out += sum_i ((h sum_j e[j] K[j][i]) / (atol + max(|y_i|, |y_new_i|) rtol))^2  (the RK error
+ * norm of scipy's RungeKutta._estimate_error_norm is sqrt(sum / n)); sum_out zeroed by the caller. */
+PSLD_API int psld_rk_error(const double* y, const double* y_new, const double* K,
+                           const double* e /* host */, int terms, double h, double atol, double rtol,
+                           int64_t n, double* sum_out, psld_stream_t stream);
+
 /* PSLD.prior_sampling (psld.py:366-370) on device: x ~ N(0,1), m ~ N(0, M); fp32 NCHW. */
 PSLD_API int psld_prior_sample(float* u, double m_std, uint64_t seed, int64_t B, int64_t chw,
                       psld_stream_t stream);

@@ -242,6 +242,8 @@ def main():
         return golden_state_dict_contract(R)
     if "--only-cc" in sys.argv:
         return golden_cc(R)
+    if "--only-ode" in sys.argv:
+        return golden_ode(R)
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
     if "--only-vp" in sys.argv:
@@ -277,6 +279,7 @@ def main():
     golden_full_size(R)
     golden_state_dict_contract(R)
     golden_cc(R)
+    golden_ode(R)
 
 
 def vp_config(**ev):
@@ -331,6 +334,31 @@ def golden_cc(R):
             out = S.sample(u0.clone(), ts, n, denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
         _save(f"sampler_cc_em_fake_{tag}.npz", final=out.double().numpy(), ts=ts.numpy(), n=np.asarray(n),
               B=np.asarray(B))
+
+
+def ode_config(**ev):
+    e = dict(sampler=dict(name="bb_ode", solver="RK45", rtol=1e-5, atol=1e-5))
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.data.image_size = 8
+    return cfg
+
+
+def golden_ode(R):
+    """bb_ode (ode.py:41-76) through the restated torchdiffeq scipy_solver wrapper (ref_loader.py): exact
+    Gaussian-data score (stable reverse dynamics), the tolerances of the shipped scripts (1e-5 CelebA /
+    ablations, 1e-4 CIFAR)."""
+    from oracle.weights import gaussian_score_fn
+    for tag, tol, den in [("tol1e-5", 1e-5, True), ("tol1e-4_nodenoise", 1e-4, False)]:
+        cfg = ode_config(sampler=dict(name="bb_ode", solver="RK45", rtol=tol, atol=tol), denoise=den)
+        sde = R.PSLD(cfg)
+        B = 3
+        u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+        S = R.get_module("samplers", "bb_ode")(cfg, sde, gaussian_score_fn(cfg))
+        out = S.sample(u0.clone(), None, 0, denoise=den, eps=cfg.evaluation.eval_eps)
+        print(tag, "nfe", S.nfe, out.dtype, "std of x", float(out[:, :3].std()))
+        _save(f"sampler_bb_ode_gauss_{tag}.npz", final=out.double().numpy(), nfe=np.asarray(S.nfe),
+              B=np.asarray(B), tol=np.asarray(tol))
 
 
 def golden_inpaint_all(R):

@@ -15,6 +15,8 @@ reference repo (mandt-lab/PSLD, ``/root/reference``):
   * forward / reverse drift, EM step, denoise . ``main/models/sde/psld.py:330-364``,
                                                 ``main/samplers/sde.py:16-58,338-370``
   * classifier-guided EM (cc_em_sde) .......... ``main/samplers/sde.py:61-122``
+  * probability-flow ODE sampler (bb_ode) ..... ``main/samplers/ode.py:8-76`` (solver: scipy RK45, as
+                                                called by torchdiffeq 0.2.3's scipy_solver wrapper)
   * time grid ................................. ``main/models/wrapper.py:51-54,101-114``
   * NCSN++ forward ............................ ``main/models/score_fn/song_sde/ncsnpp.py:287-438``
   * ResnetBlockBigGANpp / AttnBlockpp / NIN ... ``.../layerspp.py:75-91,242-274``, ``.../layers.py:531-540``
@@ -255,6 +257,49 @@ def cc_em_sample(config, score_fn, clf_fn, u0, ts, n, noise, y, clf_temp, denois
             f, _ = guided_drift(u, float(np.float32(sde.T - eps)))
             u = u + f * float(np.float32(eps))
     return u
+
+
+def pflow_drift(sde: PSLDScalars, score_fn, u: torch.Tensor, t: float):
+    """``reverse_sde(u, t, score_fn, probability_flow=True)[0]`` (``psld.py:345-364``) with ``u`` in its own
+    dtype: python scalars times a float32 state stay float32 inside the drift bracket (``psld.py:336-337``),
+    the float64 ``beta_t`` promotes afterwards; the fp32 score is halved in fp32."""
+    tau = sde.T - t
+    x, m = torch.chunk(u, 2, dim=1)
+    beta = sde.beta_t(tau)
+    fx = (0.5 * beta) * (sde.m_inv * m - sde.gamma * x).to(torch.float64)
+    fm = (0.5 * beta) * (-sde.nu * m - x).to(torch.float64)
+    gx2, gm2 = math.sqrt(beta * sde.gamma) ** 2, math.sqrt(beta * sde.m * sde.nu) ** 2
+    eps = score_fn(u.to(torch.float32), _tvec(u, float(np.float32(tau))))
+    sx, sm = torch.chunk(0.5 * score_from_eps(sde, eps, tau), 2, dim=1)
+    return torch.cat([-fx + gx2 * sx, -fm + gm2 * sm], dim=1)
+
+
+def bb_ode_sample(config, score_fn, u0, rtol, atol, solver="RK45", denoise=True, eps=1e-3):
+    """``BBODESampler.sample`` (``ode.py:41-76``): probability-flow ODE integrated from t = 0 to T - eps
+    by ``torchdiffeq.odeint(method="scipy_solver")``, restated as the ``scipy.integrate.solve_ivp`` call
+    that wrapper makes (torchdiffeq 0.2.3 is absent from the reference tree): float64 state on the
+    host, ``(t, y)`` rounded to ``u0``'s dtype for every evaluation.  Returns ``(x, nfe)``."""
+    from scipy.integrate import solve_ivp
+    sde = PSLDScalars(config)
+    shape, dtype = u0.shape, u0.dtype
+    nfe = [0]
+
+    def fun(t, y):
+        nfe[0] += 1
+        tt = float(torch.tensor(t).to(dtype))
+        u = torch.tensor(y).to(dtype).reshape(shape)
+        with torch.no_grad():
+            return pflow_drift(sde, score_fn, u, tt).numpy().reshape(-1)
+
+    t_end = sde.T - eps
+    sol = solve_ivp(fun, t_span=[0.0, t_end], y0=u0.numpy().reshape(-1), t_eval=np.asarray([0.0, t_end]),
+                    method=solver, rtol=rtol, atol=atol, max_step=float("inf"))
+    x = torch.tensor(sol.y).T[-1].to(dtype).reshape(shape)
+    if denoise:                                                    # ode.py:36-39,66-75
+        with torch.no_grad():
+            x = x + pflow_drift(sde, score_fn, x, sde.T - eps) * eps
+        nfe[0] += 1
+    return x, nfe[0]
 
 
 def sscs_sample(config, score_fn, u0, ts, n, noise, denoise=True, eps=1e-3, record=None):

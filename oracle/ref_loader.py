@@ -10,7 +10,8 @@ The reference needs three stubs to import on CPU without its absent dependencies
   1. ``torch.utils.cpp_extension.load`` → no-op (``op/upfirdn2d.py:10``,
      ``op/fused_act.py:11`` JIT-compile at import; CPU tensors then take
      ``upfirdn2d_native``, ``op/upfirdn2d.py:146-149``);
-  2. a dummy ``torchdiffeq`` module (``samplers/ode.py:2``);
+  2. a stand-in ``torchdiffeq`` module (``samplers/ode.py:2``) whose ``odeint`` restates the
+     ``scipy_solver`` wrapper of torchdiffeq 0.2.3 (the only method the reference calls);
   3. a bare ``models`` package so ``models/__init__.py`` (pytorch_lightning) is skipped.
 """
 from __future__ import annotations
@@ -21,6 +22,37 @@ import types
 
 REF_ROOT = os.environ.get("PSLD_REFERENCE_ROOT", "/root/reference")
 _loaded = None
+
+
+def scipy_solver_odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, **unused):
+    """Restatement of the ONE code path of ``torchdiffeq==0.2.3`` (``Pipfile:8``; absent here and not
+    part of the reference tree) that the reference uses: ``odeint(..., method="scipy_solver",
+    options={"solver": ...})`` = ``ScipyWrapperODESolver`` (torchdiffeq/_impl/scipy_wrapper.py): the state
+    is flattened to a float64-castable numpy vector, ``scipy.integrate.solve_ivp`` drives the solver
+    with ``t_eval = t``, and every function evaluation converts ``(t, y)`` to tensors of ``y0``'s
+    device AND dtype before calling ``func``; the solution comes back in ``y0``'s dtype."""
+    import numpy as np
+    import torch
+    from scipy.integrate import solve_ivp
+    assert method == "scipy_solver", method
+    solver = (options or {}).get("solver", "LSODA")
+    dtype, device, shape = y0.dtype, y0.device, y0.shape
+    y0n = y0.detach().cpu().numpy().reshape(-1)
+
+    def np_func(tt, y):
+        tt = torch.tensor(tt).to(device, dtype)
+        y = torch.reshape(torch.tensor(y).to(device, dtype), shape)
+        with torch.no_grad():
+            f = func(tt, y)
+        return f.detach().cpu().numpy().reshape(-1)
+
+    if t.numel() == 1:
+        return torch.tensor(y0n)[None].to(device, dtype)
+    tn = t.detach().cpu().numpy()
+    sol = solve_ivp(np_func, t_span=[tn.min(), tn.max()], y0=y0n, t_eval=tn, method=solver, rtol=rtol,
+                    atol=atol, max_step=float("inf"))
+    out = torch.tensor(sol.y).T.to(device, dtype)
+    return out.reshape(-1, *shape)
 
 
 def reference_available() -> bool:
@@ -45,7 +77,7 @@ def load_reference():
     try:
         if "torchdiffeq" not in sys.modules:
             td = types.ModuleType("torchdiffeq")
-            td.odeint = None
+            td.odeint = scipy_solver_odeint
             sys.modules["torchdiffeq"] = td
         if "models" not in sys.modules:
             pkg = types.ModuleType("models")

@@ -17,6 +17,7 @@ from .sde import PSLD, VPSDE
 from .ncsnpp import NCSNpp
 from .samplers import (ClassCondEulerMaruyamaSampler, EulerMaruyamaSampler, InpaintEulerMaruyamaSampler, Sampler,
                        SSCSSampler)
+from .ode import BBODESampler
 from .io import load_checkpoint, samples_to_uint8, select_score_fn_state
 
 register_module(category="score_fn", name="ncsnpp_b200")(NCSNpp)
@@ -25,7 +26,7 @@ __all__ = [
     "Cfg", "make_config", "tiny_config", "mid_config", "cifar10_config", "celeba64_config",
     "register_module", "get_module", "install", "PSLDSchedule", "StepTables", "time_grid",
     "PSLD", "VPSDE", "NCSNpp", "SSCSSampler", "EulerMaruyamaSampler", "InpaintEulerMaruyamaSampler",
-    "ClassCondEulerMaruyamaSampler", "Sampler",
+    "ClassCondEulerMaruyamaSampler", "BBODESampler", "Sampler",
     "load_checkpoint", "samples_to_uint8", "select_score_fn_state",
 ]
 __version__ = "0.1.0"

@@ -97,6 +97,12 @@ EXPORTS = {
                                         C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                         C.POINTER(ScoreStep), C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int64, C.c_void_p]),
+    "psld_reverse_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(ScoreStep),
+                                     C.c_double, C.c_int64, C.c_int64, C.c_void_p]),
+    "psld_rk_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int64, C.c_void_p]),
+    "psld_rk_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int,
+                                C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]),
     "psld_inpaint_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(InpaintStep), C.c_uint64,
                                        C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),

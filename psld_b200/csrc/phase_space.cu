@@ -52,7 +52,11 @@ struct Philox {
     float u2 = ((float)r.z + 0.5f) * k, u3 = (float)r.w * k;
     u0 = fminf(u0, 0.99999994f);
     u2 = fminf(u2, 0.99999994f);
+#ifdef PSLD_RNG_FAST_LOG
+    float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+#else
     float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+#endif
     float sa, ca, sb, cb;
 #ifdef PSLD_RNG_EXACT_TRIG
     sincospif(2.0f * u1, &sa, &ca);
@@ -647,6 +651,144 @@ extern "C" int psld_quantize_images(const void* state, int state_dtype, uint8_t*
     launch_pdl(quantize_kernel<double>, dim3(grid), dim3(256), 0, s, 1, (const double*)state, out_nhwc, B, C, HW);
   else
     launch_pdl(quantize_kernel<float>, dim3(grid), dim3(256), 0, s, 1, (const float*)state, out_nhwc, B, C, HW);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+// ---------------------------------------------------------------- probability-flow ODE (bb_ode)
+// Reverse drift alone, PSLD.reverse_sde (psld.py:345-364): fbar = -f + g^2 * (score_scale * score),
+// score_scale = 0.5 for the probability-flow formulation (BBODESampler.ode_fn, ode.py:42-46).  The
+// state is read in its own type (the reference evaluates f on the batch-dtype copy of y); fbar is
+// always float64 (vec_t is float64, psld.py:333-337 promotes).
+template <typename S>
+__global__ void __launch_bounds__(256)
+reverse_drift_kernel(double* __restrict__ out, const S* __restrict__ u, const float* __restrict__ eps,
+                     psld_score_step c, double score_scale, int64_t B, int64_t chw) {
+  pdl_wait();
+  const int64_t nvec = B * (chw >> 2);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = v / (chw >> 2);
+    const int64_t j = (v - b * (chw >> 2)) << 2;
+    const int64_t ox = b * 2 * chw + j;
+    St4<S> xs = load4<S>(u + ox), ms = load4<S>(u + ox + chw);
+    float4 ex, em;
+    load_eps(eps, c.mode, b, j, chw, ex, em);
+    const float exa[4] = {ex.x, ex.y, ex.z, ex.w}, ema[4] = {em.x, em.y, em.z, em.w};
+    St4<double> fx4, fm4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sx, sm;
+      score_from_eps(c, exa[i], ema[i], sx, sm);
+      // psld.py:336-337: `0.5 * beta_t * (m_inv * m - gamma * x)`: the bracket is evaluated in the
+      // STATE's dtype (python scalars times a float32 tensor stay float32, op by op, no fusion),
+      // the float64 beta_t then promotes the product
+      double bx, bm;
+      if (sizeof(S) == 4) {
+        const float x = (float)xs.v[i], m = (float)ms.v[i];
+        bx = (double)__fsub_rn(__fmul_rn((float)c.m_inv, m), __fmul_rn((float)c.gamma, x));
+        bm = (double)__fsub_rn(__fmul_rn(-(float)c.nu, m), x);
+      } else {
+        const double x = (double)xs.v[i], m = (double)ms.v[i];
+        bx = c.m_inv * m - c.gamma * x;
+        bm = -c.nu * m - x;
+      }
+      // the reference scales the fp32 score by 0.5 in fp32 (exact), then promotes (psld.py:356-359)
+      const double fx = c.half_beta * bx;
+      const double fm = c.half_beta * bm;
+      fx4.v[i] = -fx + c.g2_x * (double)(sx * (float)score_scale);
+      fm4.v[i] = -fm + c.g2_m * (double)(sm * (float)score_scale);
+    }
+    store4<double>(out + ox, fx4);
+    store4<double>(out + ox + chw, fm4);
+  }
+}
+
+// out = y + h * sum_j coef[j] K[j]   (one Runge-Kutta stage / solution combination, float64), with
+// optional rounded copies: out32 (the state as a float32 batch sees it, and the network input).
+struct RkCoef { double c[8]; };
+
+__global__ void __launch_bounds__(256)
+rk_combine_kernel(double* __restrict__ out, float* __restrict__ out32, const double* __restrict__ y,
+                  const double* __restrict__ K, RkCoef co, int terms, double h, int64_t n) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < terms; ++j) acc += K[(int64_t)j * n + i] * co.c[j];
+    const double v = y[i] + acc * h;
+    if (out) out[i] = v;
+    if (out32) out32[i] = (float)v;
+  }
+}
+
+// sum_out += sum_i ( (h * sum_j e[j] K[j][i]) / (atol + max(|y_i|, |ynew_i|) * rtol) )^2
+__global__ void __launch_bounds__(256)
+rk_error_kernel(const double* __restrict__ y, const double* __restrict__ y_new,
+                const double* __restrict__ K, RkCoef e, int terms, double h, double atol, double rtol,
+                int64_t n, double* __restrict__ sum_out) {
+  pdl_wait();
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < terms; ++j) acc += K[(int64_t)j * n + i] * e.c[j];
+    const double sc = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+    const double r = acc * h / sc;
+    local += r * r;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(sum_out, t);
+  }
+}
+
+extern "C" int psld_reverse_drift(double* out, const void* u, int state_dtype, const float* eps,
+                                  const psld_score_step* coeffs, double score_scale, int64_t B,
+                                  int64_t chw, psld_stream_t stream) {
+  PSLD_CHECK_ARG(out && u && eps && coeffs, "psld_reverse_drift: null pointer");
+  PSLD_CHECK_ARG(B > 0 && chw > 0 && chw % 4 == 0, "psld_reverse_drift: need chw %% 4 == 0");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32, "psld_reverse_drift: state dtype");
+  const int grid = grid_for(B * (chw / 4));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    launch_pdl(reverse_drift_kernel<double>, dim3(grid), dim3(256), 0, s, 1, out, (const double*)u, eps,
+               *coeffs, score_scale, B, chw);
+  else
+    launch_pdl(reverse_drift_kernel<float>, dim3(grid), dim3(256), 0, s, 1, out, (const float*)u, eps,
+               *coeffs, score_scale, B, chw);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_rk_combine(double* out, float* out32, const double* y, const double* K,
+                               const double* coef /* host */, int terms, double h, int64_t n,
+                               psld_stream_t stream) {
+  PSLD_CHECK_ARG(y && (out || out32) && (terms == 0 || (K && coef)) && terms >= 0 && terms <= 8 && n > 0,
+                 "psld_rk_combine: bad arguments");
+  RkCoef co;
+  for (int j = 0; j < 8; ++j) co.c[j] = j < terms ? coef[j] : 0.0;
+  launch_pdl(rk_combine_kernel, dim3((unsigned)grid_for(n)), dim3(256), 0, (cudaStream_t)stream, 1, out,
+             out32, y, K, co, terms, h, n);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_rk_error(const double* y, const double* y_new, const double* K,
+                             const double* e /* host */, int terms, double h, double atol, double rtol,
+                             int64_t n, double* sum_out, psld_stream_t stream) {
+  PSLD_CHECK_ARG(y && y_new && K && e && sum_out && terms > 0 && terms <= 8 && n > 0,
+                 "psld_rk_error: bad arguments");
+  RkCoef co;
+  for (int j = 0; j < 8; ++j) co.c[j] = j < terms ? e[j] : 0.0;
+  launch_pdl(rk_error_kernel, dim3((unsigned)grid_for(n)), dim3(256), 0, (cudaStream_t)stream, 1, y,
+             y_new, K, co, terms, h, atol, rtol, n, sum_out);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

@@ -56,3 +56,13 @@ def cc_config(**ev):
     cfg.data.image_size = 8
     cfg["clf"] = dict(evaluation=dict(label_to_sample=3, clf_temp=2.5))
     return Cfg(cfg)
+
+
+def ode_config(tol=1e-5, **ev):
+    """bb_ode config of oracle/make_golden.py::ode_config (sample_uncond_psld_ode.sh keys)."""
+    from psld_b200 import tiny_config
+    e = dict(sampler=dict(name="bb_ode", solver="RK45", rtol=tol, atol=tol))
+    e.update(ev)
+    cfg = tiny_config(**e)
+    cfg.data.image_size = 8
+    return cfg

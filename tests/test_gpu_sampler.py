@@ -328,6 +328,46 @@ def test_class_conditional_sampler_vs_reference_golden(golden_dir, tag, kw):
     assert torch.isfinite(b).all()
 
 
+@pytest.mark.parametrize("tag,tol,den", [("tol1e-5", 1e-5, True), ("tol1e-4_nodenoise", 1e-4, False)])
+def test_bb_ode_sampler_vs_reference_golden(golden_dir, tag, tol, den):
+    """bb_ode (ode.py:41-76): the RK45 driver restated on the device (stages, error norm and step
+    control of scipy's solve_ivp) reproduces the reference's sample AND its number of score_fn calls."""
+    from _net import ode_config
+    from psld_b200 import BBODESampler
+    g = np.load(f"{golden_dir}/sampler_bb_ode_gauss_{tag}.npz")
+    cfg = ode_config(tol, denoise=den)
+    B = int(g["B"])
+    u0 = prior((B, 3, 8, 8), 0.5, 1)
+    from oracle.weights import gaussian_score_fn
+    S = BBODESampler(cfg, PSLD(cfg), gaussian_score_fn(cfg))
+    out = S.sample(u0.cuda(), None, 0, denoise=den, eps=cfg.evaluation.eval_eps)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["final"])
+    e, m = rel_l2(out, ref), max_rel(out, ref)
+    print(f"bb_ode {tag}: rel-L2 {e:.3e} max {m:.3e} nfe {S.nfe} (reference {int(g['nfe'])}), "
+          f"steps {S.steps_accepted}+{S.steps_rejected} rejected")
+    assert S.nfe == int(g["nfe"]) and S.mean_nfe == S.nfe and S.n_steps == S.nfe
+    assert e <= 1e-5 and m <= 1e-5
+    assert out.dtype == (torch.float64 if den else torch.float32)
+
+
+def test_bb_ode_with_network_vs_oracle():
+    """bb_ode over the native NCSN++ program (tiny net, fp32 tier) vs the oracle's solve_ivp run."""
+    from _net import ode_config
+    from psld_b200 import BBODESampler
+    cfg = ode_config(1e-3)
+    cfg.data.image_size = 32
+    net, sd = make_net(cfg, "fp32")
+    B = 2
+    u0 = prior((B, 3, 32, 32), 0.5, 1)
+    S = BBODESampler(cfg, PSLD(cfg), net)
+    out = S.sample(u0.cuda(), None, 0, denoise=True, eps=1e-3)
+    ref, nfe = O.bb_ode_sample(cfg, O.OracleScoreFn(cfg, sd), u0, 1e-3, 1e-3, denoise=True, eps=1e-3)
+    e = rel_l2(out, ref)
+    print(f"bb_ode + NCSN++ fp32: rel-L2 {e:.3e}, nfe {S.nfe} vs oracle {nfe}")
+    assert S.nfe == nfe and e <= 1e-4
+
+
 def test_inpaint_sampler_philox_keeps_known_region():
     """Device-drawn prior and noise: reproducible, and the known region of the denoised result is
     the perturbation mean of x_0 (HSM), i.e. x_0 scaled by the mean coefficient at tau = eps."""

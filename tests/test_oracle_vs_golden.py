@@ -213,3 +213,21 @@ def test_cc_sampler_algebra(golden_dir, tag, kw):
     plain = O.em_sample(cfg, fake_score, u0, ts, n, noise_bank(n, (B, 6, 8, 8), 2),
                         denoise=cfg.evaluation.denoise, eps=cfg.evaluation.eval_eps)
     assert np.abs(plain.numpy() - ref).max() >= 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag,tol,den", [("tol1e-5", 1e-5, True), ("tol1e-4_nodenoise", 1e-4, False)])
+def test_bb_ode_sampler(golden_dir, tag, tol, den):
+    """Oracle restatement of BBODESampler (ode.py:41-76: probability-flow drift + the solve_ivp call
+    torchdiffeq's scipy_solver makes) vs the reference's own output and NFE count."""
+    from _net import ode_config
+    g = np.load(f"{golden_dir}/sampler_bb_ode_gauss_{tag}.npz")
+    cfg = ode_config(tol, denoise=den)
+    B = int(g["B"])
+    sde = O.PSLDScalars(cfg)
+    u0 = prior((B, 3, 8, 8), float(np.sqrt(sde.m)), 1)
+    from oracle.weights import gaussian_score_fn
+    out, nfe = O.bb_ode_sample(cfg, gaussian_score_fn(cfg), u0, tol, tol, denoise=den, eps=cfg.evaluation.eval_eps)
+    ref = g["final"]
+    assert nfe == int(g["nfe"])
+    # every evaluation sees the float32 rounding of (t, y): two runs agree to float32 resolution
+    assert np.abs(out.double().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
