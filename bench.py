@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--profile-ops", type=int, default=2, help="per-op event timing iterations")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -255,11 +257,15 @@ def measure_tier(args, precision, ctx):
     clocks = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
+    if args.profiler_range:             # ncu --profile-from-start off: capture exactly the timed steps
+        torch.cuda.cudart().cudaProfilerStart()
     with torch.cuda.stream(side):
         e0.record()                     # events on the stream the kernels are launched on
         keep2 = run_steps(args.warmup, args.steps)
         e1.record()
     torch.cuda.synchronize(dev)
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)

@@ -9,12 +9,12 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-STEP="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --no-gpu-eager --no-secondary --profile-ops 0 --no-graph"
+STEP="python bench.py --steps 1 --warmup 3 --e2e-nfe 0 --no-cpu-baseline --no-gpu-eager --no-secondary --profile-ops 0 --no-graph --profiler-range"
 for tier in ${TIERS:-bf16x3 bf16}; do
-  read SKIP CNT < <(python scripts/launch_window.py $tier 2>/dev/null)
+  # the window is the timed step itself: bench.py brackets it with cudaProfilerStart/Stop
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-      -s $SKIP -c $CNT --csv --log-file gpurun_out/traffic_$tier.csv $STEP --precision $tier > gpurun_out/ncu_traffic_$tier.log 2>&1
-  echo "traffic $tier rc=$? ($SKIP/$CNT)"
+      --profile-from-start off --csv --log-file gpurun_out/traffic_$tier.csv $STEP --precision $tier > gpurun_out/ncu_traffic_$tier.log 2>&1
+  echo "traffic $tier rc=$?"
 done
 if [ "${CAPTURES:-1}" = "1" ]; then
   for s in ${SHAPES_X3:-c32t c32cat c16 c8 qkv16}; do
@@ -30,9 +30,8 @@ if [ "${CAPTURES:-1}" = "1" ]; then
   # attention + GroupNorm apply + fused update out of a real step of each tier (first matching launch
   # after the warm-up window)
   for tier in bf16x3 bf16; do
-    read SKIP CNT < <(python scripts/launch_window.py $tier 2>/dev/null)
     for k in attn_tc gn_apply sscs_update; do
-      timeout 900 ncu --set full --import-source on --clock-control none -k regex:$k -s ${KSKIP:-12} -c 1 -f \
+      timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:$k -s ${KSKIP:-3} -c 1 -f \
           -o gpurun_out/prof_${tier}_$k $STEP --precision $tier > gpurun_out/ncu_${tier}_$k.log 2>&1
       echo "$tier $k rc=$?"
     done
