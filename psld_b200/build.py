@@ -30,13 +30,31 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles and links the library.  Safe with one process per GPU on a cold tree (torchrun /
+    Lightning start every rank at once): the whole build runs under an exclusive file lock, objects
+    go to a per-process directory, and the shared object is linked under a temporary name and moved
+    into place atomically, so no rank can dlopen a half-written file."""
     if not force and not needs_build():
         return LIB
-    objs = []
+    import fcntl
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():     # another rank built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    objs = []
+    odir = os.path.join(HERE, "build", f"obj.{os.getpid()}")
+    os.makedirs(odir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(odir, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("PSLD_NVCC_EXTRA", "").split(), "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
@@ -49,8 +67,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + f".tmp.{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)                       # atomic on the same filesystem
+    import shutil
+    shutil.rmtree(odir, ignore_errors=True)
     return LIB
 
 

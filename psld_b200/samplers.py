@@ -509,6 +509,9 @@ class InpaintEulerMaruyamaSampler(_FusedSampler):
         n = int(n_discrete_steps)
         self.nfe = n
         self._next_seed()
+        if self.record is not None or self.corrector_fn is not None:
+            raise NotImplementedError("ip_em_sde_b200 does not support `record` / a custom corrector_fn "
+                                      "(the reference's inpainting sampler has neither)")
         if isinstance(self.score_fn, NCSNpp):
             dev = next(self.score_fn.parameters()).device
         else:
