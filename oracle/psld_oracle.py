@@ -452,7 +452,7 @@ def upfirdn2d(x: torch.Tensor, k, up=1, down=1, pad=(0, 0)) -> torch.Tensor:
     z = F.pad(z, [max(p0, 0), max(p1, 0), max(p0, 0), max(p1, 0)])
     z = z[:, :, max(-p0, 0): z.shape[2] - max(-p1, 0), max(-p0, 0): z.shape[3] - max(-p1, 0)]
     Hp, Wp = z.shape[2], z.shape[3]
-    w = torch.flip(k, [0, 1]).view(1, 1, kh, kw).to(x.dtype)
+    w = torch.flip(k, [0, 1]).view(1, 1, kh, kw).to(device=x.device, dtype=x.dtype)
     o = F.conv2d(z.reshape(N * C, 1, Hp, Wp), w).reshape(N, C, Hp - kh + 1, Wp - kw + 1)
     return o[:, :, ::down, ::down]
 
