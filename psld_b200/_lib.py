@@ -10,7 +10,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpsld_b200.so")
+# PSLD_B200_LIB: load another build of the library (kernel experiments next to the committed build)
+LIB_PATH = os.environ.get("PSLD_B200_LIB") or os.path.join(HERE, "libpsld_b200.so")
 
 # ---- constants (keep in sync with include/psld_b200.h) --------------------------------
 VERSION = 100

@@ -1,18 +1,20 @@
-// tcgen05 single-head attention core for the NCSN++ AttnBlockpp (reference layerspp.py:82-86):
-//   w = softmax_keys( einsum(q, k) * C^-0.5 ) ;  h = einsum(w, v)
+// tcgen05 single-head attention block for the NCSN++ AttnBlockpp (reference layerspp.py:82-91):
+//   w = softmax_keys( einsum(q, k) * C^-0.5 ) ;  h = einsum(w, v) ;  out = (NIN_3(h) + x) * scale
 // over HW = 64/128/256 tokens of C = 64..256 channels per sample (16x16 and 8x8 maps).
 //
 // One CTA = one sample x 128 queries.  All HW keys fit in one accumulator, so there is no
 // online-softmax rescaling:
-//   S[128 x HW]  = Q K^T      tcgen05.mma, A = Q chunk, B = K chunk (both K-major, 64-channel
-//                             chunks streamed by TMA through a 3-slot ring), accumulator in TMEM
+//   S[128 x HW]  = Q K^T      tcgen05.mma, A = Q chunk (resident), B = K tile (64 channels x 128 keys,
+//                             streamed by TMA through a 3-slot ring of 16 KB tiles), accumulator in TMEM
 //   P            = exp2(S*c - max*c) -> bf16, written by the 128 softmax threads (one row each)
-//                  straight into shared memory in the 128B-swizzled K-major UMMA layout
-//   O[128 x C]   = P V        per 64-channel group g: A = P, B = V_g as an MN-major operand
-//                             (V is [keys, channels] in memory = contiguous along N)
-//   out          = O / rowsum  -> bf16 NHWC
-// TMEM: HW columns for S + C columns for O (<= 512).  q|k|v arrive packed along the channel axis
-// of one [N, HW, 3C] tensor (the fused NIN_0/1/2 GEMM), addressed with ONE 3-D tensor map.
+//                  straight into shared memory in the 128B-swizzled K-major UMMA layout, over Q
+//   O[128 x C]   = P V        per (64-channel group, 128-key half): A = P, B = V tile as an MN-major
+//                             operand (V is [keys, channels] in memory = contiguous along N); O reuses
+//                             the TMEM columns of S
+//   Y[128 x C]   = Onorm W3^T  (fused projection) A = O / rowsum written over P, B = NIN_3 weight
+//                             tiles; Y reuses the same TMEM columns; conv epilogue finishes the tile
+// q|k|v arrive packed along the channel axis of one [N, HW, 3C] tensor (the fused NIN_0/1/2 GEMM),
+// addressed with ONE 3-D tensor map.
 
 #include <cuda.h>
 
@@ -24,30 +26,40 @@
 
 namespace psld {
 
-constexpr int AT_P_TILE = 128 * 256 * 2;       // P (or normalised O) as 4 K-major tiles of [128 x 64] bf16
+constexpr int AT_TILE = 128 * 64 * 2;           // one operand tile: 128 rows x 64 bf16 (128 B rows, SW128)
+constexpr int AT_RING = 3;                      // ring slots
 constexpr int AT_THREADS = 192;
 
-// kX3 = split-bf16 operands (the fp32-tolerance tier): q|k|v rows are [3C hi | 3C lo], every GEMM
-// (S = Q K^T, O = P V, Y = O W3^T) is three MMA groups hi*hi + hi*lo + lo*hi, P and the normalised
-// O are written to shared memory as hi and lo tiles, the output is split bf16.  Operand tiles are
-// twice as large, so the ring has ONE slot (96 KB) next to the 128 KB of P; the projection
-// epilogue's staging tiles alias the slot (every MMA has retired by then).
+// Shared-memory plan (v2).  Everything is a [<=128 rows x 64 columns] bf16 tile of 16 KB:
+//   QP region  4 tiles : the Q channel chunks during S = Q K^T, then P (4 key chunks, written by the
+//                        softmax threads over Q, which is dead by then), then the normalised O (4
+//                        channel chunks: the A operand of the output projection)
+//   ring       3 slots : K tiles (64 channels x one 128-key half), then V tiles (one 128-key half x
+//                        64 channels), then NIN_3 weight tiles (<=128 output rows x 64 input channels)
+// and the accumulators share ONE 256-column TMEM window: S, then O (after every softmax thread has
+// read S), then the projection Y (after O has been normalised into shared memory).  112 KB of shared
+// memory and 256 TMEM columns per CTA = TWO CTAs per SM in the bf16 tier: the load / softmax /
+// epilogue phases of one query tile overlap the MMA phases of another (v1 ran 1 CTA per SM with
+// 231 KB and 512 columns: tensor pipe 16 %, warps active 9 %).
+// kX3 = split-bf16 operands (the fp32-tolerance tier): q|k|v rows are [3C hi | 3C lo], every GEMM is
+// three MMA groups hi*hi + hi*lo + lo*hi, every tile has a lo twin (QP 128 KB, ring 3 x 32 KB: one
+// CTA per SM, but the 3-deep ring still overlaps loads with MMAs), the output is split bf16.
 template <bool kX3>
 struct AtCfg {
-  static constexpr int kQBytes = 16384 * (kX3 ? 2 : 1);      // Q chunk [128 x 64] (hi | lo)
-  static constexpr int kKVBytes = 32768 * (kX3 ? 2 : 1);     // K chunk / V group / W3 chunk [<=256 x 64]
-  static constexpr int kSlotBytes = kQBytes + kKVBytes;
-  static constexpr int kSlots = kX3 ? 1 : 3;
-  static constexpr int kPBytes = AT_P_TILE * (kX3 ? 2 : 1);
-  static constexpr int kSmem = kSlots * kSlotBytes + kPBytes + 1024 + 256;
-  // fused output projection: 4 KB staging and 256 B additive vector per softmax/epilogue warp
-  static constexpr int kSmemProj = kSmem + (kX3 ? 0 : 4 * 4096 + 4 * 256);
+  static constexpr int kMul = kX3 ? 2 : 1;
+  static constexpr int kQP = 4 * AT_TILE * kMul;             // hi tiles, then lo tiles
+  static constexpr int kSlot = AT_TILE * kMul;               // hi | lo
+  static constexpr int kSmem = kQP + AT_RING * kSlot + 256;  // + barriers; the window must start on
+                                                             // a 1024-byte boundary (it does; trap otherwise)
+  static constexpr int kMinBlocks = kX3 ? 1 : 2;
 };
 
 struct AttnTcParams {
   __nv_bfloat16* out;
   int HW, C, N;
   int q_rows;        // rows of the Q box: min(128, HW)
+  int k_rows;        // rows of a K / V tile: min(128, HW)
+  int w_rows;        // rows of a NIN_3 weight tile: min(128, C)
   float scale_log2;  // C^-0.5 * log2(e)
   ConvTcParams ep;   // kProj: epilogue of the fused NIN_3 projection (bias, residual, scale, stats)
 };
@@ -60,200 +72,203 @@ struct AttnTcState {
 };
 
 // kProj: the block's output projection rides along (AttnBlockpp, layerspp.py:87-91):
-//   h = (NIN_3(O / rowsum) + x) * scale.  The normalised O goes to shared memory as bf16 in the
-//   P buffer (K-major over channels), W3 streams through the ring as 64-channel chunks, the
-//   product accumulates in the TMEM columns S occupied, and the conv epilogue (bias, residual,
-//   scale, bf16 store, GroupNorm statistics) finishes the tile: no O round trip through HBM and
-//   no separate 1x1 convolution launch.
+//   h = (NIN_3(O / rowsum) + x) * scale; the conv epilogue (bias, residual, scale, store, GroupNorm
+//   statistics) finishes the tile: no O round trip through HBM, no separate 1x1 convolution launch.
 template <bool kProj, bool kX3>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, AtCfg<kX3>::kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmW, const AttnTcParams p) {
   using Cfg = AtCfg<kX3>;
-  constexpr int AT_SLOTS = Cfg::kSlots;
-  constexpr int AT_SLOT_BYTES = Cfg::kSlotBytes;
-  constexpr uint32_t QB = Cfg::kQBytes;              // offset of the K / V / W3 tile inside a slot
-  constexpr uint32_t A_LO = 16384u;                  // lo half of the Q chunk (kX3)
-  constexpr uint32_t B_LO = 32768u;                  // lo half of the K / V / W3 tile (kX3)
-  constexpr uint32_t P_LO = AT_P_TILE;               // lo tiles of P / normalised O (kX3)
+  constexpr uint32_t QP_LO = 4u * AT_TILE;           // lo tiles of the QP region (kX3)
+  constexpr uint32_t S_LO = AT_TILE;                 // lo half of a ring slot (kX3)
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t p_base = base + AT_SLOTS * AT_SLOT_BYTES;
-  const uint32_t bar_base = p_base + Cfg::kPBytes;
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();                        // SW128 atoms need 1024-byte alignment
+  const uint32_t qp = base;
+  const uint32_t ring = base + Cfg::kQP;
+  const uint32_t bar_base = ring + AT_RING * Cfg::kSlot;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (AT_SLOTS + s); };
-  const uint32_t s_full = bar_base + 8u * (2 * AT_SLOTS);
-  const uint32_t p_ready = s_full + 8u;
-  const uint32_t o_full = s_full + 16u;
-  const uint32_t o_ready = s_full + 24u;
-  const uint32_t y_full = s_full + 32u;
-  const uint32_t tmem_slot = s_full + 40u;
-  // kProj only; kX3: aliases the (by then idle) operand slot
-  const uint32_t stg_base = kX3 ? base : bar_base + 256u;
-  const uint32_t addv_base = stg_base + 4u * 4096u;
-  const int lo_c = 3 * p.C;                              // kX3: lo half of a q|k|v row
+  auto empty_bar = [&](int s) { return bar_base + 8u * (AT_RING + s); };
+  const uint32_t q_full = bar_base + 8u * (2 * AT_RING);
+  const uint32_t s_full = q_full + 8u;
+  const uint32_t p_ready = q_full + 16u;
+  const uint32_t o_full = q_full + 24u;
+  const uint32_t o_ready = q_full + 32u;
+  const uint32_t y_full = q_full + 40u;
+  const uint32_t tmem_slot = q_full + 48u;
+  // kProj epilogue: staging tiles + additive vectors alias the (by then idle) ring
+  const uint32_t stg_base = ring;
+  const uint32_t addv_base = ring + 4u * 4096u;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, q0 = blockIdx.x * 128;
-  const int nck = p.C / 64;          // channel chunks (S GEMM K loop) = channel groups (PV GEMM)
+  const int nck = p.C / 64;                          // 64-channel chunks
+  const int nkh = (p.HW + 127) / 128;                // 128-key halves
+  const int nwt = (p.C + 127) / 128;                 // 128-row tiles of the NIN_3 weight
+  const int lo_c = 3 * p.C;                          // kX3: lo half of a q|k|v row
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
-    for (int s = 0; s < AT_SLOTS; ++s) {
+    if (kProj) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < AT_RING; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(q_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
     mbar_init(o_ready, 128);
     mbar_init(y_full, 1);
-    if (kProj) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(tmem_slot), "n"(512) : "memory");
+                 ::"r"(tmem_slot), "n"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();                  // q|k|v come from the previous kernel (prologue above overlaps its tail)
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tmem_S = tmem_base;                 // columns [0, HW)
-  const uint32_t tmem_O = tmem_base + 256u;          // columns [256, 256 + C)
+  const uint32_t tmem_acc = *tmem_slot_ptr;          // 256 columns: S, then O, then Y
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
+      const uint32_t mul = kX3 ? 2u : 1u;
+      mbar_arrive_expect_tx(q_full, (uint32_t)(nck * p.q_rows) * 128u * mul);
+      for (int c = 0; c < nck; ++c) {
+        tma_load_3d(qp + (uint32_t)c * AT_TILE, &tmQ, q_full, c * 64, q0, n);
+        if (kX3) tma_load_3d(qp + QP_LO + (uint32_t)c * AT_TILE, &tmQ, q_full, lo_c + c * 64, q0, n);
+      }
       int slot = 0;
       uint32_t phase = 0;
-      // Q/K channel chunks
-      for (int c = 0; c < nck; ++c) {
-        mbar_wait(empty_bar(slot), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(p.q_rows + p.HW) * 128u * (kX3 ? 2u : 1u));
-        const uint32_t sq = base + slot * AT_SLOT_BYTES;
-        tma_load_3d(sq, &tmQ, full_bar(slot), c * 64, q0, n);
-        tma_load_3d(sq + QB, &tmKV, full_bar(slot), p.C + c * 64, 0, n);
-        if (kX3) {
-          tma_load_3d(sq + A_LO, &tmQ, full_bar(slot), lo_c + c * 64, q0, n);
-          tma_load_3d(sq + QB + B_LO, &tmKV, full_bar(slot), lo_c + p.C + c * 64, 0, n);
-        }
-        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
-      }
-      // V channel groups
-      for (int g = 0; g < nck; ++g) {
-        mbar_wait(empty_bar(slot), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.HW * 128u * (kX3 ? 2u : 1u));
-        const uint32_t sv = base + slot * AT_SLOT_BYTES + QB;
-        tma_load_3d(sv, &tmKV, full_bar(slot), 2 * p.C + g * 64, 0, n);
-        if (kX3) tma_load_3d(sv + B_LO, &tmKV, full_bar(slot), lo_c + 2 * p.C + g * 64, 0, n);
-        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
-      }
-      if (kProj) {       // W3 [C out rows x 64 input channels] per chunk
-        for (int c = 0; c < nck; ++c) {
+      auto next = [&]() { if (++slot == AT_RING) { slot = 0; phase ^= 1; } };
+      // K tiles: (channel chunk, key half)
+      for (int c = 0; c < nck; ++c)
+        for (int h = 0; h < nkh; ++h) {
           mbar_wait(empty_bar(slot), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.C * 128u * (kX3 ? 2u : 1u));
-          tma_load_2d(base + slot * AT_SLOT_BYTES + QB, &tmW, full_bar(slot), c * 64, 0);
-          if (kX3) tma_load_2d(base + slot * AT_SLOT_BYTES + QB + B_LO, &tmW, full_bar(slot), c * 64, p.C);
-          if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.k_rows * 128u * mul);
+          const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+          tma_load_3d(st, &tmKV, full_bar(slot), p.C + c * 64, h * 128, n);
+          if (kX3) tma_load_3d(st + S_LO, &tmKV, full_bar(slot), lo_c + p.C + c * 64, h * 128, n);
+          next();
         }
+      // V tiles: (channel group, key half)
+      for (int g = 0; g < nck; ++g)
+        for (int h = 0; h < nkh; ++h) {
+          mbar_wait(empty_bar(slot), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.k_rows * 128u * mul);
+          const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+          tma_load_3d(st, &tmKV, full_bar(slot), 2 * p.C + g * 64, h * 128, n);
+          if (kX3) tma_load_3d(st + S_LO, &tmKV, full_bar(slot), lo_c + 2 * p.C + g * 64, h * 128, n);
+          next();
+        }
+      if (kProj) {   // NIN_3 weight tiles: (input-channel chunk, 128-row output tile)
+        for (int c = 0; c < nck; ++c)
+          for (int t = 0; t < nwt; ++t) {
+            mbar_wait(empty_bar(slot), phase ^ 1);
+            mbar_arrive_expect_tx(full_bar(slot), (uint32_t)p.w_rows * 128u * mul);
+            const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+            tma_load_2d(st, &tmW, full_bar(slot), c * 64, t * 128);
+            if (kX3) tma_load_2d(st + S_LO, &tmW, full_bar(slot), c * 64, p.C + t * 128);
+            next();
+          }
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      // S = Q K^T : M = 128, N = HW, both operands K-major
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.HW >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
-      for (int c = 0; c < nck; ++c) {
-        mbar_wait(full_bar(slot), phase);
-        tc_fence_after();
-        const uint32_t sq = base + slot * AT_SLOT_BYTES;
-        const uint64_t adesc = make_sw128_desc(sq);
-        const uint64_t bdesc = make_sw128_desc(sq + QB);
+      auto next = [&]() { if (++slot == AT_RING) { slot = 0; phase ^= 1; } };
+      // one (A tile, B tile) product group of 4 k-steps (64 channels); kX3: three groups
+      auto kgroup = [&](uint32_t d, uint32_t a_hi, uint32_t b_hi, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                        bool first) {
+        const uint64_t ad = make_sw128_desc(a_hi), bd = make_sw128_desc(b_hi);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s,
-                      (c > 0 || k > 0) ? 1u : 0u);
+          tc_mma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (!first || k > 0) ? 1u : 0u);
         if (kX3) {
-          const uint64_t adesc_lo = make_sw128_desc(sq + A_LO);
-          const uint64_t bdesc_lo = make_sw128_desc(sq + QB + B_LO);
+          const uint64_t al = make_sw128_desc(a_lo), bl = make_sw128_desc(b_lo);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc_s, 1u);
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_S, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, 1u);
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d, al + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
         }
-        tc_commit(empty_bar(slot));
-        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
-      }
-      tc_commit(s_full);
-      // O_g = P V_g : M = 128, N = 64, A = P (K-major over keys), B = V_g (MN-major)
-      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) |
-                               ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      mbar_wait(p_ready, 0);
+      };
+      // ---- S[:, h*128 ..] += Q_c K_{c,h}^T : M = 128, N = k_rows, both operands K-major
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.k_rows >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(q_full, 0);
       tc_fence_after();
-      for (int g = 0; g < nck; ++g) {
-        mbar_wait(full_bar(slot), phase);
-        tc_fence_after();
-        const uint32_t sv = base + slot * AT_SLOT_BYTES + QB;
-        for (int ks = 0; ks < p.HW / 16; ++ks) {
-          const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)(ks >> 2) * 16384u) +
-                                 (uint64_t)(2 * (ks & 3));
-          const uint64_t bdesc = make_sw128_desc(sv + (uint32_t)ks * 2048u);   // 16 keys x 128 B
-          tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
-          if (kX3) {
-            const uint64_t adesc_lo = make_sw128_desc(p_base + P_LO + (uint32_t)(ks >> 2) * 16384u) +
-                                      (uint64_t)(2 * (ks & 3));
-            const uint64_t bdesc_lo = make_sw128_desc(sv + B_LO + (uint32_t)ks * 2048u);
-            tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc, bdesc_lo, idesc_o, 1u);
-            tc_mma_bf16(tmem_O + (uint32_t)g * 64u, adesc_lo, bdesc, idesc_o, 1u);
-          }
-        }
-        tc_commit(empty_bar(slot));
-        if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
-      }
-      tc_commit(o_full);
-      if (kProj) {
-        // Y[128 x C] = Onorm W3^T : A = Onorm (bf16, K-major over channels, in the P buffer),
-        // B = W3 chunk (K-major), accumulator in the columns S used
-        const uint32_t idesc_y = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.C >> 3) << 17) |
-                                 ((uint32_t)(128 >> 4) << 24);
-        mbar_wait(o_ready, 0);
-        tc_fence_after();
-        for (int c = 0; c < nck; ++c) {
+      for (int c = 0; c < nck; ++c)
+        for (int h = 0; h < nkh; ++h) {
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(p_base + (uint32_t)c * 16384u);
-          const uint64_t bdesc = make_sw128_desc(base + slot * AT_SLOT_BYTES + QB);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_y,
-                        (c > 0 || k > 0) ? 1u : 0u);
-          if (kX3) {
-            const uint64_t adesc_lo = make_sw128_desc(p_base + P_LO + (uint32_t)c * 16384u);
-            const uint64_t bdesc_lo = make_sw128_desc(base + slot * AT_SLOT_BYTES + QB + B_LO);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_S, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc_y, 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_S, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_y, 1u);
+          const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+          kgroup(tmem_acc + (uint32_t)h * 128u, qp + (uint32_t)c * AT_TILE, st,
+                 qp + QP_LO + (uint32_t)c * AT_TILE, st + S_LO, idesc_s, c == 0);
+          tc_commit(empty_bar(slot));
+          next();
+        }
+      tc_commit(s_full);
+      // ---- O[:, g*64 ..] += P[:, keys of half h] V_{g,h} : M = 128, N = 64, A = P (K-major over
+      // keys), B = V tile as an MN-major operand (V is [keys, channels] = contiguous along N)
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) |
+                               ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(p_ready, 0);           // P is in shared memory AND every thread is done reading S
+      tc_fence_after();
+      for (int g = 0; g < nck; ++g)
+        for (int h = 0; h < nkh; ++h) {
+          mbar_wait(full_bar(slot), phase);
+          tc_fence_after();
+          const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+          const uint32_t d = tmem_acc + (uint32_t)g * 64u;
+          for (int ks = 0; ks < p.k_rows / 16; ++ks) {
+            const int kg = h * 8 + ks;                                       // global 16-key step
+            const uint32_t pa = qp + (uint32_t)(kg >> 2) * AT_TILE;
+            const uint64_t adesc = make_sw128_desc(pa) + (uint64_t)(2 * (kg & 3));
+            const uint64_t bdesc = make_sw128_desc(st + (uint32_t)ks * 2048u);   // 16 keys x 128 B
+            tc_mma_bf16(d, adesc, bdesc, idesc_o, (h > 0 || ks > 0) ? 1u : 0u);
+            if (kX3) {
+              const uint64_t adesc_lo = make_sw128_desc(pa + QP_LO) + (uint64_t)(2 * (kg & 3));
+              const uint64_t bdesc_lo = make_sw128_desc(st + S_LO + (uint32_t)ks * 2048u);
+              tc_mma_bf16(d, adesc, bdesc_lo, idesc_o, 1u);
+              tc_mma_bf16(d, adesc_lo, bdesc, idesc_o, 1u);
+            }
           }
           tc_commit(empty_bar(slot));
-          if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
+          next();
         }
+      tc_commit(o_full);
+      if (kProj) {
+        // ---- Y[:, t*128 ..] += Onorm_c W3_{c,t}^T : A = Onorm chunk (K-major over channels, in the QP
+        // region), B = weight tile (K-major), N = rows of the tile
+        mbar_wait(o_ready, 0);         // normalised O is in shared memory AND O has been read from TMEM
+        tc_fence_after();
+        for (int c = 0; c < nck; ++c)
+          for (int t = 0; t < nwt; ++t) {
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const int rows = (p.C - t * 128) < 128 ? (p.C - t * 128) : 128;
+            const uint32_t idesc_y = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(rows >> 3) << 17) |
+                                     ((uint32_t)(128 >> 4) << 24);
+            const uint32_t st = ring + (uint32_t)slot * Cfg::kSlot;
+            kgroup(tmem_acc + (uint32_t)t * 128u, qp + (uint32_t)c * AT_TILE, st,
+                   qp + QP_LO + (uint32_t)c * AT_TILE, st + S_LO, idesc_y, c == 0);
+            tc_commit(empty_bar(slot));
+            next();
+          }
         tc_commit(y_full);
       }
     }
   } else {
-    // ===== softmax + epilogue: 128 threads, one query row each =====
+    // ===================== softmax + epilogue: 128 threads, one query row each =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -262,7 +277,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     float mx = -INFINITY;
     for (int ch = 0; ch < p.HW; ch += 32) {
       uint32_t r[32];
-      tmem_ld32(tmem_S + lane_addr + (uint32_t)ch, r);
+      tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
@@ -271,10 +286,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     float sum = 0.f;
     for (int ch = 0; ch < p.HW; ch += 32) {
       uint32_t r[32];
-      tmem_ld32(tmem_S + lane_addr + (uint32_t)ch, r);
+      tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
       tmem_ld_wait();
-      // P tile (ch / 64), 16-byte chunks (ch % 64) / 8 .. +3, swizzled by (row % 8)
-      const uint32_t tile = p_base + (uint32_t)(ch >> 6) * 16384u + (uint32_t)row * 128u;
+      // P tile (ch / 64), 16-byte chunks (ch % 64) / 8 .. +3, swizzled by (row % 8); the Q tiles it
+      // overwrites were last read by MMAs that completed before s_full
+      const uint32_t tile = qp + (uint32_t)(ch >> 6) * AT_TILE + (uint32_t)row * 128u;
       const int cbase = (ch & 63) >> 3;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -295,12 +311,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         const uint32_t dst = tile + (uint32_t)(((cbase + q) ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                     ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        if (kX3) sts128(dst + P_LO, wl[0], wl[1], wl[2], wl[3]);
+        sts128(dst, w[0], w[1], w[2], w[3]);
+        if (kX3) sts128(dst + QP_LO, wl[0], wl[1], wl[2], wl[3]);
       }
     }
-    // make the generic-proxy smem writes visible to the tensor-core (async) proxy
+    // generic-proxy smem writes -> visible to the tensor core (async proxy); the TMEM reads of S are
+    // complete (tcgen05.wait::ld), so the MMA warp may overwrite the window with O
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     mbar_arrive(p_ready);
@@ -310,12 +326,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q = q0 + row;
     const bool valid = q < p.HW;
     if (kProj) {
-      // normalised O -> bf16 in the P buffer, same swizzled K-major tiles as P (tile = ch / 64)
+      // normalised O -> (split) bf16 in the QP region, same swizzled K-major tiles (tile = ch / 64);
+      // P was last read by MMAs that completed before o_full
       for (int ch = 0; ch < p.C; ch += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_O + lane_addr + (uint32_t)ch, r);
+        tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
         tmem_ld_wait();
-        const uint32_t tile = p_base + (uint32_t)(ch >> 6) * 16384u + (uint32_t)row * 128u;
+        const uint32_t tile = qp + (uint32_t)(ch >> 6) * AT_TILE + (uint32_t)row * 128u;
         const int cbase = (ch & 63) >> 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -327,9 +344,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (kX3) split_bf2(o0, o1, w[t], wl[t]);
             else w[t] = f2_to_bf2(o0, o1);
           }
-          sts128(tile + (uint32_t)(((cbase + j) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
-          if (kX3)
-            sts128(tile + P_LO + (uint32_t)(((cbase + j) ^ (row & 7)) << 4), wl[0], wl[1], wl[2], wl[3]);
+          const uint32_t dst = tile + (uint32_t)(((cbase + j) ^ (row & 7)) << 4);
+          sts128(dst, w[0], w[1], w[2], w[3]);
+          if (kX3) sts128(dst + QP_LO, wl[0], wl[1], wl[2], wl[3]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -341,32 +358,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5
 #pragma unroll 1
       for (int half = 0; half < 2; ++half)
-        tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_S, 0, m_tile, 0, quarter, half, lane,
+        tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_acc, 0, m_tile, 0, quarter, half, lane,
                                                          stg_base + (uint32_t)ew * 4096u,
                                                          addv_base + (uint32_t)ew * 256u, []() {}, []() {});
     } else {
-    __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * (p.C * (kX3 ? 2 : 1));
-    for (int ch = 0; ch < p.C; ch += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_O + lane_addr + (uint32_t)ch, r);
-      tmem_ld_wait();
-      if (valid) {
+      __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * (p.C * (kX3 ? 2 : 1));
+      for (int ch = 0; ch < p.C; ch += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint32_t w[4], wl[4];
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w[4], wl[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float o0 = __uint_as_float(r[j + 2 * t]) * inv;
-            const float o1 = __uint_as_float(r[j + 2 * t + 1]) * inv;
-            if (kX3) split_bf2(o0, o1, w[t], wl[t]);
-            else w[t] = f2_to_bf2(o0, o1);
+            for (int t = 0; t < 4; ++t) {
+              const float o0 = __uint_as_float(r[j + 2 * t]) * inv;
+              const float o1 = __uint_as_float(r[j + 2 * t + 1]) * inv;
+              if (kX3) split_bf2(o0, o1, w[t], wl[t]);
+              else w[t] = f2_to_bf2(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(orow + ch + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (kX3) *reinterpret_cast<uint4*>(orow + p.C + ch + j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
           }
-          *reinterpret_cast<uint4*>(orow + ch + j) = make_uint4(w[0], w[1], w[2], w[3]);
-          if (kX3) *reinterpret_cast<uint4*>(orow + p.C + ch + j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
+        __syncwarp();
       }
-      __syncwarp();
-    }
     }
   }
 
@@ -375,7 +392,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                 ::"r"(tmem_base), "n"(512) : "memory");
+                 ::"r"(tmem_acc), "n"(256) : "memory");
   }
 }
 
@@ -412,10 +429,11 @@ int prepare_attn_tc(psld_op& op) {
   const int q_rows = HW < 128 ? HW : 128;
   st->x3 = x3;
   int rc = encode_qkv_map(&st->tq, op.in[0], N, HW, cm * 3 * C, q_rows);
-  if (rc == PSLD_OK) rc = encode_qkv_map(&st->tkv, op.in[0], N, HW, cm * 3 * C, HW);
+  if (rc == PSLD_OK) rc = encode_qkv_map(&st->tkv, op.in[0], N, HW, cm * 3 * C, q_rows);   // 128-key halves
   if (rc != PSLD_OK) { delete st; return rc; }
   st->p.out = (__nv_bfloat16*)op.out[0];
   st->p.HW = HW; st->p.C = C; st->p.N = N; st->p.q_rows = q_rows;
+  st->p.k_rows = q_rows; st->p.w_rows = C < 128 ? C : 128;
   st->p.scale_log2 = op.f[0] * 1.4426950408889634f;
   st->grid = dim3((unsigned)((HW + 127) / 128), (unsigned)N);
   // optional fused output projection (in[1] = W3 bf16 [C out, C in], in[2] = bias, in[3] = residual)
@@ -425,7 +443,7 @@ int prepare_attn_tc(psld_op& op) {
     EncodeTiledFn enc = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(cm * C)};      // split: planes [2][C out, C in]
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)C};
+    cuuint32_t box[2] = {64, (cuuint32_t)(C < 128 ? C : 128)};        // <=128-row output tiles
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc ? enc(&st->tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.in[1]), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -454,13 +472,18 @@ int prepare_attn_tc(psld_op& op) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::kSmem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               AtCfg<false>::kSmemProj);
+                               AtCfg<false>::kSmem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                AtCfg<true>::kSmem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               AtCfg<true>::kSmemProj);
+                               AtCfg<true>::kSmem);
+    // two CTAs per SM (bf16 tier) need the maximum shared-memory carve-out
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -485,7 +508,7 @@ int run_attn_tc(const psld_op& op, cudaStream_t s) {
   PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
 #define ATTN_LAUNCH(PROJ, X3)                                                                  \
   PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<PROJ, X3>, st->grid, dim3(AT_THREADS),                \
-                             PROJ ? AtCfg<X3>::kSmemProj : AtCfg<X3>::kSmem, s, 1, st->tq, st->tkv, \
+                             AtCfg<X3>::kSmem, s, 1, st->tq, st->tkv,                              \
                              st->tw, st->p))
   if (st->proj) { if (st->x3) ATTN_LAUNCH(true, true); else ATTN_LAUNCH(true, false); }
   else { if (st->x3) ATTN_LAUNCH(false, true); else ATTN_LAUNCH(false, false); }

@@ -60,6 +60,7 @@ struct ConvGnState {
   CUtensorMap a1, a2, b, e1, e2;
   ConvGnParams p;
   int grid;
+  bool x3;       // split-bf16 operands: conv_gn_x3_kernel
 };
 
 // tap issue order: the three centre-column taps first, so that the centre slot (where the next
@@ -379,6 +380,334 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   }
 }
 
+// =====================================================================================
+// Split-bf16 ("bf16x3") variant: the fp32-tolerance tier's GroupNorm-on-load convolution.
+//
+// Every operand tile has a hi and a lo twin, so the three column-shifted variants are SIX tiles of
+// 24 KB: 144 KB, which fits shared memory once, not twice.  Instead of double-buffering the whole
+// operand set, the transform runs in TWO phases around a single set, using the centre-taps-first
+// issue order:
+//   * the raw (hi, lo) tile of chunk c+1 lands in the CENTRE slots as soon as the three centre taps
+//     of chunk c have retired (c_empty); the transform warps normalise it in place (fp32 GroupNorm
+//     + SiLU, split back into hi/lo) while the tensor core is still busy with the six SIDE taps of
+//     chunk c, and publish it (c_ready);
+//   * the MMA warp goes straight from the side taps of chunk c to the centre taps of chunk c+1;
+//     meanwhile (lr_empty) the transform warps write the left / right shifted copies from registers
+//     and publish them (lr_ready) before the centre taps are through.
+// A k-block = (tap, 64-channel chunk) feeds three MMA groups (a_hi w_hi, a_hi w_lo, a_lo w_hi) from
+// one weight stage holding W_hi | W_lo.  Four epilogue warps (each handles both column halves; the
+// tile's MMA phase is 3x longer than in the bf16 kernel, so the epilogue has time) keep the split
+// staging tiles at 16 KB.  No 1x1 shortcut extension in this variant.
+//
+// Warps (384 threads, so that the split epilogue keeps its accumulator rows in registers: 170 regs):
+// 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator, 2 = weight TMA, 3 idle,
+// 4..7 = epilogue, 8..11 = transform.
+constexpr int GX_THREADS = 384;
+constexpr int GX_TRANSFORM_WARPS = 4;
+constexpr int GX_B_STAGES = 2;
+constexpr int GX_B_STAGE = 2 * GN_B_BYTES;          // W_hi | W_lo half tiles (32 KB)
+constexpr int GX_ABUF_BYTES = 6 * GN_VAR_BYTES;     // C_hi C_lo L_hi L_lo R_hi R_lo
+constexpr int GX_STAGING_BYTES = 4 * 4096;          // 4 epilogue warps x (hi, lo) 2 KB tiles
+constexpr int GX_ADDV_BYTES = 4 * 256;
+constexpr int GX_SMEM_BYTES = GX_ABUF_BYTES + GX_B_STAGES * GX_B_STAGE + GX_STAGING_BYTES + 256 + GX_ADDV_BYTES + 768;
+
+__device__ __forceinline__ float silu_x3(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(GX_THREADS, 1)
+conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const ConvGnParams gp) {
+  const ConvTcParams& p = gp.c;
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // variant v in {0: centre, 1: left, 2: right}, plane pl in {0: hi, 1: lo}
+  auto var = [&](int v, int pl) { return base + (uint32_t)(2 * v + pl) * GN_VAR_BYTES; };
+  const uint32_t bring = base + GX_ABUF_BYTES;
+  const uint32_t stg_base = bring + GX_B_STAGES * GX_B_STAGE;
+  const uint32_t bar_base = stg_base + GX_STAGING_BYTES;
+  const uint32_t addv_base = bar_base + 256u;
+  if (addv_base + GX_ADDV_BYTES > smem_u32(smem_raw) + GX_SMEM_BYTES) __trap();
+  const uint32_t raw_full = bar_base, c_ready = bar_base + 8u, lr_ready = bar_base + 16u;
+  const uint32_t c_empty = bar_base + 24u, lr_empty = bar_base + 32u;
+  auto b_full = [&](int s) { return bar_base + 40u + 8u * s; };
+  auto b_empty = [&](int s) { return bar_base + 40u + 8u * (GX_B_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 40u + 8u * (2 * GX_B_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 40u + 8u * (2 * GX_B_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 40u + 8u * (2 * GX_B_STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    mbar_init(raw_full, 1);
+    mbar_init(c_ready, 2);          // one elected arrive per CTA of the pair
+    mbar_init(lr_ready, 2);
+    mbar_init(c_empty, 1);
+    mbar_init(lr_empty, 1);
+    for (int s = 0; s < GX_B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int b_rows = p.block_n >> 1;
+  const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
+  const int total_chunks = p.kchunks;
+
+  if (warp == 0) {
+    // ===================== raw activation tiles (hi, lo) -> the centre slots =====================
+    pdl_wait();
+    if (lane == 0) {
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+        const int n0 = m_tile / p.tiles_y;
+        const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
+        for (int cc = 0; cc < total_chunks; ++cc) {
+          mbar_wait(c_empty, ph ^ 1);             // centre taps of the previous chunk have retired
+          mbar_arrive_expect_tx(raw_full, 2u * raw_bytes);
+          const bool s1 = cc < p.kchunks1;
+          const CUtensorMap* tmA = s1 ? &tmA1 : &tmA2;
+          const int c0 = (s1 ? cc : cc - p.kchunks1) * TC_BLOCK_K;
+          tma_load_4d(var(0, 0), tmA, raw_full, c0, 0, y0, n0);
+          tma_load_4d(var(0, 1), tmA, raw_full, c0 + (s1 ? p.lo1 : p.lo2), 0, y0, n0);
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight producer: W_hi | W_lo half tiles per (tap, chunk) =============
+    int stage = 0;
+    uint32_t ph = 0;
+    const uint32_t tx = (uint32_t)b_rows * 128u * 2u * 2u;       // (hi + lo) x both CTAs
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int n_tile = unit % p.n_tiles_n;
+      const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
+      for (int cc = 0; cc < total_chunks; ++cc) {
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kblk = gn_tap(t9) * p.kchunks + cc;
+          mbar_wait(b_empty(stage), ph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
+            const uint32_t dst = bring + (uint32_t)stage * GX_B_STAGE;
+            tma_load_2d_pair(dst, &tmB, b_full(stage), kblk * TC_BLOCK_K, bn0);
+            tma_load_2d_pair(dst + GN_B_BYTES, &tmB, b_full(stage), kblk * TC_BLOCK_K, bn0 + p.w_lo_rows);
+          }
+          __syncwarp();
+          if (++stage == GX_B_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t cph = 0, bph = 0, acc_phase = 0;
+      const uint32_t row_step = (uint32_t)p.W * 128u;       // ky * W rows
+      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int cc = 0; cc < total_chunks; ++cc) {
+          for (int t9 = 0; t9 < 9; ++t9) {
+            if (t9 == 0) { mbar_wait_cluster(c_ready, cph); tc_fence_after(); }
+            if (t9 == 3) {
+              // side variants written (the transform warps are done READING the centre tiles too):
+              // once the three centre taps issued so far retire, the next raw tile may land
+              mbar_wait_cluster(lr_ready, cph);
+              tc_fence_after();
+              if (elect_one()) tc_commit_pair(c_empty);
+              __syncwarp();
+            }
+            const int tap = gn_tap(t9);
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int v = kx == 1 ? 0 : (kx == 0 ? 1 : 2);   // centre / left / right variant
+            mbar_wait(b_full(stage), bph);
+            tc_fence_after();
+            const uint64_t a_hi = make_sw128_desc(var(v, 0) + (uint32_t)ky * row_step);
+            const uint64_t a_lo = make_sw128_desc(var(v, 1) + (uint32_t)ky * row_step);
+            const uint64_t b_hi = make_sw128_desc(bring + (uint32_t)stage * GX_B_STAGE);
+            const uint64_t b_lo = make_sw128_desc(bring + (uint32_t)stage * GX_B_STAGE + GN_B_BYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc,
+                                 (cc > 0 || t9 > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+              tc_commit_pair(b_empty(stage));
+              if (t9 == 8) tc_commit_pair(lr_empty);     // side variants free
+            }
+            __syncwarp();
+            if (++stage == GX_B_STAGES) { stage = 0; bph ^= 1; }
+          }
+          cph ^= 1;
+        }
+        if (elect_one()) tc_commit_pair(tfull_bar(acc));
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== transform warps: fp32 GroupNorm + SiLU, two phases =====================
+    constexpr int TT = GX_TRANSFORM_WARPS * 32;
+    constexpr int RSTEP = TT / 8;
+    constexpr int ITEMS = (GN_MAX_ROWS + RSTEP - 1) / RSTEP;
+    const int tt = (int)threadIdx.x - 8 * 32;
+    const int j = tt & 7;                           // 16-byte chunk = channels 8j .. 8j+7
+    const int r0 = tt >> 3;
+    const uint32_t leader_c = mapa_rank(c_ready, 0), leader_lr = mapa_rank(lr_ready, 0);
+    const int Wm = p.W - 1;
+    const uint32_t sm0 = smem_u32(smem_raw);
+    auto sptr = [&](uint32_t a) { return reinterpret_cast<uint4*>(smem_raw + (a - sm0)); };
+    uint32_t ph = 0;
+    pdl_wait();
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+      const int n0 = m_tile / p.tiles_y;
+      const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
+      const bool img_ok = n0 < gp.n_images;
+      for (int cc = 0; cc < total_chunks; ++cc) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sc[q] = 0.f; sh[q] = 0.f; }
+        if (img_ok) {
+          const float4* ap = reinterpret_cast<const float4*>(
+              gp.affine + ((int64_t)n0 * gp.cin + cc * TC_BLOCK_K + j * 8) * 2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(ap + q);
+            sc[2 * q] = v.x; sh[2 * q] = v.y; sc[2 * q + 1] = v.z; sh[2 * q + 1] = v.w;
+          }
+        }
+        mbar_wait(raw_full, ph);
+        const uint32_t Ch = var(0, 0), Cl = var(0, 1);
+        // ---- phase 1: normalise the centre tiles in place (three rows in flight per thread)
+#pragma unroll 3
+        for (int u = 0; u < ITEMS; ++u) {
+          const int r = r0 + RSTEP * u;
+          if (r >= gp.rows_in) continue;
+          const int gy = y0 + (r >> gp.w_shift);
+          const bool valid = img_ok && gy >= 0 && gy < p.H;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          uint4 th = make_uint4(0u, 0u, 0u, 0u), tl = th;     // rows outside the image: zero padding
+          if (valid) {
+            th = *sptr(Ch + off);
+            tl = *sptr(Cl + off);
+            uint32_t* wh = reinterpret_cast<uint32_t*>(&th);
+            uint32_t* wl = reinterpret_cast<uint32_t*>(&tl);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fh = bf2_to_f2(wh[q]), fl = bf2_to_f2(wl[q]);
+              float a = fmaf(fh.x + fl.x, sc[2 * q], sh[2 * q]);
+              float b = fmaf(fh.y + fl.y, sc[2 * q + 1], sh[2 * q + 1]);
+              if (gp.silu) { a = silu_x3(a); b = silu_x3(b); }
+              split_bf2(a, b, wh[q], wl[q]);
+            }
+          }
+          *sptr(Ch + off) = th;
+          *sptr(Cl + off) = tl;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(GX_TRANSFORM_WARPS * 32) : "memory");
+        if (tt == 0) mbar_arrive_remote(leader_c);
+        // ---- phase 2: left / right shifted copies of the normalised centre tiles, once the side taps
+        // of the previous chunk have retired (the centre tiles stay put until lr_ready: see the MMA warp)
+        mbar_wait(lr_empty, ph ^ 1);
+#pragma unroll 3
+        for (int u = 0; u < ITEMS; ++u) {
+          const int r = r0 + RSTEP * u;
+          if (r >= gp.rows_in) continue;
+          const int x = r & Wm;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          const uint4 th = *sptr(Ch + off), tl = *sptr(Cl + off);
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          if (x < Wm) {                                              // left variant: (y, x+1) <- t(y, x)
+            const int rn = r + 1;
+            const uint32_t o2 = (uint32_t)rn * 128u + (uint32_t)((j ^ (rn & 7)) << 4);
+            *sptr(var(1, 0) + o2) = th;
+            *sptr(var(1, 1) + o2) = tl;
+          }
+          if (x == 0) { *sptr(var(1, 0) + off) = z; *sptr(var(1, 1) + off) = z; }     // left image edge
+          if (x > 0) {                                               // right variant: (y, x-1) <- t(y, x)
+            const int rp = r - 1;
+            const uint32_t o2 = (uint32_t)rp * 128u + (uint32_t)((j ^ (rp & 7)) << 4);
+            *sptr(var(2, 0) + o2) = th;
+            *sptr(var(2, 1) + o2) = tl;
+          }
+          if (x == Wm) { *sptr(var(2, 0) + off) = z; *sptr(var(2, 1) + off) = z; }    // right image edge
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(GX_TRANSFORM_WARPS * 32) : "memory");
+        if (tt == 0) mbar_arrive_remote(leader_lr);
+        ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7): both column halves per warp =====================
+    const int quarter = warp & 3;
+    const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    pdl_wait();
+    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      const int n_tile = unit % p.n_tiles_n;
+      const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+      const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096u;
+      const uint32_t addv = addv_base + (uint32_t)(warp - 4) * 256u;
+      tc_epilogue_tile<false, 32, false, true>(
+          p, tmem_base, acc, m_tile, n_tile, quarter, 0, lane, stg, addv,
+          [&]() {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+          },
+          []() {});
+      tc_epilogue_tile<false, 32, false, true>(
+          p, tmem_base, acc, m_tile, n_tile, quarter, 1, lane, stg, addv, []() {},
+          [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_relaxed(leader_tempty0 + 8u * (uint32_t)acc);
+          });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static int encode_raw_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int rows_y) {
   EncodeTiledFn enc = get_encode_fn();
@@ -422,8 +751,11 @@ int prepare_conv_gn_tc(psld_op& op) {
   if (!env) return unsupported("disabled by PSLD_TC_FUSE_GN=0");
   // network head (ncsnpp.py:430): fp32 NCHW output, first f[1] channels of a zero-padded Cout
   const bool head = op.i[PSLD_CONV_OUT_LAYOUT] == PSLD_NCHW && op.i[PSLD_CONV_OUT_DTYPE] == PSLD_F32;
-  if (op.i[PSLD_CONV_IN_DTYPE] != PSLD_BF16 || (!head && op.i[PSLD_CONV_OUT_DTYPE] != PSLD_BF16))
-    return unsupported("bf16 in/out only");
+  const int adt = op.i[PSLD_CONV_IN_DTYPE];
+  if ((adt != PSLD_BF16 && adt != PSLD_BF16S) || (!head && op.i[PSLD_CONV_OUT_DTYPE] != adt))
+    return unsupported("bf16 or split-bf16 in/out only");
+  const bool x3 = adt == PSLD_BF16S;
+  const int cm = x3 ? 2 : 1;
   if (op.i[PSLD_CONV_IN_LAYOUT] != PSLD_NHWC || (!head && op.i[PSLD_CONV_OUT_LAYOUT] != PSLD_NHWC))
     return unsupported("NHWC only");
   if (head && (op.out[1] || op.in[2])) return unsupported("head: no statistics / residual");
@@ -431,7 +763,9 @@ int prepare_conv_gn_tc(psld_op& op) {
   if (C1 % TC_BLOCK_K || C2 % TC_BLOCK_K) return unsupported("Cin %% 64 != 0");
   if (Cout % 64 || Cout > 256 && Cout % 256) return unsupported("Cout");
   if (!((W == 32 && H >= 4) || (W == 16 && H >= 8)) || (H & (H - 1))) return unsupported("map must be 16x16+ / 32x32+ wide tiles");
-  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != PSLD_BF16) return unsupported("residual dtype");
+  if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != adt) return unsupported("residual dtype");
+  if (x3 && op.in[8] != nullptr && op.i[PSLD_CONV_EXT_C1] > 0)
+    return unsupported("no 1x1 shortcut extension in the split-bf16 variant");
   if (!op.in[0] || !op.in[4] || !op.in[6] || !op.out[0] || (C2 > 0 && !op.in[1])) {
     set_error("conv_gn_tc: null pointer");
     return PSLD_EINVAL;
@@ -452,10 +786,11 @@ int prepare_conv_gn_tc(psld_op& op) {
   }
   ConvGnState* st = new (std::nothrow) ConvGnState();
   if (!st) { set_error("conv_gn_tc: out of host memory"); return PSLD_ECUDA; }
-  int rc = encode_raw_map(&st->a1, op.in[0], N, H, W, C1, BH + 2);
+  st->x3 = x3;
+  int rc = encode_raw_map(&st->a1, op.in[0], N, H, W, cm * C1, BH + 2);
   if (rc == PSLD_OK)
-    rc = C2 > 0 ? encode_raw_map(&st->a2, op.in[1], N, H, W, C2, BH + 2)
-                : encode_raw_map(&st->a2, op.in[0], N, H, W, C1, BH + 2);
+    rc = C2 > 0 ? encode_raw_map(&st->a2, op.in[1], N, H, W, cm * C2, BH + 2)
+                : encode_raw_map(&st->a2, op.in[0], N, H, W, cm * C1, BH + 2);
   // optional 1x1 shortcut over a second, un-normalised input cat(e1, e2): extra K-blocks
   const int E1 = op.i[PSLD_CONV_EXT_C1], E2 = op.i[PSLD_CONV_EXT_C2];
   const bool ext = op.in[8] != nullptr && E1 > 0;
@@ -465,12 +800,13 @@ int prepare_conv_gn_tc(psld_op& op) {
   }
   if (rc == PSLD_OK)
     rc = ext ? encode_raw_map(&st->e1, op.in[8], N, H, W, E1, BH + 2)
-             : encode_raw_map(&st->e1, op.in[0], N, H, W, C1, BH + 2);
+             : encode_raw_map(&st->e1, op.in[0], N, H, W, cm * C1, BH + 2);
   if (rc == PSLD_OK)
     rc = (ext && E2 > 0) ? encode_raw_map(&st->e2, op.in[9], N, H, W, E2, BH + 2)
-                         : encode_raw_map(&st->e2, op.in[0], N, H, W, C1, BH + 2);
+                         : encode_raw_map(&st->e2, op.in[0], N, H, W, cm * C1, BH + 2);
   const int K = 9 * (C1 + C2) + (ext ? E1 + E2 : 0);
-  if (rc == PSLD_OK) rc = encode_w_half_map(&st->b, op.in[4], Cout, K, block_n / 2);
+  // split bf16: weight planes [2][Cout, K] seen as one [2*Cout, K] matrix
+  if (rc == PSLD_OK) rc = encode_w_half_map(&st->b, op.in[4], cm * Cout, K, block_n / 2);
   if (rc != PSLD_OK) { delete st; return rc; }
   ConvGnParams& g = st->p;
   ConvTcParams& p = g.c;
@@ -494,6 +830,7 @@ int prepare_conv_gn_tc(psld_op& op) {
   p.block_n = block_n; p.n_tiles_n = Cout / block_n;
   p.M = (int64_t)N * H * W;
   p.num_tiles = (int)(((m_tiles + 1) / 2) * p.n_tiles_n);
+  p.lo1 = C1; p.lo2 = C2; p.loe1 = E1; p.loe2 = E2; p.w_lo_rows = Cout;
   g.affine = (const float*)op.in[6];
   g.cin = C1 + C2;
   g.silu = op.i[PSLD_CONV_GN_SILU];
@@ -506,6 +843,8 @@ int prepare_conv_gn_tc(psld_op& op) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GN_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gn_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_gn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete st;
@@ -528,8 +867,12 @@ int release_conv_gn_tc(psld_op& op) {
 int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
   const ConvGnState* st = (const ConvGnState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
-  PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
-                             s, 2, st->a1, st->a2, st->b, st->e1, st->e2, st->p));
+  if (st->x3)
+    PSLD_CHECK_CUDA(launch_pdl(conv_gn_x3_kernel, dim3((unsigned)st->grid), dim3(GX_THREADS), GX_SMEM_BYTES,
+                               s, 2, st->a1, st->a2, st->b, st->p));
+  else
+    PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
+                               s, 2, st->a1, st->a2, st->b, st->e1, st->e2, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

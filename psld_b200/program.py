@@ -97,7 +97,9 @@ class Plan:
     def _gn_fusable(self, x1, x2, cout):
         """Host mirror of prepare_conv_gn_tc (csrc/conv_gn_tc.cu): can act(GroupNorm(x)) -> conv3x3
         run as ONE kernel that normalises its input tile in shared memory?"""
-        if not self.bf16 or not self.fuse_gn or os.environ.get("PSLD_TC_FUSE_GN", "1") == "0":
+        if not self.tc or not self.fuse_gn or os.environ.get("PSLD_TC_FUSE_GN", "1") == "0":
+            return False
+        if self.x3 and os.environ.get("PSLD_X3_FUSE_GN", "1") == "0":
             return False
         N, H, W, C1 = x1.shape
         C2 = x2.shape[-1] if x2 is not None else 0
@@ -132,7 +134,10 @@ class Plan:
         if not self.stat_chunks or self.stat_used[-1] + need > self.stat_chunks[-1].numel():
             if len(self.stat_chunks) == self._STAT_SLOTS:
                 raise RuntimeError("psld_b200: GroupNorm statistics arena exhausted")
-            self.stat_chunks.append(self._new(max(self._STAT_CHUNK, need), dtype=torch.float64))
+            # arena size grows with the batch (~18 K doubles per sample for the CIFAR-10 net): at most
+            # _STAT_SLOTS arenas may be needed, whatever the batch
+            chunk = max(self._STAT_CHUNK, 1 << int(self.B * 6000).bit_length())
+            self.stat_chunks.append(self._new(max(chunk, need), dtype=torch.float64))
             self.stat_used.append(0)
         off = self.stat_used[-1]
         self.stat_used[-1] = off + need
@@ -314,6 +319,9 @@ class Plan:
                 op.f[1] = float(Cout)
             elif out_nchw_f32:
                 op.f[1] = float(Cout)
+            if self.x3:      # weight planes [2][Cout, K]
+                hi = wt.to(torch.bfloat16)
+                wt = torch.cat([hi, (wt - hi.to(torch.float32)).to(torch.bfloat16)], 0)
             wt = self._w(wt, torch.bfloat16)
             op.inp[4] = wt.data_ptr()
             mg = None
@@ -470,6 +478,8 @@ class Plan:
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
             gn1 = self.fuse_gn_residual or os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
+            if gn1 and hasattr(m, "Conv_2") and self.x3:
+                gn1 = False          # the split-bf16 fused kernel has no 1x1 shortcut extension
             if gn1 and hasattr(m, "Conv_2"):
                 # blocks with a Conv_2 shortcut keep the unfused Conv_1 (apply pass + conv_tc with
                 # the shortcut as K-extension): the fused kernel accepts the extension too, but its

@@ -139,6 +139,54 @@ def test_conv_tc_x3_fused_shortcut(case):
     assert rel_l2(val(out).permute(0, 3, 1, 2), ref) <= 2e-5
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 0, 64), (3, 32, 32, 256, 0, 256), (2, 16, 16, 128, 128, 256),
+                                  (5, 16, 16, 256, 0, 128), (1, 32, 32, 256, 128, 256), (37, 16, 16, 256, 0, 256)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_conv_gn_fused_x3(case, silu):
+    """GroupNorm(+SiLU)-on-load 3x3 conv of the split-bf16 tier (conv_gn_x3_kernel: fp32 normalisation of
+    the raw hi+lo tile in shared memory, two-phase transform around a single operand set, three MMA
+    groups per tap) vs the fp64 definition."""
+    N, H, W, C1, C2, Cout = case
+    r = _rng(sum(case) + 5)
+    x1 = _s(r.standard_normal((N, H, W, C1)) * 1.7 + 0.3)
+    x2 = _s(r.standard_normal((N, H, W, C2)) * 0.6 - 0.2) if C2 else None
+    Cin = C1 + C2
+    w = _t(r.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9))
+    b = _t(0.1 * r.standard_normal(Cout))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cin)), 0.2 * r.standard_normal((N, Cin))], -1))
+    res = _s(r.standard_normal((N, H, W, Cout)))
+    temb = _t(r.standard_normal((N, Cout)))
+    kw = dict(residual=res, temb=temb, temb_off=0, temb_bstride=Cout, scale=0.7071)
+    op, out, keep = conv_op(x1, x2, w, b, engine=L.ENGINE_TC_GN, mg_stats=True, affine=aff, gn_silu=silu, **kw)
+    run_op(op, prepare=True)
+    xx = val(x1).double().cpu() if x2 is None else torch.cat([val(x1).double().cpu(), val(x2).double().cpu()], -1)
+    a = xx * aff.double().cpu()[:, None, None, :, 0] + aff.double().cpu()[:, None, None, :, 1]
+    if silu:
+        a = F.silu(a)
+    ref = conv_ref(a, None, w, b, **kw)
+    err, emx = rel_l2(val(out).permute(0, 3, 1, 2), ref), max_rel(val(out).permute(0, 3, 1, 2), ref)
+    print(f"x3 GN-fused conv {case} silu={silu}: rel-L2 {err:.2e} max {emx:.2e}")
+    assert err <= 2e-5 and emx <= 3e-5, (err, emx)
+    mref = mg_ref(ref.permute(0, 2, 3, 1))
+    assert float((keep[-1].double().cpu() - mref).abs().max()) <= 3e-5 * float(mref.abs().max())
+
+
+def test_conv_gn_fused_x3_output_head():
+    """Final act(GroupNorm(h)) -> conv3x3 -> 6 channels as fp32 NCHW through the split-bf16 fused kernel."""
+    r = _rng(78)
+    N, H, W, Cin = 3, 32, 32, 128
+    x = _s(r.standard_normal((N, H, W, Cin)) * 1.3 + 0.1)
+    w = _t(r.standard_normal((6, Cin, 3, 3)) / 34.0)
+    b = _t(0.1 * r.standard_normal(6))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cin)), 0.2 * r.standard_normal((N, Cin))], -1))
+    op, out, keep = conv_op(x, None, w, b, engine=L.ENGINE_TC_GN, out_nchw_f32=True, affine=aff, gn_silu=True)
+    run_op(op, prepare=True)
+    a = F.silu(val(x).double().cpu() * aff.double().cpu()[:, None, None, :, 0] + aff.double().cpu()[:, None, None, :, 1])
+    ref = conv_ref(a, None, w, b)
+    assert out.shape == (N, 6, H, W)
+    assert rel_l2(out, ref) <= 2e-5
+
+
 def test_memory_bound_kernels_on_split_tensors():
     """GroupNorm(+SiLU) over a virtual concat, the three FIR resamplers and the CUDA-core attention
     core with split-bf16 input and output vs fp64 references of the same (hi + lo) inputs."""
