@@ -31,7 +31,7 @@ for line in sass.splitlines():
         body[cur].append(line.strip())
 for fn, lines in body.items():
     name = demangle(fn)
-    if not re.search(r"conv_tc_kernel|conv_gn_tc_kernel|attn_tc_kernel", name):
+    if not re.search(r"conv_tc_kernel|conv_gn_tc_kernel|conv_gn_x3_kernel|attn_tc_kernel", name):
         continue
     cnt = collections.Counter()
     first = {}
