@@ -61,7 +61,8 @@ def parse():
                     help="tier on the main line (the other tensor-core tier is reported as <tier>_path)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other tensor-core tier")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager GPU context baseline")
-    ap.add_argument("--state", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--state", default="float64", choices=["float32", "float64"],
+                    help="sampler state dtype (the reference's state is float64 after the first step)")
     ap.add_argument("--e2e-nfe", type=int, default=NFE, help="0 disables the end-to-end run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -438,12 +439,19 @@ def main_b200(args):
     lib = L.lib()
     state_dtype = torch.float32 if args.state == "float32" else torch.float64
     # fused phase-space update alone (HBM-bound), timed at this batch
-    upd = time_update(lib, main["_state"], main["_plan"], B, 3 * H * H, L.stream_ptr(dev), dev, state_dtype,
-                      sde, ts)
-    upd["peak"] = pk["hbm"]
-    upd["frac"] = upd["achieved"] / pk["hbm"]
-    if "achieved" in upd.get("large", {}):
-        upd["large"]["frac"] = upd["large"]["achieved"] / pk["hbm"]
+    def _update_roofline(sd):
+        st = main["_state"] if sd == state_dtype else main["_state"].to(sd)
+        u = time_update(lib, st, main["_plan"], B, 3 * H * H, L.stream_ptr(dev), dev, sd, sde, ts)
+        u["peak"] = pk["hbm"]
+        u["frac"] = u["achieved"] / pk["hbm"]
+        u["state_dtype"] = "float64" if sd == torch.float64 else "float32"
+        if "achieved" in u.get("large", {}):
+            u["large"]["frac"] = u["large"]["achieved"] / pk["hbm"]
+        return u
+
+    upd = _update_roofline(state_dtype)
+    other_sd = torch.float32 if state_dtype == torch.float64 else torch.float64
+    upd["other_state_dtype"] = _update_roofline(other_sd)      # the throughput / reference-faithful twin
 
     # ---- the other tensor-core tier, stated separately (north_star: "the bf16 score_fn path stated
     # separately"): same workload, same measurement, its own roofline and end-to-end number

@@ -39,7 +39,7 @@ if [ "${CAPTURES:-1}" = "1" ]; then
 fi
 if [ "${MEMCHECK:-1}" = "1" ]; then
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -q --no-header -p no:cacheprovider \
-      -m gpu tests/test_gpu_x3.py -k "conv_tc_x3 or attention or memory_bound or split" > gpurun_out/memcheck_x3.log 2>&1
+      -m gpu tests/test_gpu_x3.py -k "conv_tc_x3 or conv_gn_fused or attention or memory_bound or split" > gpurun_out/memcheck_x3.log 2>&1
   echo "memcheck x3 rc=$? $(tail -n 1 gpurun_out/memcheck_x3.log)"
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -q --no-header -p no:cacheprovider \
       -m gpu tests/test_gpu_kernels.py -k "conv_tc or conv_gn or attention_tc or groupnorm or fir" > gpurun_out/memcheck_kernels.log 2>&1

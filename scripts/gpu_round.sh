@@ -16,9 +16,9 @@ PT="python -m pytest -q -rA --no-header -p no:cacheprovider --timeout 600 -m gpu
 run k_other 900 $PT tests/test_gpu_kernels.py -k "not conv_tc"
 run k_tc 600 $PT tests/test_gpu_kernels.py -k "conv_tc"
 run net_fp32 900 $PT tests/test_gpu_network.py -k "fp32 or contract or shared"
-run net_bf16 900 $PT tests/test_gpu_network.py -k "bf16"
+run net_bf16 900 $PT tests/test_gpu_network.py -k "bf16 or checkpoint or in_place"
 run sampler 1200 $PT tests/test_gpu_sampler.py
-run x3_kernels 900 $PT tests/test_gpu_x3.py -k "split or conv_tc_x3 or memory_bound or attention"
+run x3_kernels 900 $PT tests/test_gpu_x3.py -k "not (forward or sampler or trajectory or full_batch)"
 run x3_net 1500 $PT tests/test_gpu_x3.py -k "forward or sampler or trajectory or full_batch"
 run smoke 600 python __graft_entry__.py smoke
 if [ "${SKIP_BENCH:-0}" != "1" ]; then

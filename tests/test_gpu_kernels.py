@@ -354,6 +354,8 @@ CONV_TC_CASES = [
     (5, 4, 4, 64, 0, 96, 3),           # 4x4 maps, 8 images per tile, Cout = 3 x 32
     (1, 64, 64, 64, 0, 32, 3),         # CelebA-size map
     (2, 32, 32, 256, 256, 256, 1),
+    (41, 32, 32, 128, 0, 256, 3),      # 164 tile pairs over 74 clusters: persistent multi-wave loop, both accumulators
+    (37, 16, 16, 256, 128, 256, 3),    # odd tile count (partial last pair), two sources, 3 waves
 ]
 
 

@@ -2,9 +2,11 @@
 
 Tolerances (relative L2 over the whole output, stated per path):
   fp32 path (CUDA-core fp32 convolutions) ... <= 2e-5   (measured ~2e-6; fp32 summation order)
-  bf16 path (tcgen05 convolutions) .......... <= 3e-2   (bf16 activations+weights; the reference
-                                                         under bf16 autocast sits at 4e-3..6e-3
-                                                         per SURVEY.md §8c, bf16 storage adds to it)
+  bf16 path (tcgen05 convolutions) .......... <= 2e-2   (measured 0.85e-2..1.2e-2: bf16 activations +
+                                                         weights; the reference under bf16 autocast
+                                                         sits at 4e-3..6e-3 per SURVEY.md §8c, bf16
+                                                         storage adds to it; gate <= 2x measured)
+  bf16x3 path (default tier) ................ <= 5e-5   (measured 1.4e-5..2.2e-5; tests/test_gpu_x3.py)
 """
 import numpy as np
 import pytest
@@ -29,7 +31,7 @@ def _full(c):
 
 
 @pytest.mark.parametrize("name", ["tiny", "mid", "cifar10", "celeba64"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
 def test_forward_vs_golden(golden_dir, name, precision, tol):
     g = np.load(f"{golden_dir}/forward_{name}.npz")
     cfg = CASES[name]()
@@ -133,14 +135,23 @@ def test_in_place_weight_update_invalidates_plans():
 
 
 @pytest.mark.parametrize("sf,B,precision,tol", [
-    (dict(nf=96, ch_mult=[1, 2], num_res_blocks=1), 3, "bf16", 3e-2),     # channels 96/192/288: SIMT fallbacks, odd group sizes
-    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 5, "bf16", 3e-2),  # 8x8 level, 2 images per tile, odd batch
-    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 1, "bf16", 3e-2),  # single sample (single-tile layers)
+    (dict(nf=96, ch_mult=[1, 2], num_res_blocks=1), 3, "bf16", 2e-2),     # channels 96/192/288: SIMT fallbacks, odd group sizes
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 5, "bf16", 2.4e-2),  # 8x8 level, 2 images per tile, odd batch
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 1, "bf16", 2.4e-2),  # single sample (single-tile layers)
     (dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, fir=False, progressive_input="none",
           embedding_type="positional"), 2, "fp32", 2e-5),                 # ablation-script architecture flags
     (dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, fir=False, progressive_input="none",
-          embedding_type="positional"), 2, "bf16", 3e-2),
+          embedding_type="positional"), 2, "bf16", 2.4e-2),
     (dict(nf=32, ch_mult=[1, 2], num_res_blocks=1, out_ch=3), 2, "fp32", 2e-5),   # score_m nets (out_ch = C)
+    # the default tier (bf16x3) on the same odd shapes: split-bf16 CUDA-core fallbacks, 8x8 tiles with two
+    # images, single-sample plans, the ablation-script switches, score_m nets
+    (dict(nf=96, ch_mult=[1, 2], num_res_blocks=1), 3, "bf16x3", 5e-5),
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 5, "bf16x3", 5e-5),
+    (dict(nf=64, ch_mult=[1, 1, 2], num_res_blocks=1), 1, "bf16x3", 5e-5),
+    (dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, fir=False, progressive_input="none",
+          embedding_type="positional"), 2, "bf16x3", 5e-5),
+    (dict(nf=32, ch_mult=[1, 2], num_res_blocks=1, out_ch=3), 2, "bf16x3", 5e-5),
+    (dict(nf=128, ch_mult=[1, 2, 2, 2], num_res_blocks=1, attn_resolutions=[8]), 2, "bf16x3", 5e-5),  # attention at 8x8 only
 ])
 def test_forward_odd_configs_vs_oracle(sf, B, precision, tol):
     """Shapes outside the tensor-core sweet spot, odd batches and the non-default architecture
@@ -186,4 +197,4 @@ def test_full_size_workload_properties():
     y32 = net32(x[idx].contiguous(), t[:4])
     e_prec = rel_l2(ys, y32)
     print(f"B=256 vs B=4 plan {e_shard:.3e}; shared time row {e_row:.3e}; bf16 vs fp32 path {e_prec:.3e}")
-    assert e_shard <= 1e-3 and e_row <= 1e-3 and e_prec <= 3e-2
+    assert e_shard <= 1e-3 and e_row <= 1e-3 and e_prec <= 2e-2

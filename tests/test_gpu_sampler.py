@@ -6,7 +6,8 @@ Tolerances, relative to max|ref| (trajectories with random weights expand, SURVE
       (limited by the fp32 score network boundary, not by the fused update: ~1e-8 measured on CPU)
   tiny NCSN++, fp32 network, fp64 state, 100 NFE .... rel-L2 <= 1e-5, max-abs/max|ref| <= 1e-5
       (measured on B200: 3.4e-7 / 3.9e-7)
-  bf16 network path (stated separately) ............. rel-L2 <= 2e-2 (measured 2.7e-3)
+  bf16 network path (stated separately) ............. rel-L2 <= 6e-3 (measured 3.1e-3; gate <= 2x)
+  bf16x3 network path (default tier) ................ rel-L2 <= 1e-4 (measured 4.8e-6; tests/test_gpu_x3.py)
 """
 import numpy as np
 import pytest
@@ -149,7 +150,7 @@ def test_native_sampler_vs_reference_golden(golden_dir, kind, fname):
     out16, _, _ = _run(cfg, net16, u0, nb, fuse=True, record=False)
     e16 = rel_l2(out16, torch.from_numpy(g["final"]))
     print(f"bf16 network path: final rel-L2 {e16:.3e}")
-    assert e16 <= 2e-2
+    assert e16 <= 6e-3
 
 
 def test_native_equals_generic_path():
@@ -459,4 +460,4 @@ def test_native_sampler_celeba64_vs_oracle():
     out16, _, _ = _run(cfg, net16, u0, nb, fuse=True, record=False)
     e16 = rel_l2(out16, ref)
     print(f"celeba64 SSCS {n}+1 NFE: fp32 path rel-L2 {e:.3e}, bf16 path {e16:.3e}")
-    assert e <= 1e-5 and e16 <= 2e-2
+    assert e <= 1e-5 and e16 <= 1.4e-2
