@@ -358,7 +358,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5
 #pragma unroll 1
       for (int half = 0; half < 2; ++half)
-        tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_acc, 0, m_tile, 0, quarter, half, lane,
+        tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_acc, 0, m_tile, 0, p.ep.block_n, quarter, half, lane,
                                                          stg_base + (uint32_t)ew * 4096u,
                                                          addv_base + (uint32_t)ew * 256u, []() {}, []() {});
     } else {

@@ -356,7 +356,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       tc_epilogue_tile<true, 32, false>(
-          p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, half, lane,
           stg_base + (uint32_t)(warp - 4) * 2048u, addv_base + (uint32_t)(warp - 4) * 256u,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -682,14 +682,14 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096u;
       const uint32_t addv = addv_base + (uint32_t)(warp - 4) * 256u;
       tc_epilogue_tile<false, 32, false, true>(
-          p, tmem_base, acc, m_tile, n_tile, quarter, 0, lane, stg, addv,
+          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, 0, lane, stg, addv,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
           },
           []() {});
       tc_epilogue_tile<false, 32, false, true>(
-          p, tmem_base, acc, m_tile, n_tile, quarter, 1, lane, stg, addv, []() {},
+          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, 1, lane, stg, addv, []() {},
           [&]() {
             tc_fence_before();
             __syncwarp();

@@ -47,7 +47,7 @@
 namespace psld {
 
 struct ConvTcState {
-  CUtensorMap a1, a2, b, e1, e2;
+  CUtensorMap a1, a2, b, b2, e1, e2;      // b2: weight map with the N-slice box of the split tail units
   ConvTcParams p;
   int grid;
   bool pair;      // 2-CTA (cta_group::2) variant
@@ -65,8 +65,9 @@ __device__ long long g_tc_trace[160 * 8];
 template <bool kPair, bool kX3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmE1,
-               const __grid_constant__ CUtensorMap tmE2, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmE1, const __grid_constant__ CUtensorMap tmE2,
+               const ConvTcParams p) {
   using Cfg = TcCfg<kPair, kX3>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -127,7 +128,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // K = taps x input channels, optionally followed by a 1x1 "extension" over a second input
   // (the residual block's Conv_2 shortcut accumulated into the same tile, layerspp.py:269-274)
   const int total_kb = p.taps * p.kchunks + p.ext_kchunks;
-  const int b_rows = kPair ? (p.block_n >> 1) : p.block_n;        // weight rows this CTA loads
+  // virtual unit v -> (unit, N slice): full units first, then the N-split units of the last round
+  auto decode = [&](int v, int& unit, int& nsub, int& bn) {
+    if (v < p.tail_start) {
+      unit = v; nsub = -1; bn = p.block_n;
+    } else {
+      const int t = v - p.tail_start;
+      const int u = t / p.n_split;
+      unit = p.tail_start + u; nsub = t - u * p.n_split; bn = p.block_n / p.n_split;
+    }
+  };
 
   if (warp == 0 || warp == 10) {
     // ===================== TMA producers (both CTAs of a pair) =====================
@@ -138,25 +148,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     {
       const bool is_a = warp == 0;
       if (is_a) pdl_wait();     // activations come from the previous kernel; weights do not
-      const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) *
-                             (kPair ? 2u : 1u) * (kX3 ? 2u : 1u);
+      const uint32_t tx_mul = (kPair ? 2u : 1u) * (kX3 ? 2u : 1u);
       // one A / B tile of this stage (kX3: called for the hi half, then for the lo half)
       auto load_a = [&](uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int x, int y, int n) {
         if (kPair) tma_load_4d_pair(dst, tm, bar, c, x, y, n);
         else tma_load_4d(dst, tm, bar, c, x, y, n);
       };
-      auto load_b = [&](uint32_t dst, uint32_t bar, int k, int row) {
-        if (kPair) tma_load_2d_pair(dst, &tmB, bar, k, row);
-        else tma_load_2d(dst, &tmB, bar, k, row);
+      auto load_b = [&](uint32_t dst, const CUtensorMap* tm, uint32_t bar, int k, int row) {
+        if (kPair) tma_load_2d_pair(dst, tm, bar, k, row);
+        else tma_load_2d(dst, tm, bar, k, row);
       };
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        decode(v, unit, nsub, bn);
         const int n_tile = unit % p.n_tiles_n;
         const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
         const int n0 = (m_tile / p.tiles_y) * p.BN_img;
         const int y0 = (m_tile % p.tiles_y) * p.BH * p.stride - p.pad;
-        const int bn0 = n_tile * p.block_n + (kPair ? (int)rank * b_rows : 0);
+        const int b_rows = kPair ? (bn >> 1) : bn;                 // weight rows this CTA loads
+        const CUtensorMap* tmW = nsub < 0 ? &tmB : &tmB2;
+        const int bn0 = n_tile * p.block_n + (nsub < 0 ? 0 : nsub * bn) + (kPair ? (int)rank * b_rows : 0);
+        const uint32_t my_tx = (is_a ? (uint32_t)TC_A_BYTES : (uint32_t)b_rows * TC_BLOCK_K * 2) * tx_mul;
         int kb = 0;
         for (int ky = 0; ky < p.KS; ++ky) {
           for (int kx = 0; kx < p.KS; ++kx) {
@@ -174,9 +188,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     load_a(sa + TC_A_BYTES, tmA, full_bar(stage), c0 + (s1 ? p.lo1 : p.lo2), kx - p.pad,
                            y0 + ky, n0);
                 } else {
-                  load_b(sa + Cfg::kBOff, full_bar(stage), kb * TC_BLOCK_K, bn0);
+                  load_b(sa + Cfg::kBOff, tmW, full_bar(stage), kb * TC_BLOCK_K, bn0);
                   if (kX3)
-                    load_b(sa + Cfg::kBOff + Cfg::kBBytes, full_bar(stage), kb * TC_BLOCK_K,
+                    load_b(sa + Cfg::kBOff + Cfg::kBBytes, tmW, full_bar(stage), kb * TC_BLOCK_K,
                            bn0 + p.w_lo_rows);
                 }
               }
@@ -199,9 +213,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 load_a(sa + TC_A_BYTES, tmE, full_bar(stage), c0 + (s1 ? p.loe1 : p.loe2), 0,
                        y0 + p.pad, n0);
             } else {
-              load_b(sa + Cfg::kBOff, full_bar(stage), kb * TC_BLOCK_K, bn0);
+              load_b(sa + Cfg::kBOff, tmW, full_bar(stage), kb * TC_BLOCK_K, bn0);
               if (kX3)
-                load_b(sa + Cfg::kBOff + Cfg::kBBytes, full_bar(stage), kb * TC_BLOCK_K,
+                load_b(sa + Cfg::kBOff + Cfg::kBBytes, tmW, full_bar(stage), kb * TC_BLOCK_K,
                        bn0 + p.w_lo_rows);
             }
           }
@@ -217,15 +231,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // instruction in an ELECT / R2UR.BROADCAST sequence and the issue loop itself (about 120
     // instructions per k-block, never waiting on a barrier) paces the tensor pipe.
     if (rank == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128 (256 for a pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        decode(v, unit, nsub, bn);
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128 (256 for a pair)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) |
+                               ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
         if (kPair) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
@@ -233,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (kb == 0 && unit == unit0) TC_TRACE(2);
+          if (kb == 0 && v == unit0) TC_TRACE(2);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + Cfg::kBOff);
@@ -277,11 +292,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     pdl_wait();                 // residual / temb reads and every global write come after this
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
-      const int n_tile = unit % p.n_tiles_n;
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+      int unit, nsub, bn;
+      decode(v, unit, nsub, bn);
+      const int n_tile = nsub < 0 ? unit % p.n_tiles_n : (unit % p.n_tiles_n) * p.n_split + nsub;   // in units of bn
       const int m_tile = kPair ? 2 * (unit / p.n_tiles_n) + (int)rank : unit / p.n_tiles_n;
       tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(
-          p, tmem_base, acc, m_tile, n_tile, quarter, half, lane,
+          p, tmem_base, acc, m_tile, n_tile, bn, quarter, half, lane,
           stg_base + (uint32_t)(warp - 2) * 4096u, addv_base + (uint32_t)(warp - 2) * 256u,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -445,6 +462,7 @@ int prepare_conv_tc(psld_op& op) {
   // split bf16 weights: two planes [2][Cout, K] seen as one [2*Cout, K] matrix
   if (rc == PSLD_OK) rc = encode_w_map(&st->b, op.in[4], cm * Cout, K, pair ? block_n / 2 : block_n);
   if (rc != PSLD_OK) { delete st; return rc; }
+  st->b2 = st->b;
 
   ConvTcParams& p = st->p;
   p.bias = (const float*)op.in[5];
@@ -477,11 +495,40 @@ int prepare_conv_tc(psld_op& op) {
   const int64_t m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
   p.num_tiles = (int)(m_units * p.n_tiles_n);          // work units (tiles, or tile pairs)
   st->pair = pair;
+  // ---- last partial round: split its units along N when that lets the idle clusters share the work
+  // (16x16 CIFAR layers at B = 256: 256 tile pairs over 74 clusters = 3 rounds + 34 units; as 68
+  // half-N units the tail costs half a round: 4 -> 3.5 rounds).  PSLD_TC_TAIL_SPLIT=0 disables it.
+  {
+    static const int split_env = [] {
+      const char* e = getenv("PSLD_TC_TAIL_SPLIT");
+      return e ? atoi(e) : 1;
+    }();
+    const int workers = pair ? sms / 2 : sms;
+    const int full = p.num_tiles / workers, tail = p.num_tiles % workers;
+    int best = 1;
+    double best_cost = full + (tail > 0 ? 1.0 : 0.0);
+    if (split_env && tail > 0 && !head) {
+      for (int ns : {2, 4}) {
+        const int sub = block_n / ns;
+        if (block_n % ns || sub < 64 || sub % 64) continue;
+        const double cost = full + (double)((tail * ns + workers - 1) / workers) / ns;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+      }
+    }
+    p.n_split = best;
+    p.tail_start = best > 1 ? p.num_tiles - tail : p.num_tiles;
+    p.num_virtual = p.tail_start + (p.num_tiles - p.tail_start) * best;
+    if (best > 1) {
+      const int sub = block_n / best;
+      rc = encode_w_map(&st->b2, op.in[4], cm * Cout, K, pair ? sub / 2 : sub);
+      if (rc != PSLD_OK) { delete st; return rc; }
+    }
+  }
   if (pair) {
     const int pairs = sms / 2;
-    st->grid = 2 * (p.num_tiles < pairs ? p.num_tiles : pairs);
+    st->grid = 2 * (p.num_virtual < pairs ? p.num_virtual : pairs);
   } else {
-    st->grid = p.num_tiles < sms ? p.num_tiles : sms;
+    st->grid = p.num_virtual < sms ? p.num_virtual : sms;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -522,7 +569,7 @@ int run_conv_tc(const psld_op& op, cudaStream_t s) {
 #define CONV_TC_LAUNCH(PAIR, X3)                                                               \
   PSLD_CHECK_CUDA(launch_pdl(conv_tc_kernel<PAIR, X3>, dim3((unsigned)st->grid), dim3(TC_THREADS), \
                              TcCfg<PAIR, X3>::kSmemBytes, s, PAIR ? 2 : 1, st->a1, st->a2, st->b,  \
-                             st->e1, st->e2, st->p))
+                             st->b2, st->e1, st->e2, st->p))
   if (st->pair) {
     if (st->x3) CONV_TC_LAUNCH(true, true); else CONV_TC_LAUNCH(true, false);
   } else {

@@ -44,6 +44,10 @@ struct ConvTcParams {
   // 1 / 2 / shortcut 1 / shortcut 2 (= the source's channel count) and row offset of the lo plane of
   // the weight matrix (= its padded Cout); the output / residual rows are [Cout hi | Cout lo]
   int lo1, lo2, loe1, loe2, w_lo_rows;
+  // last partial round: units >= tail_start are processed as n_split N-slices of block_n / n_split
+  // channels each ("virtual units" tail_start + (u - tail_start) * n_split + slice), so that the
+  // clusters that would idle in that round share its work; num_virtual = total loop trip count
+  int tail_start, n_split, num_virtual;
 };
 
 
@@ -176,6 +180,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 // NCHW network head) + GroupNorm micro-group statistics.  Called by the 8 epilogue warps;
 // `quarter` = TMEM lane quarter (warp id % 4), `half` selects alternate column groups, `stg` =
 // this warp's 4 KB staging tile and `addv` its 256 B additive-vector slot in shared memory.
+// `bn` = N width of THIS tile (p.block_n, or a fraction of it for the N-split units of the last
+// partial round), `n_tile` = index in units of `bn`.
 // `acquire()` is called once before the first TMEM access (it waits for the accumulator),
 // `release()` right after this warp's LAST TMEM read (it hands the accumulator back to the MMA
 // warp before the global stores are issued, so the release never waits on them).
@@ -187,7 +193,7 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 template <bool kPrefetchRes = true, int GC = 64, bool kTmemAhead = true, bool kSplit = false,
           class Acquire, class Release>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int acc,
-                                                 int m_tile, int n_tile, int quarter, int half,
+                                                 int m_tile, int n_tile, const int bn, int quarter, int half,
                                                  int lane, uint32_t stg, uint32_t addv,
                                                  Acquire acquire, Release release) {
   static_assert(GC == 64 || GC == 32, "staging group = 64 or 32 columns");
@@ -197,7 +203,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
   const bool valid = m < p.M;
   const int slot = m_tile * 4 + quarter;             // 32-row slot of the micro-group stats
   const bool stats = p.mg_stats != nullptr && (int64_t)slot * 32 < p.M;
-  if (p.y != nullptr && (p.block_n & (GC - 1)) == 0 && (p.HW & 31) == 0) {
+  if (p.y != nullptr && (bn & (GC - 1)) == 0 && (p.HW & 31) == 0) {
     // ---- staged path: GC-column groups go through a per-warp 32 x (2*GC) B shared-memory tile
     // (16-byte chunks XOR-swizzled by row) so that BOTH the residual loads and the output
     // stores hit global memory as full 128-byte (GC = 32: 64-byte) row segments, 4 (8) rows per
@@ -215,7 +221,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     const int64_t m_base = (int64_t)m_tile * TC_BLOCK_M + quarter * 32;
     const bool full = m_base + 32 <= p.M;             // warp-uniform: no per-row bounds checks
     const int sub_row = lane / CPR, chunk = lane % CPR;
-    const int ncg = p.block_n / GC;
+    const int ncg = bn / GC;
     constexpr uint32_t TILE = 32u * RB;               // bytes of one staging tile
     const int64_t ldo = (int64_t)p.Cout * NT;          // output / residual row stride (elements)
     const uint32_t my_row = stg + (uint32_t)lane * RB;
@@ -227,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_add = [&](int cg) {
       if (lane < GC / 4) {
-        const int c = n_tile * p.block_n + cg * GC + 4 * lane;
+        const int c = n_tile * bn + cg * GC + 4 * lane;
         av = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (tembw) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(tembw + c));
@@ -239,7 +245,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     auto load_res = [&](int cg) {
 #pragma unroll
       for (int pl = 0; pl < NT; ++pl) {
-        const __nv_bfloat16* rp = p.res + (int64_t)n_tile * p.block_n + cg * GC + chunk * 8 +
+        const __nv_bfloat16* rp = p.res + (int64_t)n_tile * bn + cg * GC + chunk * 8 +
                                   (m_base + sub_row) * ldo + pl * p.Cout;
         if (full) {
 #pragma unroll
@@ -346,7 +352,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
     acquire();
     if (half >= ncg) release();
     for (int cg = half; cg < ncg; cg += 2) {
-      const int co_base = n_tile * p.block_n + cg * GC;
+      const int co_base = n_tile * bn + cg * GC;
       const bool more = cg + 2 < ncg;
       if (lane < GC / 4)
         sts128(addv + (uint32_t)lane * 16u, __float_as_uint(av.x * scale), __float_as_uint(av.y * scale),
@@ -424,19 +430,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvTcParams& p, uint32_t
   const float* temb = p.temb ? p.temb + (int64_t)img * p.temb_bstride + p.temb_off : nullptr;
   const bool has_res = valid && p.res != nullptr;
   uint4 rq[4];                                       // residual of the chunk being processed
-  if (has_res && half * 32 < p.block_n) {
-    const __nv_bfloat16* rp = p.res + m * p.Cout + n_tile * p.block_n + half * 32;
+  if (has_res && half * 32 < bn) {
+    const __nv_bfloat16* rp = p.res + m * p.Cout + n_tile * bn + half * 32;
 #pragma unroll
     for (int t = 0; t < 4; ++t) rq[t] = *reinterpret_cast<const uint4*>(rp + 8 * t);
   }
-  for (int ch = half * 32; ch < p.block_n; ch += 64) {
+  for (int ch = half * 32; ch < bn; ch += 64) {
     uint32_t r[32];
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                            (uint32_t)acc * 256u + (uint32_t)ch;
     tmem_ld32(taddr, r);
-    const int co0 = n_tile * p.block_n + ch;
+    const int co0 = n_tile * bn + ch;
     uint4 rn[4];                                     // prefetch the next chunk's residual
-    const bool more = ch + 64 < p.block_n;
+    const bool more = ch + 64 < bn;
     if (has_res && more) {
       const __nv_bfloat16* rp = p.res + m * p.Cout + co0 + 64;
 #pragma unroll

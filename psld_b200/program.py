@@ -117,6 +117,8 @@ class Plan:
         E1 = e1.shape[-1]
         E2 = e2.shape[-1] if e2 is not None else 0
         pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        if self.x3 and (H * W) % 32:        # split-bf16 output goes through the staged epilogue only
+            return False
         return (Cb % 64 == 0 and E1 % 64 == 0 and E2 % 64 == 0 and cout % 32 == 0 and pow2(W)
                 and pow2(H) and 4 <= W <= 128 and tuple(e1.shape[:3]) == (N, H, W))
 
