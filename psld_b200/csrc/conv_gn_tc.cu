@@ -57,7 +57,7 @@ struct ConvGnParams {
 };
 
 struct ConvGnState {
-  CUtensorMap a1, a2, b, e1, e2;
+  CUtensorMap a1, a2, b, b2, e1, e2;     // b2: weight map with the N-slice box of the split tail units
   ConvGnParams p;
   int grid;
   bool x3;       // split-bf16 operands: conv_gn_x3_kernel
@@ -80,7 +80,8 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 __global__ void __launch_bounds__(GN_THREADS, 1)
 conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmE1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmE1,
                   const __grid_constant__ CUtensorMap tmE2, const ConvGnParams gp) {
   const ConvTcParams& p = gp.c;
   extern __shared__ uint8_t smem_raw[];
@@ -143,7 +144,6 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   // (setmaxnreg re-balancing between the warpgroups was tried: ptxas lowers the budget of the
   // .dec branches but does not raise the epilogue's above the launch-bound value, so it only
   // added spills; all warps keep the launch allocation.)
-  const int b_rows = p.block_n >> 1;
   const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
   // K = 9 taps x normalised input chunks, then the 1x1 shortcut chunks over a second, raw input
   const int total_chunks = p.kchunks + p.ext_kchunks;
@@ -154,7 +154,9 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (lane == 0) {
       int buf = 0;
       uint32_t ph = 0;
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
         const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
         const int n0 = m_tile / p.tiles_y;
         const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
@@ -181,10 +183,14 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     {
       int stage = 0;
       uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)b_rows * 128u * 2u;
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
         const int n_tile = unit % p.n_tiles_n;
-        const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
+        const int b_rows = bn >> 1;
+        const CUtensorMap* tmW = nsub < 0 ? &tmB : &tmB2;
+        const int bn0 = n_tile * p.block_n + (nsub < 0 ? 0 : nsub * bn) + (int)rank * b_rows;
+        const uint32_t tx = (uint32_t)b_rows * 128u * 2u;
         for (int cc = 0; cc < total_chunks; ++cc) {
           const int ntap = cc < p.kchunks ? 9 : 1;
           for (int t9 = 0; t9 < ntap; ++t9) {
@@ -192,7 +198,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             mbar_wait(b_empty(stage), ph ^ 1);
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
-              tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, &tmB, b_full(stage),
+              tma_load_2d_pair(bring + (uint32_t)stage * GN_B_BYTES, tmW, b_full(stage),
                                kblk * TC_BLOCK_K, bn0);
             }
             __syncwarp();
@@ -205,15 +211,17 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ===================== MMA issuer (leader CTA) =====================
     // whole warp converged, one elected lane issues (see conv_tc.cu)
     if (rank == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int buf = 0, stage = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_phase = 0;
       const uint32_t row_step = (uint32_t)p.W * 128u;       // ky * W rows
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) |
+                               ((uint32_t)(256 >> 4) << 24);
         for (int cc = 0; cc < total_chunks; ++cc) {
           mbar_wait_cluster(a_ready(buf), aph);
           tc_fence_after();
@@ -261,7 +269,9 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     int buf = 0;
     uint32_t ph = 0;
     pdl_wait();                 // the affine table comes from the GroupNorm fold just before
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       const int n0 = m_tile / p.tiles_y;
       const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
@@ -352,11 +362,13 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     pdl_wait();
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
-      const int n_tile = unit % p.n_tiles_n;
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
+      const int n_tile = nsub < 0 ? unit % p.n_tiles_n : (unit % p.n_tiles_n) * p.n_split + nsub;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       tc_epilogue_tile<true, 32, false>(
-          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, half, lane,
+          p, tmem_base, acc, m_tile, n_tile, bn, quarter, half, lane,
           stg_base + (uint32_t)(warp - 4) * 2048u, addv_base + (uint32_t)(warp - 4) * 256u,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -415,7 +427,8 @@ __device__ __forceinline__ float silu_x3(float x) { return __fdividef(x, 1.0f + 
 
 __global__ void __launch_bounds__(GX_THREADS, 1)
 conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const ConvGnParams gp) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                  const ConvGnParams gp) {
   const ConvTcParams& p = gp.c;
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
@@ -470,7 +483,6 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int b_rows = p.block_n >> 1;
   const uint32_t raw_bytes = (uint32_t)gp.rows_in * 128u;
   const int total_chunks = p.kchunks;
 
@@ -479,7 +491,9 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     pdl_wait();
     if (lane == 0) {
       uint32_t ph = 0;
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
         const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
         const int n0 = m_tile / p.tiles_y;
         const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
@@ -499,10 +513,14 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ===================== weight producer: W_hi | W_lo half tiles per (tap, chunk) =============
     int stage = 0;
     uint32_t ph = 0;
-    const uint32_t tx = (uint32_t)b_rows * 128u * 2u * 2u;       // (hi + lo) x both CTAs
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
       const int n_tile = unit % p.n_tiles_n;
-      const int bn0 = n_tile * p.block_n + (int)rank * b_rows;
+      const int b_rows = bn >> 1;
+      const CUtensorMap* tmW = nsub < 0 ? &tmB : &tmB2;
+      const int bn0 = n_tile * p.block_n + (nsub < 0 ? 0 : nsub * bn) + (int)rank * b_rows;
+      const uint32_t tx = (uint32_t)b_rows * 128u * 2u * 2u;       // (hi + lo) x both CTAs
       for (int cc = 0; cc < total_chunks; ++cc) {
         for (int t9 = 0; t9 < 9; ++t9) {
           const int kblk = gn_tap(t9) * p.kchunks + cc;
@@ -510,8 +528,8 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
             const uint32_t dst = bring + (uint32_t)stage * GX_B_STAGE;
-            tma_load_2d_pair(dst, &tmB, b_full(stage), kblk * TC_BLOCK_K, bn0);
-            tma_load_2d_pair(dst + GN_B_BYTES, &tmB, b_full(stage), kblk * TC_BLOCK_K, bn0 + p.w_lo_rows);
+            tma_load_2d_pair(dst, tmW, b_full(stage), kblk * TC_BLOCK_K, bn0);
+            tma_load_2d_pair(dst + GN_B_BYTES, tmW, b_full(stage), kblk * TC_BLOCK_K, bn0 + p.w_lo_rows);
           }
           __syncwarp();
           if (++stage == GX_B_STAGES) { stage = 0; ph ^= 1; }
@@ -521,15 +539,17 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (rank == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t cph = 0, bph = 0, acc_phase = 0;
       const uint32_t row_step = (uint32_t)p.W * 128u;       // ky * W rows
-      for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) |
+                               ((uint32_t)(256 >> 4) << 24);
         for (int cc = 0; cc < total_chunks; ++cc) {
           for (int t9 = 0; t9 < 9; ++t9) {
             if (t9 == 0) { mbar_wait_cluster(c_ready, cph); tc_fence_after(); }
@@ -588,7 +608,9 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     auto sptr = [&](uint32_t a) { return reinterpret_cast<uint4*>(smem_raw + (a - sm0)); };
     uint32_t ph = 0;
     pdl_wait();
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       const int n0 = m_tile / p.tiles_y;
       const int y0 = (m_tile % p.tiles_y) * p.BH - 1;
@@ -676,20 +698,22 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     pdl_wait();
-    for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
-      const int n_tile = unit % p.n_tiles_n;
+    for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
+      const int n_tile = nsub < 0 ? unit % p.n_tiles_n : (unit % p.n_tiles_n) * p.n_split + nsub;
       const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
       const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096u;
       const uint32_t addv = addv_base + (uint32_t)(warp - 4) * 256u;
       tc_epilogue_tile<false, 32, false, true>(
-          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, 0, lane, stg, addv,
+          p, tmem_base, acc, m_tile, n_tile, bn, quarter, 0, lane, stg, addv,
           [&]() {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
           },
           []() {});
       tc_epilogue_tile<false, 32, false, true>(
-          p, tmem_base, acc, m_tile, n_tile, p.block_n, quarter, 1, lane, stg, addv, []() {},
+          p, tmem_base, acc, m_tile, n_tile, bn, quarter, 1, lane, stg, addv, []() {},
           [&]() {
             tc_fence_before();
             __syncwarp();
@@ -838,7 +862,16 @@ int prepare_conv_gn_tc(psld_op& op) {
   g.w_shift = W == 32 ? 5 : 4;
   g.n_images = N;
   const int pairs = sms / 2;
-  st->grid = 2 * (p.num_tiles < pairs ? p.num_tiles : pairs);
+  st->b2 = st->b;
+  {
+    static const int split_env = [] { const char* e = getenv("PSLD_TC_TAIL_SPLIT"); return e ? atoi(e) : 1; }();
+    const int ns = tc_plan_tail_split(p, pairs, 64, split_env && !head);
+    if (ns > 1) {
+      rc = encode_w_half_map(&st->b2, op.in[4], cm * Cout, K, block_n / ns / 2);
+      if (rc != PSLD_OK) { delete st; return rc; }
+    }
+  }
+  st->grid = 2 * (p.num_virtual < pairs ? p.num_virtual : pairs);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -869,10 +902,10 @@ int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
   PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
   if (st->x3)
     PSLD_CHECK_CUDA(launch_pdl(conv_gn_x3_kernel, dim3((unsigned)st->grid), dim3(GX_THREADS), GX_SMEM_BYTES,
-                               s, 2, st->a1, st->a2, st->b, st->p));
+                               s, 2, st->a1, st->a2, st->b, st->b2, st->p));
   else
     PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
-                               s, 2, st->a1, st->a2, st->b, st->e1, st->e2, st->p));
+                               s, 2, st->a1, st->a2, st->b, st->b2, st->e1, st->e2, st->p));
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

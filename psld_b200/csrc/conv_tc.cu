@@ -128,16 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // K = taps x input channels, optionally followed by a 1x1 "extension" over a second input
   // (the residual block's Conv_2 shortcut accumulated into the same tile, layerspp.py:269-274)
   const int total_kb = p.taps * p.kchunks + p.ext_kchunks;
-  // virtual unit v -> (unit, N slice): full units first, then the N-split units of the last round
-  auto decode = [&](int v, int& unit, int& nsub, int& bn) {
-    if (v < p.tail_start) {
-      unit = v; nsub = -1; bn = p.block_n;
-    } else {
-      const int t = v - p.tail_start;
-      const int u = t / p.n_split;
-      unit = p.tail_start + u; nsub = t - u * p.n_split; bn = p.block_n / p.n_split;
-    }
-  };
+  auto decode = [&](int v, int& unit, int& nsub, int& bn) { tc_decode_unit(p, v, unit, nsub, bn); };
 
   if (warp == 0 || warp == 10) {
     // ===================== TMA producers (both CTAs of a pair) =====================
@@ -503,21 +494,7 @@ int prepare_conv_tc(psld_op& op) {
       const char* e = getenv("PSLD_TC_TAIL_SPLIT");
       return e ? atoi(e) : 1;
     }();
-    const int workers = pair ? sms / 2 : sms;
-    const int full = p.num_tiles / workers, tail = p.num_tiles % workers;
-    int best = 1;
-    double best_cost = full + (tail > 0 ? 1.0 : 0.0);
-    if (split_env && tail > 0 && !head) {
-      for (int ns : {2, 4}) {
-        const int sub = block_n / ns;
-        if (block_n % ns || sub < 64 || sub % 64) continue;
-        const double cost = full + (double)((tail * ns + workers - 1) / workers) / ns;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
-      }
-    }
-    p.n_split = best;
-    p.tail_start = best > 1 ? p.num_tiles - tail : p.num_tiles;
-    p.num_virtual = p.tail_start + (p.num_tiles - p.tail_start) * best;
+    const int best = tc_plan_tail_split(p, pair ? sms / 2 : sms, 64, split_env && !head);
     if (best > 1) {
       const int sub = block_n / best;
       rc = encode_w_map(&st->b2, op.in[4], cm * Cout, K, pair ? sub / 2 : sub);

@@ -76,6 +76,39 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + kAddvBytes + 768;
 };
 
+// virtual unit v -> (unit, N slice index or -1, N width): full units first, then the N-split units of
+// the last partial round (ConvTcParams::tail_start / n_split)
+__device__ __forceinline__ void tc_decode_unit(const ConvTcParams& p, int v, int& unit, int& nsub, int& bn) {
+  if (v < p.tail_start) {
+    unit = v; nsub = -1; bn = p.block_n;
+  } else {
+    const int t = v - p.tail_start;
+    const int u = t / p.n_split;
+    unit = p.tail_start + u; nsub = t - u * p.n_split; bn = p.block_n / p.n_split;
+  }
+}
+
+// Host: choose the N-split of the last partial round.  `workers` = clusters (or CTAs) that run
+// concurrently, `min_sub` = smallest / granularity of the N slice.  Fills tail_start / n_split /
+// num_virtual and returns n_split.
+static inline int tc_plan_tail_split(ConvTcParams& p, int workers, int min_sub, bool enable) {
+  const int full = p.num_tiles / workers, tail = p.num_tiles % workers;
+  int best = 1;
+  double best_cost = full + (tail > 0 ? 1.0 : 0.0);
+  if (enable && tail > 0) {
+    for (int ns : {2, 4}) {
+      const int sub = p.block_n / ns;
+      if (p.block_n % ns || sub < min_sub || sub % min_sub) continue;
+      const double cost = full + (double)((tail * ns + workers - 1) / workers) / ns;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+    }
+  }
+  p.n_split = best;
+  p.tail_start = best > 1 ? p.num_tiles - tail : p.num_tiles;
+  p.num_virtual = p.tail_start + (p.num_tiles - p.tail_start) * best;
+  return best;
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
