@@ -409,11 +409,17 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 // A k-block = (tap, 64-channel chunk) feeds three MMA groups (a_hi w_hi, a_hi w_lo, a_lo w_hi) from
 // one weight stage holding W_hi | W_lo.  Four epilogue warps (each handles both column halves; the
 // tile's MMA phase is 3x longer than in the bf16 kernel, so the epilogue has time) keep the split
-// staging tiles at 16 KB.  No 1x1 shortcut extension in this variant.
+// staging tiles at 16 KB.
+// The 1x1 shortcut extension (the block's Conv_2 over the RAW block input, accumulated into the same
+// tile as extra centre-tap k-blocks) follows the 9-tap chunks of a tile: its tiles need no halo and no
+// transform, so they stream through a 3-deep ring of 32 KB (hi | lo) slots carved out of the left /
+// right variant region (idle by then), loaded by their own producer warp with 2-CTA TMA (credited to
+// the leader's barrier, as in conv_tc); the centre slots stay free, so the next tile's first raw tile
+// lands and is normalised while the shortcut k-blocks run.
 //
 // Warps (384 threads, so that the split epilogue keeps its accumulator rows in registers: 170 regs):
-// 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator, 2 = weight TMA, 3 idle,
-// 4..7 = epilogue, 8..11 = transform.
+// 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator, 2 = weight TMA, 3 = shortcut-tile
+// TMA, 4..7 = epilogue, 8..11 = transform.
 constexpr int GX_THREADS = 384;
 constexpr int GX_TRANSFORM_WARPS = 4;
 constexpr int GX_B_STAGES = 2;
@@ -428,6 +434,7 @@ __device__ __forceinline__ float silu_x3(float x) { return __fdividef(x, 1.0f + 
 __global__ void __launch_bounds__(GX_THREADS, 1)
 conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmE1, const __grid_constant__ CUtensorMap tmE2,
                   const ConvGnParams gp) {
   const ConvTcParams& p = gp.c;
   extern __shared__ uint8_t smem_raw[];
@@ -435,6 +442,8 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // variant v in {0: centre, 1: left, 2: right}, plane pl in {0: hi, 1: lo}
   auto var = [&](int v, int pl) { return base + (uint32_t)(2 * v + pl) * GN_VAR_BYTES; };
+  // shortcut ring: 3 slots of (hi 16 KB | lo 16 KB) over the left / right variant region (96 KB)
+  auto ext_slot = [&](int k) { return base + 2u * GN_VAR_BYTES + (uint32_t)k * 32768u; };
   const uint32_t bring = base + GX_ABUF_BYTES;
   const uint32_t stg_base = bring + GX_B_STAGES * GX_B_STAGE;
   const uint32_t bar_base = stg_base + GX_STAGING_BYTES;
@@ -447,6 +456,9 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 40u + 8u * (2 * GX_B_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 40u + 8u * (2 * GX_B_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 40u + 8u * (2 * GX_B_STAGES + 4);
+  auto ext_full = [&](int k) { return tmem_slot + 8u + 8u * k; };
+  auto ext_empty = [&](int k) { return tmem_slot + 32u + 8u * k; };
+  const uint32_t ext_done = tmem_slot + 56u;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -463,6 +475,11 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     mbar_init(lr_ready, 2);
     mbar_init(c_empty, 1);
     mbar_init(lr_empty, 1);
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(ext_full(k), 1);
+      mbar_init(ext_empty(k), 1);
+    }
+    mbar_init(ext_done, 1);
     for (int s = 0; s < GX_B_STAGES; ++s) {
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
@@ -521,9 +538,10 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const CUtensorMap* tmW = nsub < 0 ? &tmB : &tmB2;
       const int bn0 = n_tile * p.block_n + (nsub < 0 ? 0 : nsub * bn) + (int)rank * b_rows;
       const uint32_t tx = (uint32_t)b_rows * 128u * 2u * 2u;       // (hi + lo) x both CTAs
-      for (int cc = 0; cc < total_chunks; ++cc) {
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int kblk = gn_tap(t9) * p.kchunks + cc;
+      for (int cc = 0; cc < total_chunks + p.ext_kchunks; ++cc) {
+        const int ntap = cc < total_chunks ? 9 : 1;
+        for (int t9 = 0; t9 < ntap; ++t9) {
+          const int kblk = ntap == 9 ? gn_tap(t9) * p.kchunks + cc : 8 * p.kchunks + cc;
           mbar_wait(b_empty(stage), ph ^ 1);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(b_full(stage), tx);
@@ -536,11 +554,41 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== shortcut tiles (raw hi, lo; no halo, no transform) =====================
+    if (p.ext_kchunks > 0) {
+      pdl_wait();
+      int eslot = 0;
+      uint32_t eph = 0, lph = 0;
+      for (int v = unit0; v < p.num_virtual; v += unit_step) {
+        int unit, nsub, bn;
+        tc_decode_unit(p, v, unit, nsub, bn);
+        const int m_tile = 2 * (unit / p.n_tiles_n) + (int)rank;
+        const int n0 = m_tile / p.tiles_y;
+        const int y0 = (m_tile % p.tiles_y) * p.BH;
+        // the ring lives in the left / right variant region: wait until the side taps of EVERY 9-tap
+        // chunk of this tile have retired (every lr_empty phase must be observed, in order)
+        for (int cc = 0; cc < total_chunks; ++cc) { mbar_wait(lr_empty, lph); lph ^= 1; }
+        for (int e = 0; e < p.ext_kchunks; ++e) {
+          mbar_wait(ext_empty(eslot), eph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(ext_full(eslot), 4u * TC_A_BYTES);   // (hi + lo) x both CTAs
+            const bool s1 = e < p.ext_kchunks1;
+            const CUtensorMap* tmE = s1 ? &tmE1 : &tmE2;
+            const int c0 = (s1 ? e : e - p.ext_kchunks1) * TC_BLOCK_K;
+            tma_load_4d_pair(ext_slot(eslot), tmE, ext_full(eslot), c0, 0, y0, n0);
+            tma_load_4d_pair(ext_slot(eslot) + 16384u, tmE, ext_full(eslot), c0 + (s1 ? p.loe1 : p.loe2), 0, y0, n0);
+          }
+          __syncwarp();
+          if (++eslot == 3) { eslot = 0; eph ^= 1; }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (rank == 0) {
-      int stage = 0, acc = 0;
-      uint32_t cph = 0, bph = 0, acc_phase = 0;
+      int stage = 0, acc = 0, eslot = 0;
+      uint32_t cph = 0, bph = 0, acc_phase = 0, eph = 0;
       const uint32_t row_step = (uint32_t)p.W * 128u;       // ky * W rows
       for (int v = unit0; v < p.num_virtual; v += unit_step) {
         int unit, nsub, bn;
@@ -589,6 +637,33 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           }
           cph ^= 1;
         }
+        // 1x1 shortcut k-blocks: raw (hi, lo) tiles of the block input from the 3-slot ring
+        for (int e = 0; e < p.ext_kchunks; ++e) {
+          mbar_wait(ext_full(eslot), eph);
+          mbar_wait(b_full(stage), bph);
+          tc_fence_after();
+          const uint64_t a_hi = make_sw128_desc(ext_slot(eslot));
+          const uint64_t a_lo = make_sw128_desc(ext_slot(eslot) + 16384u);
+          const uint64_t b_hi = make_sw128_desc(bring + (uint32_t)stage * GX_B_STAGE);
+          const uint64_t b_lo = make_sw128_desc(bring + (uint32_t)stage * GX_B_STAGE + GN_B_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+              tc_mma_bf16_pair(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+              tc_mma_bf16_pair(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+              tc_mma_bf16_pair(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+            tc_commit_pair(b_empty(stage));
+            tc_commit_pair(ext_empty(eslot));
+            if (e == p.ext_kchunks - 1) tc_commit_pair(ext_done);   // left / right region free again
+          }
+          __syncwarp();
+          if (++stage == GX_B_STAGES) { stage = 0; bph ^= 1; }
+          if (++eslot == 3) { eslot = 0; eph ^= 1; }
+        }
         if (elect_one()) tc_commit_pair(tfull_bar(acc));
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -606,7 +681,7 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     const int Wm = p.W - 1;
     const uint32_t sm0 = smem_u32(smem_raw);
     auto sptr = [&](uint32_t a) { return reinterpret_cast<uint4*>(smem_raw + (a - sm0)); };
-    uint32_t ph = 0;
+    uint32_t ph = 0, tph = 0;
     pdl_wait();
     for (int v = unit0; v < p.num_virtual; v += unit_step) {
         int unit, nsub, bn;
@@ -662,6 +737,7 @@ conv_gn_x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         // ---- phase 2: left / right shifted copies of the normalised centre tiles, once the side taps
         // of the previous chunk have retired (the centre tiles stay put until lr_ready: see the MMA warp)
         mbar_wait(lr_empty, ph ^ 1);
+        if (cc == 0 && p.ext_kchunks > 0) { mbar_wait(ext_done, tph ^ 1); tph ^= 1; }   // previous tile's shortcut ring
 #pragma unroll 3
         for (int u = 0; u < ITEMS; ++u) {
           const int r = r0 + RSTEP * u;
@@ -788,8 +864,6 @@ int prepare_conv_gn_tc(psld_op& op) {
   if (Cout % 64 || Cout > 256 && Cout % 256) return unsupported("Cout");
   if (!((W == 32 && H >= 4) || (W == 16 && H >= 8)) || (H & (H - 1))) return unsupported("map must be 16x16+ / 32x32+ wide tiles");
   if (op.in[2] && op.i[PSLD_CONV_RES_DTYPE] != adt) return unsupported("residual dtype");
-  if (x3 && op.in[8] != nullptr && op.i[PSLD_CONV_EXT_C1] > 0)
-    return unsupported("no 1x1 shortcut extension in the split-bf16 variant");
   if (!op.in[0] || !op.in[4] || !op.in[6] || !op.out[0] || (C2 > 0 && !op.in[1])) {
     set_error("conv_gn_tc: null pointer");
     return PSLD_EINVAL;
@@ -823,10 +897,11 @@ int prepare_conv_gn_tc(psld_op& op) {
     return unsupported("shortcut extension needs E %% 64 == 0");
   }
   if (rc == PSLD_OK)
-    rc = ext ? encode_raw_map(&st->e1, op.in[8], N, H, W, E1, BH + 2)
+    // split-bf16 kernel: the shortcut tile is the tile's own BH rows (no halo), [hi | lo] channels
+    rc = ext ? encode_raw_map(&st->e1, op.in[8], N, H, W, cm * E1, x3 ? BH : BH + 2)
              : encode_raw_map(&st->e1, op.in[0], N, H, W, cm * C1, BH + 2);
   if (rc == PSLD_OK)
-    rc = (ext && E2 > 0) ? encode_raw_map(&st->e2, op.in[9], N, H, W, E2, BH + 2)
+    rc = (ext && E2 > 0) ? encode_raw_map(&st->e2, op.in[9], N, H, W, cm * E2, x3 ? BH : BH + 2)
                          : encode_raw_map(&st->e2, op.in[0], N, H, W, cm * C1, BH + 2);
   const int K = 9 * (C1 + C2) + (ext ? E1 + E2 : 0);
   // split bf16: weight planes [2][Cout, K] seen as one [2*Cout, K] matrix
@@ -902,7 +977,7 @@ int run_conv_gn_tc(const psld_op& op, cudaStream_t s) {
   PSLD_CHECK_ARG(st != nullptr, "conv_gn_tc: op not prepared (call psld_op_prepare)");
   if (st->x3)
     PSLD_CHECK_CUDA(launch_pdl(conv_gn_x3_kernel, dim3((unsigned)st->grid), dim3(GX_THREADS), GX_SMEM_BYTES,
-                               s, 2, st->a1, st->a2, st->b, st->b2, st->p));
+                               s, 2, st->a1, st->a2, st->b, st->b2, st->e1, st->e2, st->p));
   else
     PSLD_CHECK_CUDA(launch_pdl(conv_gn_tc_kernel, dim3((unsigned)st->grid), dim3(GN_THREADS), GN_SMEM_BYTES,
                                s, 2, st->a1, st->a2, st->b, st->b2, st->e1, st->e2, st->p));

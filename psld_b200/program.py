@@ -480,14 +480,15 @@ class Plan:
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
             gn1 = self.fuse_gn_residual or os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
-            if gn1 and hasattr(m, "Conv_2") and self.x3:
-                gn1 = False          # the split-bf16 fused kernel has no 1x1 shortcut extension
             if gn1 and hasattr(m, "Conv_2"):
-                # blocks with a Conv_2 shortcut keep the unfused Conv_1 (apply pass + conv_tc with
-                # the shortcut as K-extension): the fused kernel accepts the extension too, but its
-                # two big operand buffers cannot hide the load latency of one-tap chunks (measured
-                # +1.1 ms of conv for -0.64 ms of GroupNorm per step); PSLD_TC_FUSE_GN_EXT=1 enables it
-                gn1 = (os.environ.get("PSLD_TC_FUSE_GN_EXT", "0") == "1"
+                # blocks with a Conv_2 shortcut.  bf16: they keep the unfused Conv_1 (apply pass +
+                # conv_tc with the shortcut as K-extension): the fused kernel accepts the extension
+                # too, but its two big operand buffers cannot hide the load latency of one-tap chunks
+                # (measured +1.1 ms of conv for -0.64 ms of GroupNorm per step).  bf16x3: the fused
+                # kernel streams the shortcut tiles through a 3-slot ring of their own, so the
+                # extension costs what it costs in conv_tc and the apply pass goes away.
+                # PSLD_TC_FUSE_GN_EXT overrides either default.
+                gn1 = (os.environ.get("PSLD_TC_FUSE_GN_EXT", "1" if self.x3 else "0") == "1"
                        and self._ext_fusable(h, x1, x2, m.out_ch))
             if gn1 and self._gn_fusable(h, None, m.out_ch):
                 aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)

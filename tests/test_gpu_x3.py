@@ -171,6 +171,33 @@ def test_conv_gn_fused_x3(case, silu):
     assert float((keep[-1].double().cpu() - mref).abs().max()) <= 3e-5 * float(mref.abs().max())
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 256, 256, 256, 256), (3, 16, 16, 256, 256, 0, 256),
+                                  (2, 32, 32, 128, 64, 0, 128), (3, 16, 16, 256, 128, 256, 256),
+                                  (39, 16, 16, 256, 256, 256, 256)])
+def test_conv_gn_fused_x3_with_shortcut(case):
+    """GroupNorm_1+SiLU on load -> Conv_1, plus the Conv_2 1x1 shortcut over the RAW block input
+    cat(e1, e2) as extra k-blocks from the kernel's 3-slot shortcut ring (layerspp.py:262-274)."""
+    N, H, W, Cb, E1, E2, Cout = case
+    r = _rng(sum(case) + 13)
+    h = _s(r.standard_normal((N, H, W, Cb)) * 1.5 + 0.2)
+    e1 = _s(r.standard_normal((N, H, W, E1)))
+    e2 = _s(r.standard_normal((N, H, W, E2))) if E2 else None
+    w = _t(r.standard_normal((Cout, Cb, 3, 3)) / np.sqrt(Cb * 9))
+    we = _t(r.standard_normal((Cout, E1 + E2, 1, 1)) / np.sqrt(E1 + E2))
+    bias = _t(0.1 * r.standard_normal(Cout))
+    aff = _t(np.stack([1 + 0.3 * r.standard_normal((N, Cb)), 0.2 * r.standard_normal((N, Cb))], -1))
+    op, out, keep = conv_op(h, None, w, bias, engine=L.ENGINE_TC_GN, scale=0.7071, ext=(e1, e2, we),
+                            mg_stats=True, affine=aff, gn_silu=True)
+    run_op(op, prepare=True)
+    a = F.silu(val(h).double().cpu() * aff.double().cpu()[:, None, None, :, 0] + aff.double().cpu()[:, None, None, :, 1])
+    ref = (conv_ref(a, None, w, bias) + conv_ref(e1, e2, we, None)) * 0.7071
+    err, emx = rel_l2(val(out).permute(0, 3, 1, 2), ref), max_rel(val(out).permute(0, 3, 1, 2), ref)
+    print(f"x3 GN-fused conv + shortcut {case}: rel-L2 {err:.2e} max {emx:.2e}")
+    assert err <= 2e-5 and emx <= 3e-5, (err, emx)
+    mref = mg_ref(ref.permute(0, 2, 3, 1))
+    assert float((keep[-1].double().cpu() - mref).abs().max()) <= 3e-5 * float(mref.abs().max())
+
+
 def test_conv_gn_fused_x3_output_head():
     """Final act(GroupNorm(h)) -> conv3x3 -> 6 channels as fp32 NCHW through the split-bf16 fused kernel."""
     r = _rng(78)
