@@ -42,7 +42,17 @@ WORKLOADS = {
     "celeba64": ("celeba64_config", 84.06e9, 64,
                  "PSLD CelebA-64 NCSN++ (nf=128, ch_mult=[1,2,2,2], 4 res blocks, attn@16, fir, fourier), "
                  "SSCS sampler, 1000 NFE, random-init weights (BASELINE configs[3])"),
+    # classifier-free guidance: two score_fn passes per step (two random-init networks), w = 1.5
+    "cifar10_cfg": ("cifar10_config", 2 * 76.43e9, 128,
+                    "PSLD CIFAR-10 NCSN++ x2 (conditional + unconditional network, classifier-free guidance "
+                    "eps = (1+w) eps_c - w eps_u, w = 1.5: two score_fn passes per step), SSCS sampler, 1000 NFE, "
+                    "random-init weights (BASELINE configs[4]: --batch-total 1024 on 8 GPUs)"),
 }
+CFG_WEIGHT = 1.5
+
+
+def metric_name(workload):
+    return METRIC.replace("CIFAR-10", "CelebA-64") if workload == "celeba64" else METRIC
 
 
 def parse():
@@ -52,8 +62,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = workload default")
-    ap.add_argument("--workload", default="cifar10", choices=["cifar10", "celeba64"],
-                    help="cifar10 = BASELINE configs[1] (headline); celeba64 = configs[3]")
+    ap.add_argument("--workload", default="cifar10", choices=["cifar10", "celeba64", "cifar10_cfg"],
+                    help="cifar10 = BASELINE configs[1] (headline); celeba64 = configs[3]; "
+                         "cifar10_cfg = configs[4] (classifier-free guidance, two passes per step)")
     ap.add_argument("--batch-total", type=int, default=0,
                     help="fixed TOTAL batch sharded over the GPUs (strong scaling; BASELINE configs[2]: 2048, "
                          "configs[3]: 512); overrides --batch")
@@ -139,7 +150,7 @@ class ClockSampler:
 
 
 # ======================================================================== reference arm (CPU)
-def run_cpu_port(cfg, batch, steps, warmup, threads=None):
+def run_cpu_port(cfg, batch, steps, warmup, threads=None, guided=False):
     """Times the oracle port of SSCSSampler.sample on the host cores: `steps` predictor steps
     (one score_fn call + the half-step algebra each) on `batch` samples."""
     import numpy as np
@@ -153,6 +164,8 @@ def run_cpu_port(cfg, batch, steps, warmup, threads=None):
     shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
     sd = fill_state_dict(shapes, 0)
     score = O.OracleScoreFn(cfg, sd)
+    if guided:
+        score = O.GuidedScoreFn(score, O.OracleScoreFn(cfg, fill_state_dict(shapes, 1)), CFG_WEIGHT)
     ts, n = O.time_grid(cfg)
     u0 = prior((batch, 3, H, H), 0.5, 1)
 
@@ -167,7 +180,8 @@ def run_cpu_port(cfg, batch, steps, warmup, threads=None):
     dt = go(steps)
     per_step = dt / steps
     return {"value": batch / (NFE * per_step), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle port of SSCSSampler.sample, {cfg.data.image_size}x{cfg.data.image_size} NCSN++ fp32, batch {batch}, "
+            "sample": f"oracle port of SSCSSampler.sample, {cfg.data.image_size}x{cfg.data.image_size} NCSN++ fp32"
+                      f"{' x2 (classifier-free guidance)' if guided else ''}, batch {batch}, "
                       f"{steps} of {NFE} NFE timed after {warmup} warm-up, extrapolated linearly",
             "ms_per_step": per_step * 1e3, "sample_nfe_per_sec": batch / per_step}
 
@@ -181,11 +195,12 @@ def main_reference(args):
     cfg = getattr(psld_b200, cfg_name)()
     batch = args.cpu_batch
     # bound the run: (steps+warmup) CPU steps of ~0.17 s/sample each must end within minutes
-    per_sample_est = 0.2
+    guided = args.workload == "cifar10_cfg"
+    per_sample_est = 0.4 if guided else 0.2
     while batch > 1 and (args.steps + args.warmup) * batch * per_sample_est > 240:
         batch //= 2
-    r = run_cpu_port(cfg, batch, args.steps, args.warmup)
-    line = {"metric": METRIC if args.workload == "cifar10" else METRIC.replace("CIFAR-10", "CelebA-64"),
+    r = run_cpu_port(cfg, batch, args.steps, args.warmup, guided=guided)
+    line = {"metric": metric_name(args.workload),
             "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -428,6 +443,10 @@ def main_b200(args):
     cfg.evaluation.sampler["state_dtype"] = args.state
     torch.manual_seed(1234)
     net = NCSNpp(cfg).eval().to(dev)   # random-init weights
+    guided = args.workload == "cifar10_cfg"
+    if guided:                         # two networks, two passes per step (BASELINE configs[4])
+        from psld_b200 import ClassifierFreeGuidance
+        net = ClassifierFreeGuidance(cond=net, uncond=NCSNpp(cfg).eval().to(dev), weight=CFG_WEIGHT)
     sde = PSLD(cfg)
     B = args.batch
     H = cfg.data.image_size
@@ -465,9 +484,9 @@ def main_b200(args):
 
     cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_port(make_cfg(), args.cpu_batch, args.cpu_steps, 1)
+        r = run_cpu_port(make_cfg(), args.cpu_batch, args.cpu_steps, 1, guided=guided)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    if rank == 0 and world == 1 and not args.no_gpu_eager:
+    if rank == 0 and world == 1 and not args.no_gpu_eager and not guided:
         try:
             eager = gpu_eager_baseline(make_cfg(), min(B, 64), dev)
         except Exception as e:      # context only: never fail the bench line on it
@@ -475,7 +494,7 @@ def main_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC if args.workload == "cifar10" else METRIC.replace("CIFAR-10", "CelebA-64"),
+            "metric": metric_name(args.workload),
             "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None,

@@ -229,6 +229,9 @@ PSLD_API int psld_quantize_images(const void* state, int state_dtype, uint8_t* o
 #define PSLD_OP_ATTN 6   /* softmax(q k^T / sqrt(C)) v                                  */
 #define PSLD_OP_ZERO 7   /* out[0] = buffer, i[0] | i[1] << 31 = bytes: cudaMemsetAsync(0).  Clears
                             the GroupNorm statistics accumulators at the top of a program   */
+#define PSLD_OP_AXPBY 8  /* out[0] = f[0] * in[0] + f[1] * in[1] over i[0] | i[1] << 31 floats (in[1] may be
+                            NULL: out = f[0] * in[0]).  Classifier-free guidance: a guided program is
+                            [cond program | copy net_in | uncond program | eps = (1+w) eps_c - w eps_u]  */
 
 #define PSLD_ENGINE_SIMT 0 /* fp32 FFMA implicit GEMM (any shape)                       */
 #define PSLD_ENGINE_TC 1   /* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, Cin%64==0;
@@ -329,6 +332,10 @@ enum { PSLD_CONV_N = 0, PSLD_CONV_H, PSLD_CONV_W, PSLD_CONV_C1, PSLD_CONV_C2, PS
  *   statistics accumulator of out[0] (as for PSLD_OP_CONV)                                 */
 enum { PSLD_ATTN_N = 0, PSLD_ATTN_HW, PSLD_ATTN_C, PSLD_ATTN_DTYPE, PSLD_ATTN_PROJ };
 
+/* Standalone PSLD_OP_AXPBY: out = a * x + b * y over n floats (y may be NULL). */
+PSLD_API int psld_axpby(float* out, float a, const float* x, float b, const float* y, int64_t n,
+                        psld_stream_t stream);
+
 /* Validate an op and build its per-op host state (TMA descriptors for PSLD_ENGINE_TC).
  * Returns PSLD_EUNSUPPORTED when the shape is not eligible for op->engine. */
 PSLD_API int psld_op_prepare(psld_op* op);
@@ -360,7 +367,9 @@ typedef struct {
                            1 = SCORE+B+C in one pass (C = half A of step i+1, own draw);
                            2 = same, with B and C pre-merged by the host into half_b (one
                                Gaussian draw, exact in law; only without pre-drawn noise)    */
-  int32_t temb_op;      /* index of the PSLD_OP_TEMB op in the program                  */
+  int32_t temb_op;      /* index of the (first) PSLD_OP_TEMB op in the program; EVERY PSLD_OP_TEMB op of
+                           the program receives the call's time (a classifier-free-guidance program
+                           holds two networks)                                           */
   int64_t B, chw;
   uint64_t seed;
   void* state;          /* [B,2C,H,W] state_dtype, in: prior, out: samples              */

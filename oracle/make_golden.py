@@ -151,6 +151,8 @@ def golden_sampler(R, cfg, fname, B, seed_w=0, seed_p=1, seed_n=2, keep=2, score
     name = cfg.evaluation.sampler.name
     if score == "net":
         net, _ = ref_net(R, cfg, seed_w)
+    elif callable(score):
+        net = score
     else:
         net = fake_score
     ts, n = reference_time_grid(cfg)
@@ -244,6 +246,8 @@ def main():
         return golden_cc(R)
     if "--only-ode" in sys.argv:
         return golden_ode(R)
+    if "--only-guidance" in sys.argv:
+        return golden_guidance(R)
     if "--only-inpaint" in sys.argv:
         return golden_inpaint_all(R)
     if "--only-vp" in sys.argv:
@@ -280,6 +284,7 @@ def main():
     golden_state_dict_contract(R)
     golden_cc(R)
     golden_ode(R)
+    golden_guidance(R)
 
 
 def vp_config(**ev):
@@ -368,6 +373,43 @@ def golden_inpaint_all(R):
         cfg.training.mode = mode
         cfg.data.image_size = 8
         golden_inpaint(R, cfg, f"sampler_ip_em_fake_{mode}.npz", B=3)
+
+
+
+
+# ---------------------------------------------------------------- classifier-free guidance (configs[4])
+CFG_WEIGHT = 1.5
+
+
+def guided(net_c, net_u, w):
+    """eps = (1 + w) eps_c - w eps_u in float32, this order (the reference has no CFG sampler: the
+    definition is this composition of two UNMODIFIED reference networks at its score_fn call site)."""
+    a, b = torch.tensor(1.0 + w, dtype=torch.float32), torch.tensor(-w, dtype=torch.float32)
+
+    def fn(u, t):
+        with torch.no_grad():
+            return a * net_c(u, t) + b * net_u(u, t)
+    return fn
+
+
+def golden_guidance(R):
+    # forward: two reference NCSN++ (weight seeds 0 / 1) of the tcgen05-eligible mid config
+    cfg = mid_config()
+    fc, fu = ref_net(R, cfg, 0)[0], ref_net(R, cfg, 1)[0]
+    r = np.random.default_rng([11, 7])
+    x = torch.from_numpy((r.standard_normal((2, 6, 32, 32)) * 1.5).astype(np.float32))
+    t = torch.from_numpy(np.asarray([0.731, 0.0123], dtype=np.float32))
+    y = guided(fc, fu, CFG_WEIGHT)(x, t)
+    with torch.no_grad():
+        yc = fc(x, t)
+    _save("forward_cfg_mid.npz", x=x.numpy(), t=t.numpy(), y=y.numpy(), y_cond=yc.numpy(),
+          seeds=np.asarray([0, 1]), weight=np.asarray(CFG_WEIGHT))
+    # trajectory: the reference's own SSCS / EM samplers driven by the guided score_fn
+    for name in ("sscs_sde", "em_sde"):
+        cfg = tiny_config(sampler=name, n_discrete_steps=40)
+        fc, fu = ref_net(R, cfg, 0)[0], ref_net(R, cfg, 1)[0]
+        golden_sampler(R, cfg, f"sampler_cfg_tiny_{name.split('_')[0]}40.npz", B=4,
+                       score=guided(fc, fu, CFG_WEIGHT))
 
 
 if __name__ == "__main__":

@@ -614,6 +614,22 @@ class OracleScoreFn:
             return ncsnpp_forward(self.config, self.sd, u, t)
 
 
+class GuidedScoreFn:
+    """Classifier-free guidance over two score functions: eps = (1 + w) eps_c - w eps_u, evaluated in
+    float32 in exactly this order (two products, one sum).  BASELINE configs[4]; the reference ships
+    no such sampler (its NCSN++ takes no label, ncsnpp.py:288), so this composition of two reference
+    forwards at the reference's score_fn call site (sde.py:320, psld.py:354) is the definition the
+    CUDA path is held to - parity is pinned on the two forwards, not on a reference CFG run."""
+
+    def __init__(self, cond, uncond, weight):
+        self.cond, self.uncond, self.weight = cond, uncond, float(weight)
+
+    def __call__(self, u, t):
+        a = torch.tensor(1.0 + self.weight, dtype=torch.float32, device=u.device)
+        b = torch.tensor(-self.weight, dtype=torch.float32, device=u.device)
+        return a * self.cond(u, t) + b * self.uncond(u, t)
+
+
 # --------------------------------------------------------------------------------------
 # 5. Caller-side image quantisation (callbacks.py:103-107, util.py:147-158)
 # --------------------------------------------------------------------------------------

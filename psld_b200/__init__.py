@@ -15,6 +15,7 @@ from .registry import get_module, install, register_module
 from .schedule import PSLDSchedule, StepTables, time_grid
 from .sde import PSLD, VPSDE
 from .ncsnpp import NCSNpp
+from .guidance import ClassifierFreeGuidance
 from .samplers import (ClassCondEulerMaruyamaSampler, EulerMaruyamaSampler, InpaintEulerMaruyamaSampler, Sampler,
                        SSCSSampler)
 from .ode import BBODESampler
@@ -25,7 +26,7 @@ register_module(category="score_fn", name="ncsnpp_b200")(NCSNpp)
 __all__ = [
     "Cfg", "make_config", "tiny_config", "mid_config", "cifar10_config", "celeba64_config",
     "register_module", "get_module", "install", "PSLDSchedule", "StepTables", "time_grid",
-    "PSLD", "VPSDE", "NCSNpp", "SSCSSampler", "EulerMaruyamaSampler", "InpaintEulerMaruyamaSampler",
+    "PSLD", "VPSDE", "NCSNpp", "ClassifierFreeGuidance", "SSCSSampler", "EulerMaruyamaSampler", "InpaintEulerMaruyamaSampler",
     "ClassCondEulerMaruyamaSampler", "BBODESampler", "Sampler",
     "load_checkpoint", "samples_to_uint8", "select_score_fn_state",
 ]

@@ -19,7 +19,7 @@ OK, EINVAL, ECUDA, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4
 F32, BF16, F64, BF16S = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 STAGE_HALF_A, STAGE_SCORE, STAGE_HALF_B, STAGE_HALF_C = 1, 2, 4, 8
-OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN, OP_ZERO = 1, 2, 3, 4, 5, 6, 7
+OP_LAYOUT, OP_TEMB, OP_GN, OP_FIR, OP_CONV, OP_ATTN, OP_ZERO, OP_AXPBY = 1, 2, 3, 4, 5, 6, 7, 8
 ENGINE_SIMT, ENGINE_TC, ENGINE_TC_GN = 0, 1, 2
 OP_NI, OP_NF, OP_NP = 28, 24, 10
 
@@ -114,6 +114,8 @@ EXPORTS = {
                                     C.c_void_p]),
     "psld_quantize_images": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                        C.c_void_p]),
+    "psld_axpby": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64,
+                             C.c_void_p]),
     "psld_op_prepare": (C.c_int, [C.POINTER(Op)]),
     "psld_op_release": (C.c_int, [C.POINTER(Op)]),
     "psld_op_run": (C.c_int, [C.POINTER(Op), C.c_void_p]),

@@ -40,6 +40,7 @@ static int op_launch_count(const psld_op& op) {
     case PSLD_OP_FIR: return 1;
     case PSLD_OP_CONV: return 1;
     case PSLD_OP_ATTN: return 1;
+    case PSLD_OP_AXPBY: return 1;
     default: return 0;
   }
 }
@@ -55,6 +56,7 @@ static int dispatch(const psld_op& op, cudaStream_t s) {
       return op.engine == PSLD_ENGINE_TC ? run_conv_tc(op, s) : run_conv_simt(op, s);
     case PSLD_OP_ATTN:
       return op.engine == PSLD_ENGINE_TC ? run_attn_tc(op, s) : run_attn_simt(op, s);
+    case PSLD_OP_AXPBY: return run_axpby(op, s);
     case PSLD_OP_ZERO: {         // statistics accumulators (a memset node, not a kernel of ours)
       const size_t bytes = (size_t)op.i[0] | ((size_t)op.i[1] << 31);
       if (bytes == 0) return PSLD_OK;
@@ -85,6 +87,11 @@ extern "C" int psld_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = prop.major;
   if (cc_minor) *cc_minor = prop.minor;
   return PSLD_OK;
+}
+
+extern "C" int psld_axpby(float* out, float a, const float* x, float b, const float* y, int64_t n,
+                          psld_stream_t stream) {
+  return launch_axpby(out, a, x, b, y, n, (cudaStream_t)stream);
 }
 
 extern "C" int psld_op_prepare(psld_op* op) {
@@ -134,7 +141,9 @@ static int run_net(const psld_op* ops, int n_ops, int temb_op, const float* time
                    cudaStream_t s, int* step_counter = nullptr) {
   for (int i = 0; i < n_ops; ++i) {
     int rc;
-    if (i == temb_op) {
+    // every time-embedding op of the program gets this call's time: a classifier-free-guidance
+    // program holds two networks (temb_op indexes the first)
+    if (i == temb_op || ops[i].kind == PSLD_OP_TEMB) {
       psld_op t = ops[i];
       t.in[0] = time_ptr;      // this call's (log) time, identical for the whole batch
       t.out[2] = step_counter; // graph replay: row index read on the device

@@ -195,6 +195,9 @@ static inline size_t dtype_size(int dt) { return dt == PSLD_BF16 ? 2 : (dt == PS
 
 // per-op entry points (implemented in the .cu files, dispatched from capi.cu)
 int run_layout(const psld_op& op, cudaStream_t s);
+int run_axpby(const psld_op& op, cudaStream_t s);
+int launch_axpby(float* out, float a, const float* x, float b, const float* y, int64_t n,
+                 cudaStream_t s);
 int run_temb(const psld_op& op, cudaStream_t s);
 int run_gn(const psld_op& op, cudaStream_t s);
 int run_fir(const psld_op& op, cudaStream_t s);

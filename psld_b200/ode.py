@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .ncsnpp import NCSNpp
+from .guidance import is_native
 from .registry import register_module
 from .samplers import Sampler
 from .schedule import PSLDSchedule, _fill_score, _score_rows
@@ -120,7 +120,7 @@ class BBODESampler(Sampler):
 
     def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
         lib = L.lib()
-        native = isinstance(self.score_fn, NCSNpp)
+        native = is_native(self.score_fn)
         if native:
             dev = next(self.score_fn.parameters()).device
         else:

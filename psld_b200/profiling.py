@@ -8,7 +8,7 @@ import torch
 from . import _lib as L
 
 KIND_NAMES = {L.OP_LAYOUT: "layout", L.OP_TEMB: "temb", L.OP_GN: "groupnorm", L.OP_FIR: "fir",
-              L.OP_CONV: "conv", L.OP_ATTN: "attention", L.OP_ZERO: "zero"}
+              L.OP_CONV: "conv", L.OP_ATTN: "attention", L.OP_ZERO: "zero", L.OP_AXPBY: "axpby"}
 
 
 def op_name(op):
@@ -27,7 +27,7 @@ def op_flops(op, cin_valid=None) -> float:
     if op.kind == L.OP_CONV:
         M = i[L.CONV_N] * i[L.CONV_OH] * i[L.CONV_OW]
         K = i[L.CONV_KS] ** 2 * (cin_valid if cin_valid else i[L.CONV_C1] + i[L.CONV_C2])
-        if op.engine == L.ENGINE_TC:
+        if op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN):
             K += i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]      # fused 1x1 shortcut
         cout = int(op.f[1]) if (op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN) and op.f[1] >= 1) else i[L.CONV_COUT]
         return 2.0 * M * K * cout
@@ -80,7 +80,7 @@ def profile_plan(plan, iters: int = 3, warmup: int = 1):
             key = f"{op_name(op)} {i[L.CONV_OH]}x{i[L.CONV_OW]} {i[L.CONV_C1] + i[L.CONV_C2]}->" \
                   f"{i[L.CONV_COUT]} k{i[L.CONV_KS]}s{i[L.CONV_STRIDE]}" \
                   f"{'+res' if op.inp[2] else ''}{'+temb' if op.inp[3] else ''}" \
-                  f"{'+sc' + str(i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]) if (op.engine == L.ENGINE_TC and i[L.CONV_EXT_C1]) else ''}"
+                  f"{'+sc' + str(i[L.CONV_EXT_C1] + i[L.CONV_EXT_C2]) if (op.engine in (L.ENGINE_TC, L.ENGINE_TC_GN) and i[L.CONV_EXT_C1]) else ''}"
             c = classes.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
             c["ms"] += acc[k] / iters
             c["n"] += 1

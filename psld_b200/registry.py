@@ -41,12 +41,12 @@ def install(reference_util=None, override: bool = False):
 
     ``reference_util``: the reference's imported ``util`` module (default: ``import util``).
     New names (``sscs_sde_b200``, ``em_sde_b200``, ``ip_em_sde_b200``, ``cc_em_sde_b200``, ``bb_ode_b200``,
-    ``ncsnpp_b200``, ``psld_b200``) are always
+    ``ncsnpp_b200``, ``cfg_ncsnpp_b200``, ``psld_b200``) are always
     added; with ``override=True`` the reference's own names (``sscs_sde``, ``em_sde``,
     ``ncsnpp``) are re-pointed too, by writing ``util._MODULES[category][name]`` directly
     (``register_module`` would raise on the duplicate, util.py:46-50).
     """
-    from . import ncsnpp, ode, samplers, sde  # noqa: F401  (registers into _MODULES)
+    from . import guidance, ncsnpp, ode, samplers, sde  # noqa: F401  (registers into _MODULES)
     if reference_util is None:
         import util as reference_util  # the reference's main/util.py must be on sys.path
     reg = reference_util._MODULES

@@ -8,7 +8,8 @@ Drop-in for the reference's ``SSCSSampler`` / ``EulerMaruyamaSampler``
   attributes ``.nfe``, property ``.n_steps``; identity corrector by default.
 
 Two execution paths, both on the GPU, neither with a CPU/eager fallback for the update:
-  * ``score_fn`` is a :class:`psld_b200.ncsnpp.NCSNpp`  ->  the whole loop runs natively in
+  * ``score_fn`` is a :class:`psld_b200.ncsnpp.NCSNpp` (or two of them under
+    :class:`psld_b200.guidance.ClassifierFreeGuidance`)  ->  the whole loop runs natively in
     ``psld_sampler_run`` (one C call; per step = network program + ONE fused update kernel);
   * any other callable ``score_fn(u f32, t f32[B]) -> eps``  ->  a thin Python loop that calls
     ``score_fn`` and the same fused kernels (``psld_sscs_update`` / ``psld_em_update``).
@@ -29,7 +30,7 @@ import torch
 
 from . import _lib as L
 from .distributed import call_seed, current_rank
-from .ncsnpp import NCSNpp
+from .guidance import is_native
 from .registry import register_module
 from .schedule import InpaintTables, PSLDSchedule, StepTables, VPSchedule, VPStepTables
 
@@ -189,7 +190,7 @@ class _FusedSampler(Sampler):
     def _sample_vp(self, batch, ts, n, denoise, eps):
         """Euler-Maruyama on the VP-SDE (state [B,C,H,W]): score_fn + one fused update per step."""
         lib = L.lib()
-        if isinstance(self.score_fn, NCSNpp):
+        if is_native(self.score_fn):
             dev = next(self.score_fn.parameters()).device
         else:
             dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -238,7 +239,7 @@ class _FusedSampler(Sampler):
         self._next_seed()
         if self.vp is not None:
             return self._sample_vp(batch, ts, n, denoise, eps)
-        native = isinstance(self.score_fn, NCSNpp)
+        native = is_native(self.score_fn)
         if native:
             dev = next(self.score_fn.parameters()).device
         else:
@@ -433,7 +434,7 @@ class ClassCondEulerMaruyamaSampler(_FusedSampler):
         n = int(n_discrete_steps)
         self.nfe = n
         self._next_seed()
-        if isinstance(self.score_fn, NCSNpp):
+        if is_native(self.score_fn):
             dev = next(self.score_fn.parameters()).device
         else:
             dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -512,7 +513,7 @@ class InpaintEulerMaruyamaSampler(_FusedSampler):
         if self.record is not None or self.corrector_fn is not None:
             raise NotImplementedError("ip_em_sde_b200 does not support `record` / a custom corrector_fn "
                                       "(the reference's inpainting sampler has neither)")
-        if isinstance(self.score_fn, NCSNpp):
+        if is_native(self.score_fn):
             dev = next(self.score_fn.parameters()).device
         else:
             dev = x_0.device if x_0.is_cuda else torch.device("cuda", torch.cuda.current_device())

@@ -20,10 +20,11 @@ run net_bf16 900 $PT tests/test_gpu_network.py -k "bf16 or checkpoint or in_plac
 run sampler 1200 $PT tests/test_gpu_sampler.py
 run x3_kernels 900 $PT tests/test_gpu_x3.py -k "not (forward or sampler or trajectory or full_batch)"
 run x3_net 1500 $PT tests/test_gpu_x3.py -k "forward or sampler or trajectory or full_batch"
+run guidance 900 $PT tests/test_gpu_guidance.py
 run smoke 600 python __graft_entry__.py smoke
 if [ "${SKIP_BENCH:-0}" != "1" ]; then
   run bench 1500 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --e2e-nfe ${E2E_NFE:-20} --cpu-steps 1 --cpu-batch 4 ${BENCH_ARGS:-}
 fi
-grep -h -E "passed|failed|error" gpurun_out/k_*.log gpurun_out/net_*.log gpurun_out/sampler.log gpurun_out/x3_*.log gpurun_out/smoke.log | tail -20
+grep -h -E "passed|failed|error" gpurun_out/k_*.log gpurun_out/net_*.log gpurun_out/sampler.log gpurun_out/x3_*.log gpurun_out/guidance.log gpurun_out/smoke.log | tail -20
 grep -h -E "^FAILED|^ERROR" gpurun_out/*.log | head -20
 tail -c 6000 gpurun_out/bench.log

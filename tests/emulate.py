@@ -89,6 +89,12 @@ def run_plan(plan, x, t):
             if i[L.GN_SILU]:
                 y = F.silu(y)
             g(op.out[0]).copy_(y.permute(0, 2, 3, 1))
+        elif op.kind == L.OP_AXPBY:
+            n = i[0] | (i[1] << 31)
+            xa, ya, dst = g(op.inp[0]), g(op.inp[1]), g(op.out[0])
+            assert xa.numel() == n == dst.numel() and (ya is None or ya.numel() == n)
+            a, b = torch.tensor(f[0], dtype=torch.float32), torch.tensor(f[1], dtype=torch.float32)
+            dst.copy_(a * xa if ya is None else a * xa + b * ya)
         elif op.kind == L.OP_FIR:
             KH = i[L.FIR_KH]
             k = np.asarray([f[j] for j in range(KH * KH)], np.float32).reshape(KH, KH)

@@ -1,0 +1,149 @@
+"""Classifier-free guidance (BASELINE configs[4]: two score_fn passes per step) on the GPU.
+
+The reference has no CFG sampler and its NCSN++ takes no label (ncsnpp.py:288), so the guided
+score_fn is DEFINED as eps = (1 + w) eps_c - w eps_u over two NCSN++ networks; what is pinned:
+  * goldens made from two UNMODIFIED reference networks and the reference's own SSCS / EM samplers
+    driven by that composition (oracle/make_golden.py::golden_guidance);
+  * w = 0 reproduces the conditional network's sampler bit for bit.
+Tolerances (rel-L2 vs the golden; the combination amplifies each network's error by up to 1 + 2w = 4):
+  forward, mid net .... fp32 1e-5 (measured 2.1e-6), bf16x3 5e-5 (1.8e-5), bf16 2e-2 (9.8e-3)
+  40-NFE trajectories . fp32 5e-6 (1.1e-6), bf16x3 5e-5 (1.4e-5; the tier's stated bound is 1e-4), bf16 1.8e-2 (8.8e-3)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from _net import make_net, sampler_inputs
+from _ops import max_rel, rel_l2
+from psld_b200 import (BBODESampler, ClassifierFreeGuidance, EulerMaruyamaSampler, PSLD, SSCSSampler, mid_config,
+                       time_grid, tiny_config)
+from psld_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+W = 1.5
+
+
+def _guided(cfg, precision, w=W):
+    a, _ = make_net(cfg, precision, seed=0)
+    b, _ = make_net(cfg, precision, seed=1)
+    return ClassifierFreeGuidance(cond=a, uncond=b, weight=w), a, b
+
+
+@pytest.mark.parametrize("n", [4, 1027, 6 * 32 * 32 * 5])
+def test_axpby_kernel(n):
+    r = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n + 4, generator=r, device="cuda")[:n] if n % 4 == 0 else torch.randn(n, generator=r, device="cuda")
+    y = torch.randn(n, generator=r, device="cuda")
+    out = torch.empty(n, device="cuda")
+    lib = L.lib()
+    s = L.stream_ptr()
+    L.check(lib.psld_axpby(L.ptr(out), 2.5, L.ptr(x), -1.5, L.ptr(y), n, s), "axpby")
+    a, b = torch.tensor(2.5, device="cuda"), torch.tensor(-1.5, device="cuda")
+    assert torch.equal(out, a * x + b * y)          # two fp32 products, one sum: exact
+    L.check(lib.psld_axpby(L.ptr(out), 1.0, L.ptr(x), -0.0, L.ptr(y), n, s), "axpby")
+    assert torch.equal(out, x)                      # w = 0
+    L.check(lib.psld_axpby(L.ptr(out), 1.0, L.ptr(x), 0.0, None, n, s), "axpby")
+    assert torch.equal(out, x)                      # copy form
+    assert lib.psld_axpby(L.ptr(out), 1.0, None, 0.0, None, n, s) == L.EINVAL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16x3", 5e-5), ("bf16", 2e-2)])
+def test_guided_forward_vs_reference_golden(golden_dir, precision, tol):
+    g = np.load(f"{golden_dir}/forward_cfg_mid.npz")
+    net, a, _ = _guided(mid_config(), precision, float(g["weight"]))
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    y = net(x, t)
+    e = rel_l2(y, torch.from_numpy(g["y"]))
+    print(f"guided forward ({precision}): rel-L2 {e:.3e}")
+    assert e <= tol
+    # w = 0: the guided program returns the conditional network's output bit for bit
+    net.weight = 0.0
+    assert torch.equal(net(x, t), a(x, t))
+    # the guided plan follows the weight and in-place parameter updates of either network
+    net.weight = float(g["weight"])
+    assert rel_l2(net(x, t), torch.from_numpy(g["y"])) <= tol
+    with torch.no_grad():
+        net.uncond.all_modules[-1].weight.mul_(2.0)
+    assert rel_l2(net(x, t), y) > 1e-3
+
+
+@pytest.mark.parametrize("kind", ["sscs_sde", "em_sde"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-6), ("bf16x3", 5e-5), ("bf16", 1.8e-2)])
+def test_guided_sampler_vs_reference_golden(golden_dir, kind, precision, tol):
+    """Whole native loop over the guided program vs the reference's sampler driven by the same
+    composition of two reference networks (pre-drawn noise)."""
+    g = np.load(f"{golden_dir}/sampler_cfg_tiny_{kind.split('_')[0]}40.npz")
+    cfg = tiny_config(sampler=kind, n_discrete_steps=40)
+    net, _, _ = _guided(cfg, precision)
+    n = int(g["n"])
+    u0, nb = sampler_inputs(cfg, int(g["B"]), n, kind)
+    S = (SSCSSampler if kind == "sscs_sde" else EulerMaruyamaSampler)(cfg, PSLD(cfg), net)
+    S.use_graph, S.fuse_halves = False, False
+    S.noise = torch.stack(nb).cuda()
+    ts, n2 = time_grid(cfg)
+    out = S.sample(u0.cuda(), ts.cuda(), n2, denoise=True, eps=1e-3)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["final"])
+    e = rel_l2(out, ref)
+    print(f"guided {kind} ({precision}): final rel-L2 {e:.3e} max-abs/max|ref| {max_rel(out, ref):.3e}")
+    assert n2 == n and S.nfe == n and e <= tol
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_guidance_weight_zero_is_the_unguided_sampler(precision):
+    """with w = 0 the two-pass sampler reproduces the one-network sampler bit for bit
+    (Philox noise, fused halves, CUDA-graph replay: the production configuration)."""
+    cfg = mid_config(sampler="sscs_sde", n_discrete_steps=8)
+    net, a, _ = _guided(cfg, precision, 0.0)
+    sde = PSLD(cfg)
+    ts, n = time_grid(cfg)
+    u0 = sde.prior_sampling_device((3, 3, 32, 32), seed=5, device="cuda")
+    outs = []
+    for fn in (net, a):
+        S = SSCSSampler(cfg, sde, fn)
+        outs.append(S.sample(u0.clone(), ts.cuda(), n, denoise=True, eps=1e-3))
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+    # and a non-zero weight changes the samples
+    net.weight = 1.5
+    out_w = SSCSSampler(cfg, sde, net).sample(u0.clone(), ts.cuda(), n, denoise=True, eps=1e-3)
+    assert torch.isfinite(out_w).all() and not torch.equal(out_w, outs[0])
+
+
+def test_guided_graph_replay_equals_host_loop():
+    cfg = mid_config(sampler="sscs_sde", n_discrete_steps=6)
+    net, _, _ = _guided(cfg, "bf16x3")
+    sde = PSLD(cfg)
+    ts, n = time_grid(cfg)
+    u0 = sde.prior_sampling_device((2, 3, 32, 32), seed=9, device="cuda")
+    outs = []
+    for graph in (True, False):
+        S = SSCSSampler(cfg, sde, net)
+        S.use_graph = graph
+        outs.append(S.sample(u0.clone(), ts.cuda(), n, denoise=True, eps=1e-3))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_guided_score_fn_under_bb_ode():
+    """The guided score_fn is a score_fn: the probability-flow ODE sampler replays its program too.
+    w = 0 reproduces the one-network ODE solve exactly (same NFE, same end state); w != 0 differs."""
+    from _net import ode_config
+    cfg = ode_config(1e-3)
+    cfg.data.image_size = 32
+    net, a, _ = _guided(cfg, "fp32", 0.0)
+    sde = PSLD(cfg)
+    u0 = sde.prior_sampling_device((2, 3, 32, 32), seed=3, device="cuda")
+    res = []
+    for fn in (net, a):
+        S = BBODESampler(cfg, sde, fn)
+        res.append((S.sample(u0.clone(), None, 0, denoise=False, eps=1e-3), S.nfe))
+    torch.cuda.synchronize()
+    assert res[0][1] == res[1][1] > 6 and torch.equal(res[0][0], res[1][0])
+    net.weight = W
+    S = BBODESampler(cfg, sde, net)
+    out = S.sample(u0.clone(), None, 0, denoise=False, eps=1e-3)
+    assert torch.isfinite(out).all() and not torch.equal(out, res[0][0])

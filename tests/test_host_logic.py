@@ -238,3 +238,43 @@ def test_call_seed_per_call_and_rank(monkeypatch):
     assert current_rank() == 11
     monkeypatch.setenv("RANK", "5")
     assert current_rank() == 5
+
+
+def test_guided_program_vs_golden(golden_dir):
+    """Classifier-free guidance (BASELINE configs[4]): the ONE program the guided score_fn compiles to
+    ([cond | copy | uncond | axpby]) interpreted on the host reproduces the composition of two reference
+    forwards; w = 0 returns the conditional network's output exactly; plans follow weight updates."""
+    from psld_b200 import ClassifierFreeGuidance
+    g = np.load(f"{golden_dir}/forward_cfg_mid.npz")
+    cfg = mid_config()
+    nets = []
+    for seed in g["seeds"]:
+        net = NCSNpp(cfg).eval()
+        net.precision = "fp32"
+        net.load_state_dict(fill_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, int(seed)))
+        nets.append(net)
+    x, t, y, yc = (torch.from_numpy(g[k]) for k in ("x", "t", "y", "y_cond"))
+    from psld_b200.guidance import GuidedPlan
+    a, b = (build_plan(n, 2, 2, False, dry=True) for n in nets)
+    gp = GuidedPlan(a, b, float(g["weight"]))
+    assert gp.n_ops == a.n_ops + b.n_ops + 2 and gp.launches == a.launches + b.launches + 2
+    assert sum(op.kind == L.OP_TEMB for op in gp.ops) == 2 and gp.ops[gp.temb_op].kind == L.OP_TEMB
+    assert all(op.inp[0] == a.time_buf.data_ptr() for op in gp.ops if op.kind == L.OP_TEMB)
+    out = run_plan(gp, x, t)
+    assert float((out - y).norm() / y.norm()) <= 1e-5
+    out0 = run_plan(GuidedPlan(a, b, 0.0), x, t)
+    assert torch.equal(out0, run_plan(a, x, t)) and float((out0 - yc).norm() / yc.norm()) <= 1e-5
+    # module surface: registry name, cls(config) construction, state-dict prefixes, shape checks
+    cls = get_module("score_fn", "cfg_ncsnpp_b200")
+    assert cls is ClassifierFreeGuidance
+    c2 = tiny_config()
+    c2.model.score_fn["guidance_weight"] = 2.0
+    m = cls(c2)
+    assert m.weight == 2.0 and m.in_ch == 6
+    keys = list(m.state_dict().keys())
+    assert keys[0].startswith("cond.all_modules.") and keys[-1].startswith("uncond.all_modules.")
+    assert len(keys) == 2 * len(NCSNpp(c2).state_dict())
+    with pytest.raises(ValueError):
+        ClassifierFreeGuidance(cond=nets[0], uncond=nets[0], weight=1.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 6, 32, 32), torch.ones(1))

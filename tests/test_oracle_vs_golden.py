@@ -231,3 +231,36 @@ def test_bb_ode_sampler(golden_dir, tag, tol, den):
     assert nfe == int(g["nfe"])
     # every evaluation sees the float32 rounding of (t, y): two runs agree to float32 resolution
     assert np.abs(out.double().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------- classifier-free guidance (configs[4])
+def _guided_oracle(cfg, w):
+    from psld_b200 import NCSNpp
+    shapes = {k: tuple(v.shape) for k, v in NCSNpp(cfg).state_dict().items()}
+    return O.GuidedScoreFn(O.OracleScoreFn(cfg, fill_state_dict(shapes, 0)),
+                           O.OracleScoreFn(cfg, fill_state_dict(shapes, 1)), w)
+
+
+def test_guided_forward(golden_dir):
+    """eps = (1 + w) eps_c - w eps_u of two reference NCSN++ networks (oracle/make_golden.py::golden_guidance)."""
+    g = np.load(f"{golden_dir}/forward_cfg_mid.npz")
+    fn = _guided_oracle(mid_config(), float(g["weight"]))
+    y = fn(torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=1e-5 * np.abs(g["y"]).max())
+    y0 = O.GuidedScoreFn(fn.cond, fn.uncond, 0.0)(torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
+    assert torch.equal(y0, fn.cond(torch.from_numpy(g["x"]), torch.from_numpy(g["t"])))   # w = 0: identity
+
+
+@pytest.mark.parametrize("kind", ["sscs_sde", "em_sde"])
+def test_guided_sampler(golden_dir, kind):
+    """The reference's own SSCS / EM sampler driven by the guided score_fn vs the oracle loop."""
+    g = np.load(f"{golden_dir}/sampler_cfg_tiny_{kind.split('_')[0]}40.npz")
+    cfg = tiny_config(sampler=kind, n_discrete_steps=40)
+    ts, n = O.time_grid(cfg)
+    B = int(g["B"])
+    u0 = prior((B, 3, 32, 32), 0.5, 1)
+    nb = noise_bank((2 if kind == "sscs_sde" else 1) * n, (B, 6, 32, 32), 2)
+    fn = O.sscs_sample if kind == "sscs_sde" else O.em_sample
+    out = fn(cfg, _guided_oracle(cfg, 1.5), u0, ts, n, nb)
+    ref = g["final"]
+    assert np.abs(out.numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
