@@ -82,6 +82,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   constexpr uint32_t QP_LO = 4u * AT_TILE;           // lo tiles of the QP region (kX3)
   constexpr uint32_t S_LO = AT_TILE;                 // lo half of a ring slot (kX3)
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger_early();
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();                        // SW128 atoms need 1024-byte alignment
   const uint32_t qp = base;

@@ -46,6 +46,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Memory-bound / tiny kernels trigger at their first instruction: the dependent grid is launched by
+// the hardware once EVERY block of this grid has started (so it never competes with unscheduled
+// blocks), its prologue (barrier init, TMEM allocation, descriptor prefetch) and launch latency then
+// overlap this kernel's last wave; correctness still rests on the dependent's pdl_wait().
+// -DPSLD_NO_EARLY_TRIGGER restores the implicit trigger at exit (A/B switch).
+__device__ __forceinline__ void pdl_trigger_early() {
+#ifndef PSLD_NO_EARLY_TRIGGER
+  pdl_launch_dependents();
+#endif
+}
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

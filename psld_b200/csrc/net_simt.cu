@@ -22,6 +22,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int HW,
                     int CP, int CW) {
+  pdl_trigger_early();
   pdl_wait();
   // only channels [0, CW) of the CP-wide rows are written (CW < CP: the rest keeps the zeros the
   // buffer was allocated with)
@@ -39,6 +40,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, in
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+  pdl_trigger_early();
   pdl_wait();
   const int64_t total = (int64_t)N * C * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -101,6 +103,7 @@ int run_layout(const psld_op& op, cudaStream_t s) {
 __global__ void __launch_bounds__(256)
 axpby_kernel(float* __restrict__ out, float a, const float* __restrict__ x, float b,
              const float* __restrict__ y, int64_t n) {
+  pdl_trigger_early();
   pdl_wait();
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -144,6 +147,7 @@ int run_axpby(const psld_op& op, cudaStream_t s) {
 __global__ void temb_embed_kernel(const float* __restrict__ t, const float* __restrict__ W,
                                   float* __restrict__ emb, int nt, int nf, int emb_type,
                                   int logged, const int* __restrict__ step_ptr) {
+  pdl_trigger_early();
   pdl_wait();
   if (step_ptr) t += *step_ptr;      // graph replay: t is a per-call table, the step lives on device
   const int E = emb_type == 0 ? 2 * nf : nf;
@@ -171,6 +175,7 @@ template <bool kSiluIn>
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ in, const float* __restrict__ W,
                    const float* __restrict__ b, float* __restrict__ out, int rows, int K, int O) {
+  pdl_trigger_early();
   pdl_wait();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -306,6 +311,7 @@ template <typename T, int VW>   // VW = channels per thread (8, or 4 when C % 8 
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ part,
                 int HW, int C1, int C2, int G, int nchunk) {
+  pdl_trigger_early();
   pdl_wait();
   extern __shared__ double sh[];  // [2*G]
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -405,6 +411,7 @@ gn_apply_kernel(const TI* __restrict__ x1, const TI* __restrict__ x2,
                 const double* __restrict__ mg2, const float* __restrict__ gamma,
                 const float* __restrict__ beta, TO* __restrict__ y, int HW, int C1, int C2, int G,
                 int nchunk, int nchunk_apply, float eps, int silu) {
+  pdl_trigger_early();
   pdl_wait();
   extern __shared__ float shf[];  // mean[G], rstd[G]
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -489,6 +496,7 @@ __global__ void __launch_bounds__(256)
 gn_affine_micro_kernel(const double* __restrict__ mg1, const double* __restrict__ mg2,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        float* __restrict__ affine, int HW, int C1, int C2, int G, float eps) {
+  pdl_trigger_early();
   pdl_wait();
   const int n = blockIdx.x;
   const int C = C1 + C2, cpg = C / G;
@@ -512,6 +520,7 @@ __global__ void __launch_bounds__(256)
 gn_affine_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ affine, int HW, int C, int G,
                  int nchunk, float eps) {
+  pdl_trigger_early();
   pdl_wait();
   extern __shared__ float shf[];  // mean[G], rstd[G]
   const int n = blockIdx.x;
@@ -620,6 +629,7 @@ template <typename T, int VW, int UP, int DOWN>
 __global__ void __launch_bounds__(256)
 fir_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C,
            int Cact, int OH, int OW, int up_rt, int down_rt, int pad0, int KH) {
+  pdl_trigger_early();
   pdl_wait();
   const int up = UP ? UP : up_rt, down = DOWN ? DOWN : down_rt;
   const int vpr = Cact / VW;      // only the first Cact channels are filtered (rest: left as is)
@@ -675,6 +685,7 @@ fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int 
                   int C, int OH, int OW, int up_x, int up_y, int down_x, int down_y, int pad_x0,
                   int pad_y0, int KH, int KW, int64_t sn, int64_t sy, int64_t sx, int64_t sc,
                   int64_t on, int64_t oyS, int64_t oxS, int64_t oc, int lo) {
+  pdl_trigger_early();
   pdl_wait();
   const int64_t total = (int64_t)N * OH * OW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -711,6 +722,7 @@ fir_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 fir_up2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W, int C) {
+  pdl_trigger_early();
   pdl_wait();
   const int vpr = C / 8;
   const int64_t total = (int64_t)N * H * W * vpr;
@@ -768,6 +780,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fir_down2_kernel(const T* __restrict__ x, T* __restrict__ y, FirTaps taps, int N, int H, int W,
                  int C) {
+  pdl_trigger_early();
   pdl_wait();
   const int vpr = C / 8;
   const int OH = H / 2, OW = W / 2, QH = OH / 2, QW = OW / 2;

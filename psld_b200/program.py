@@ -479,41 +479,7 @@ class Plan:
             aff0 = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W, affine_only=True)
             h = self.op_conv(x1, x2, m.Conv_0.weight, None, ks=3, temb_off=temb_off, affine=aff0)
             self._release_affine(aff0)
-            gn1 = self.fuse_gn_residual or os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
-            if gn1 and hasattr(m, "Conv_2"):
-                # blocks with a Conv_2 shortcut.  bf16: they keep the unfused Conv_1 (apply pass +
-                # conv_tc with the shortcut as K-extension): the fused kernel accepts the extension
-                # too, but its two big operand buffers cannot hide the load latency of one-tap chunks
-                # (measured +1.1 ms of conv for -0.64 ms of GroupNorm per step).  bf16x3: the fused
-                # kernel streams the shortcut tiles through a 3-slot ring of their own, so the
-                # extension costs what it costs in conv_tc and the apply pass goes away.
-                # PSLD_TC_FUSE_GN_EXT overrides either default.
-                gn1 = (os.environ.get("PSLD_TC_FUSE_GN_EXT", "1" if self.x3 else "0") == "1"
-                       and self._ext_fusable(h, x1, x2, m.out_ch))
-            if gn1 and self._gn_fusable(h, None, m.out_ch):
-                aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
-                b, b_aff = h, aff1
-            else:
-                b = self.op_gn(h, None, m.GroupNorm_1, True, H * W)
-                self._release(h)
-                b_aff = None
-            ext, sc = None, None
-            if hasattr(m, "Conv_2"):
-                if self._ext_fusable(b, x1, x2, m.out_ch):
-                    ext = (x1, x2, m.Conv_2.weight, m.Conv_2.bias)
-                else:
-                    sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
-            else:
-                assert x2 is None
-                sc = x1
-            out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
-                               out=self._new(N, H, W, m.out_ch), affine=b_aff, ext=ext)
-            if b_aff is not None:
-                self._release_affine(b_aff)
-            self._release(b)
-            if hasattr(m, "Conv_2") and sc is not None:
-                self._release(sc)
-            return out
+            return self._block_tail(m, h, x1, x2, scale)
         a = self.op_gn(x1, x2, m.GroupNorm_0, True, H * W)
         xs1, xs2 = x1, x2
         fir_tmp = []
@@ -536,24 +502,50 @@ class Plan:
             fir_tmp.append(xs1)
         h = self.op_conv(a, None, m.Conv_0.weight, None, ks=3, temb_off=temb_off)  # bias: see temb
         self._release(a)
-        b = self.op_gn(h, None, m.GroupNorm_1, True, h.shape[1] * h.shape[2])
-        self._release(h)
-        ext, sc = None, None
-        if hasattr(m, "Conv_2"):
-            if self._ext_fusable(b, xs1, xs2, m.out_ch):
-                ext = (xs1, xs2, m.Conv_2.weight, m.Conv_2.bias)
-            else:
-                sc = self.op_conv(xs1, xs2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
-        else:
-            assert xs2 is None
-            sc = xs1
-        out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
-                           out=self._new(*b.shape[:-1], m.out_ch), ext=ext)
-        self._release(b)
-        if hasattr(m, "Conv_2") and sc is not None:
-            self._release(sc)
+        out = self._block_tail(m, h, xs1, xs2, scale)
         for t in fir_tmp:
             self._release(t)
+        return out
+
+    def _block_tail(self, m, h, x1, x2, scale):
+        """act(GroupNorm_1(h)) -> Conv_1 (+ Conv_2 shortcut over cat(x1, x2) or identity skip) -> * scale
+        (layerspp.py:264-274).  ``h`` is consumed."""
+        N, H, W, _ = h.shape
+        has_sc = hasattr(m, "Conv_2")
+        gn1 = self.fuse_gn_residual or os.environ.get("PSLD_TC_FUSE_GN1", "1") == "1"
+        if gn1 and has_sc:
+            # blocks with a Conv_2 shortcut.  bf16: they keep the unfused Conv_1 (apply pass +
+            # conv_tc with the shortcut as K-extension): the fused kernel accepts the extension
+            # too, but its two big operand buffers cannot hide the load latency of one-tap chunks
+            # (measured +1.1 ms of conv for -0.64 ms of GroupNorm per step).  bf16x3: the fused
+            # kernel streams the shortcut tiles through a 3-slot ring of their own, so the
+            # extension costs what it costs in conv_tc and the apply pass goes away.
+            # PSLD_TC_FUSE_GN_EXT overrides either default.
+            gn1 = (os.environ.get("PSLD_TC_FUSE_GN_EXT", "1" if self.x3 else "0") == "1"
+                   and self._ext_fusable(h, x1, x2, m.out_ch))
+        if gn1 and self._gn_fusable(h, None, m.out_ch):
+            aff1 = self.op_gn(h, None, m.GroupNorm_1, True, H * W, affine_only=True)
+            b, b_aff = h, aff1
+        else:
+            b = self.op_gn(h, None, m.GroupNorm_1, True, H * W)
+            self._release(h)
+            b_aff = None
+        ext, sc = None, None
+        if has_sc:
+            if self._ext_fusable(b, x1, x2, m.out_ch):
+                ext = (x1, x2, m.Conv_2.weight, m.Conv_2.bias)
+            else:
+                sc = self.op_conv(x1, x2, m.Conv_2.weight, m.Conv_2.bias, ks=1, want_stats=False)
+        else:
+            assert x2 is None
+            sc = x1
+        out = self.op_conv(b, None, m.Conv_1.weight, m.Conv_1.bias, ks=3, residual=sc, scale=scale,
+                           out=self._new(N, H, W, m.out_ch), affine=b_aff, ext=ext)
+        if b_aff is not None:
+            self._release_affine(b_aff)
+        self._release(b)
+        if has_sc and sc is not None:
+            self._release(sc)
         return out
 
     def attnblock(self, m, x):
