@@ -119,6 +119,16 @@ class ClassifierFreeGuidance(nn.Module):
             setattr(self, k, getattr(self.cond, k, None))
         self._plans = {}
 
+    def __deepcopy__(self, memo):
+        import copy
+        return type(self)(cond=copy.deepcopy(self.cond, memo), uncond=copy.deepcopy(self.uncond, memo),
+                          weight=self.weight)
+
+    def load_state_dict(self, *a, **kw):
+        r = super().load_state_dict(*a, **kw)
+        self._plans = {}
+        return r
+
     @property
     def precision(self):
         return self.cond.precision

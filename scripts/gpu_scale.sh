@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU bench lines for BASELINE configs[2] (CIFAR-10, B_total = 2048, strong scaling) and
-# configs[3] (CelebA-64, B_total = 512) on N GPUs of one box:  N=<n> bash scripts/gpu_scale.sh
+# configs[3] (CelebA-64, B_total = 512) and configs[4] (WORKLOADS=cfg: classifier-free guidance, B_total = 1024) on N GPUs of one box:  N=<n> bash scripts/gpu_scale.sh
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -28,4 +28,5 @@ except Exception as e:
 for w in ${WORKLOADS:-cifar celeba}; do
   if [ "$w" = "cifar" ]; then run cifar2048 --batch-total 2048; fi
   if [ "$w" = "celeba" ]; then run celeba512 --workload celeba64 --batch-total 512; fi
+  if [ "$w" = "cfg" ]; then run cfg1024 --workload cifar10_cfg --batch-total 1024; fi
 done

@@ -274,6 +274,10 @@ def test_guided_program_vs_golden(golden_dir):
     keys = list(m.state_dict().keys())
     assert keys[0].startswith("cond.all_modules.") and keys[-1].startswith("uncond.all_modules.")
     assert len(keys) == 2 * len(NCSNpp(c2).state_dict())
+    import copy
+    m2 = copy.deepcopy(m)                       # main/eval/sample.py deep-copies the score_fn
+    assert m2.weight == 2.0 and m2.cond is not m.cond and list(m2.state_dict().keys()) == keys
+    m2.load_state_dict(m.state_dict())
     with pytest.raises(ValueError):
         ClassifierFreeGuidance(cond=nets[0], uncond=nets[0], weight=1.0)
     with pytest.raises(RuntimeError, match="CUDA"):
