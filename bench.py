@@ -312,12 +312,14 @@ def measure_tier(args, precision, ctx):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and B == 256 and args.workload == "cifar10":
             tj = json.load(open(tp)).get(precision, {})
-            ks = [tj["kernels"][k] for k in ("conv_tc_kernel", "conv_gn_tc_kernel") if k in tj.get("kernels", {})]
+            ks = [tj["kernels"][k] for k in ("conv_tc_kernel", "conv_gn_tc_kernel", "conv_gn_x3_kernel")
+                  if k in tj.get("kernels", {})]
             if ks:
                 traffic = sum(k["traffic_bytes_per_launch"] * k["launches"] for k in ks) / sum(k["launches"] for k in ks)
                 tsrc = tj["source"]
         roof = {"bound": "tensor",
-                "kernel": "conv_tc_kernel" + (" + conv_gn_tc_kernel" if "conv_tc_gn" in prof else "") +
+                "kernel": "conv_tc_kernel" + ((" + conv_gn_x3_kernel" if precision == "bf16x3" else " + conv_gn_tc_kernel")
+                                             if "conv_tc_gn" in prof else "") +
                           " (tcgen05 implicit-GEMM convolutions, " + TIER_DTYPE[precision] + ")",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sustained"],

@@ -22,6 +22,11 @@ if [ "${CAPTURES:-1}" = "1" ]; then
         -o gpurun_out/prof_x3_$s python scripts/one_op.py $s > gpurun_out/ncu_x3_$s.log 2>&1
     echo "x3 $s rc=$?"
   done
+  for s in ${SHAPES_X3_GN:-g32sc g16sc g32res}; do      # fused GroupNorm kernel of the split tier (incl. shortcut ring)
+    ONE_OP_X3=1 ONE_OP_REPS=4 timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv_gn -s 5 -c 1 -f \
+        -o gpurun_out/prof_x3_$s python scripts/one_op.py $s > gpurun_out/ncu_x3_$s.log 2>&1
+    echo "x3 $s rc=$?"
+  done
   for s in ${SHAPES_BF16:-g32cat g32 g16 c16 c8}; do
     ONE_OP_REPS=4 timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv -s 5 -c 1 -f \
         -o gpurun_out/prof_bf16_$s python scripts/one_op.py $s > gpurun_out/ncu_bf16_$s.log 2>&1
@@ -29,7 +34,7 @@ if [ "${CAPTURES:-1}" = "1" ]; then
   done
   # attention + GroupNorm apply + fused update out of a real step of each tier (first matching launch
   # after the warm-up window)
-  for tier in bf16x3 bf16; do
+  for tier in ${STEP_TIERS-bf16x3 bf16}; do
     for k in attn_tc gn_apply sscs_update; do
       timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:$k -s ${KSKIP:-3} -c 1 -f \
           -o gpurun_out/prof_${tier}_$k $STEP --precision $tier > gpurun_out/ncu_${tier}_$k.log 2>&1
@@ -42,7 +47,7 @@ if [ "${MEMCHECK:-1}" = "1" ]; then
       -m gpu tests/test_gpu_x3.py -k "conv_tc_x3 or conv_gn_fused or attention or memory_bound or split" > gpurun_out/memcheck_x3.log 2>&1
   echo "memcheck x3 rc=$? $(tail -n 1 gpurun_out/memcheck_x3.log)"
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -q --no-header -p no:cacheprovider \
-      -m gpu tests/test_gpu_kernels.py -k "conv_tc or conv_gn or attention_tc or groupnorm or fir" > gpurun_out/memcheck_kernels.log 2>&1
+      -m gpu tests/test_gpu_kernels.py tests/test_gpu_guidance.py -k "conv_tc or conv_gn or attention_tc or groupnorm or fir or axpby or guided_forward" > gpurun_out/memcheck_kernels.log 2>&1
   echo "memcheck kernels rc=$? $(tail -n 1 gpurun_out/memcheck_kernels.log)"
 fi
 if [ "${BENCH:-1}" = "1" ]; then

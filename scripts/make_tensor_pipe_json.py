@@ -16,7 +16,10 @@ tags = sys.argv[1:] or ["r2a"]
 DESC = {"c32t": "32x32 256->256 3x3 +temb", "c32cat": "32x32 512->256 3x3 +temb (largest class)",
         "c16": "16x16 256->256 3x3 +res", "c8": "8x8 256->256 3x3 +res", "qkv16": "16x16 256->768 1x1 (q|k|v)",
         "g32": "32x32 256->256 3x3 GroupNorm-on-load +temb", "g32cat": "32x32 512->256 3x3 GroupNorm-on-load +temb",
-        "g16": "16x16 256->256 3x3 GroupNorm-on-load +temb", "attn_tc": "attention 16x16 (+ fused NIN_3 projection)"}
+        "g16": "16x16 256->256 3x3 GroupNorm-on-load +temb",
+        "g32sc": "32x32 256->256 3x3 GroupNorm-on-load + fused 1x1 shortcut over 512 raw channels",
+        "g16sc": "16x16 256->256 3x3 GroupNorm-on-load + fused 1x1 shortcut over 512 raw channels",
+        "g32res": "32x32 256->256 3x3 GroupNorm-on-load +res", "attn_tc": "attention 16x16 (+ fused NIN_3 projection)"}
 out = {"bf16x3": {"captures": {}}, "bf16": {"captures": {}}}
 paths = [(t, p) for t in tags for p in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{t}_ncu_*.csv")))]
 for tag, path in paths:
