@@ -193,6 +193,12 @@ PSLD_API int psld_vp_em_update(void* x_out, const void* x_in, int state_dtype, f
 PSLD_API int psld_reverse_drift(double* out, const void* u, int state_dtype, const float* eps,
                                 const psld_score_step* coeffs /* host */, double score_scale,
                                 int64_t B, int64_t chw, psld_stream_t stream);
+/* The same drift for the VP-SDE baseline (vpsde.py:42-67; scripts_psld/ablations/uncond/cifar10/
+ * sample_uncond_vpsde_ode.sh): fbar = 0.5 beta x + g^2 score_scale (eps * neg_inv_std), x: [n] elements
+ * (n % 4 == 0) in state_dtype, coefficients = the psld_vp_step of this time (dt, gs unused). */
+PSLD_API int psld_vp_reverse_drift(double* out, const void* x, int state_dtype, const float* eps,
+                                   const psld_vp_step* coeffs /* host */, double score_scale, int64_t n,
+                                   psld_stream_t stream);
 /* out = y + h * sum_{j < terms} coef[j] K[j]; K = [terms, n] float64, coef on the HOST (terms <= 8);
  * out32 (optional) receives the float32 rounding of the same values (the float32-batch view of the
  * state = the next network input); out may be NULL when only out32 is wanted. */

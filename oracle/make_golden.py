@@ -246,6 +246,8 @@ def main():
         return golden_cc(R)
     if "--only-ode" in sys.argv:
         return golden_ode(R)
+    if "--only-ode-vp" in sys.argv:
+        return golden_ode_vp(R)
     if "--only-guidance" in sys.argv:
         return golden_guidance(R)
     if "--only-inpaint" in sys.argv:
@@ -284,6 +286,7 @@ def main():
     golden_state_dict_contract(R)
     golden_cc(R)
     golden_ode(R)
+    golden_ode_vp(R)
     golden_guidance(R)
 
 
@@ -363,6 +366,22 @@ def golden_ode(R):
         out = S.sample(u0.clone(), None, 0, denoise=den, eps=cfg.evaluation.eval_eps)
         print(tag, "nfe", S.nfe, out.dtype, "std of x", float(out[:, :3].std()))
         _save(f"sampler_bb_ode_gauss_{tag}.npz", final=out.double().numpy(), nfe=np.asarray(S.nfe),
+              B=np.asarray(B), tol=np.asarray(tol))
+
+
+def golden_ode_vp(R):
+    """bb_ode over the VP-SDE baseline (scripts_psld/ablations/uncond/cifar10/sample_uncond_vpsde_ode.sh):
+    the reference's own BBODESampler + VPSDE, exact Gaussian-data score, float32 and float64 batches."""
+    from oracle.weights import vp_gaussian_score_fn
+    for tag, tol, den, dt in [("tol1e-5", 1e-5, True, torch.float32), ("tol1e-4_f64_nodenoise", 1e-4, False, torch.float64)]:
+        cfg = vp_config(sampler=dict(name="bb_ode", solver="RK45", rtol=tol, atol=tol), denoise=den)
+        sde = R.get_module("sde", "vpsde")(cfg)
+        B = 3
+        x0 = prior((B, 3, 8, 8), 1.0, 1)[:, :3].contiguous().to(dt)
+        S = R.get_module("samplers", "bb_ode")(cfg, sde, vp_gaussian_score_fn(cfg))
+        out = S.sample(x0.clone(), None, 0, denoise=den, eps=cfg.evaluation.eval_eps)
+        print("vp", tag, "nfe", S.nfe, out.dtype, "std of x", float(out.std()))
+        _save(f"sampler_bb_ode_vp_gauss_{tag}.npz", final=out.double().numpy(), nfe=np.asarray(S.nfe),
               B=np.asarray(B), tol=np.asarray(tol))
 
 

@@ -280,7 +280,9 @@ def bb_ode_sample(config, score_fn, u0, rtol, atol, solver="RK45", denoise=True,
     that wrapper makes (torchdiffeq 0.2.3 is absent from the reference tree): float64 state on the
     host, ``(t, y)`` rounded to ``u0``'s dtype for every evaluation.  Returns ``(x, nfe)``."""
     from scipy.integrate import solve_ivp
-    sde = PSLDScalars(config)
+    vp = str(config.model.sde.name) == "vpsde"        # sample_uncond_vpsde_ode.sh: same sampler, VP-SDE
+    sde = VPScalars(config) if vp else PSLDScalars(config)
+    drift = vp_pflow_drift if vp else pflow_drift
     shape, dtype = u0.shape, u0.dtype
     nfe = [0]
 
@@ -289,7 +291,7 @@ def bb_ode_sample(config, score_fn, u0, rtol, atol, solver="RK45", denoise=True,
         tt = float(torch.tensor(t).to(dtype))
         u = torch.tensor(y).to(dtype).reshape(shape)
         with torch.no_grad():
-            return pflow_drift(sde, score_fn, u, tt).numpy().reshape(-1)
+            return drift(sde, score_fn, u, tt).numpy().reshape(-1)
 
     t_end = sde.T - eps
     sol = solve_ivp(fun, t_span=[0.0, t_end], y0=u0.numpy().reshape(-1), t_eval=np.asarray([0.0, t_end]),
@@ -297,7 +299,7 @@ def bb_ode_sample(config, score_fn, u0, rtol, atol, solver="RK45", denoise=True,
     x = torch.tensor(sol.y).T[-1].to(dtype).reshape(shape)
     if denoise:                                                    # ode.py:36-39,66-75
         with torch.no_grad():
-            x = x + pflow_drift(sde, score_fn, x, sde.T - eps) * eps
+            x = x + drift(sde, score_fn, x, sde.T - eps) * eps
         nfe[0] += 1
     return x, nfe[0]
 
@@ -418,6 +420,19 @@ def vp_reverse_drift(sde: VPScalars, score_fn, x: torch.Tensor, t: float):
     eps = score_fn(x.to(torch.float32), _tvec(x, float(np.float32(tau))))
     score = -eps.to(torch.float64) / sde.std(tau)                  # vpsde.py:27-28
     return 0.5 * beta * x + g ** 2 * score, g
+
+
+def vp_pflow_drift(sde: VPScalars, score_fn, x: torch.Tensor, t: float):
+    """``VPSDE.reverse_sde(x, t, score_fn, probability_flow=True)[0]`` (``vpsde.py:48-67``): beta_t and std
+    are float64 tensors in the reference, so a float32 state / eps promote before the first product; the
+    float64 score is halved."""
+    tau = sde.T - t
+    beta = sde.beta_t(tau)
+    g = math.sqrt(beta)
+    eps = score_fn(x.to(torch.float32), _tvec(x, float(np.float32(tau))))
+    score = 0.5 * (-eps.to(torch.float64) / sde.std(tau))
+    f = (-0.5 * beta) * x.to(torch.float64)
+    return -f + g ** 2 * score
 
 
 def vp_em_sample(config, score_fn, x0, ts, n, noise, denoise=True, eps=1e-3, record=None):

@@ -100,6 +100,8 @@ EXPORTS = {
                                         C.c_int64, C.c_void_p]),
     "psld_reverse_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(ScoreStep),
                                      C.c_double, C.c_int64, C.c_int64, C.c_void_p]),
+    "psld_vp_reverse_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VpStep),
+                                        C.c_double, C.c_int64, C.c_void_p]),
     "psld_rk_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int64, C.c_void_p]),
     "psld_rk_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int,

@@ -18,7 +18,10 @@
 // The three centre-column taps are issued first: the centre slot (where the raw tile lands) is
 // released after a third of a chunk's MMAs, so the next-but-one raw tile is in flight early.
 // An optional 1x1 "extension" over a second, un-normalised input (the block's Conv_2 shortcut)
-// adds one-tap chunks that bypass the transform (off by default in the plan: slower than conv_tc).
+// adds one-tap chunks that bypass the transform.  In THIS (bf16) kernel they travel through the two
+// big operand sets, whose latency a one-tap chunk cannot hide, so the bf16 plan keeps shortcut blocks
+// on conv_tc + an apply pass (PSLD_TC_FUSE_GN_EXT=1 forces them here); the split-bf16 kernel below
+// streams them through a ring of their own and takes them by default.
 //
 // Warps (640 threads): 0 = raw-tile TMA, 1 = MMA issuer (leader CTA) + TMEM allocator,
 // 2 = weight TMA, 3 idle, 4..11 = epilogue (shared with conv_tc), 12..19 = transform.

@@ -704,6 +704,32 @@ reverse_drift_kernel(double* __restrict__ out, const S* __restrict__ u, const fl
   }
 }
 
+// VP-SDE twin (vpsde.py:42-67 with probability_flow): f = (-0.5 beta) x, score = -eps / std, halved,
+// fbar = -f + g^2 score, all in float64 (beta_t, std are float64 tensors in the reference, so the
+// float32 state / eps promote before the first product).  x: [n] elements.
+template <typename S>
+__global__ void __launch_bounds__(256)
+vp_reverse_drift_kernel(double* __restrict__ out, const S* __restrict__ x, const float* __restrict__ eps,
+                        psld_vp_step c, double score_scale, int64_t n) {
+  pdl_wait();
+  const int64_t nvec = n >> 2;
+  const double nhb = -c.half_beta;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    St4<S> xs = load4<S>(x + 4 * v);
+    const float4 e = *reinterpret_cast<const float4*>(eps + 4 * v);
+    const float ea[4] = {e.x, e.y, e.z, e.w};
+    St4<double> f4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double f = nhb * (double)xs.v[i];
+      const double score = score_scale * ((double)ea[i] * c.neg_inv_std);
+      f4.v[i] = -f + c.g2 * score;
+    }
+    store4<double>(out + 4 * v, f4);
+  }
+}
+
 // out = y + h * sum_j coef[j] K[j]   (one Runge-Kutta stage / solution combination, float64), with
 // optional rounded copies: out32 (the state as a float32 batch sees it, and the network input).
 struct RkCoef { double c[8]; };
@@ -763,6 +789,23 @@ extern "C" int psld_reverse_drift(double* out, const void* u, int state_dtype, c
   else
     launch_pdl(reverse_drift_kernel<float>, dim3(grid), dim3(256), 0, s, 1, out, (const float*)u, eps,
                *coeffs, score_scale, B, chw);
+  PSLD_CHECK_LAUNCH();
+  return PSLD_OK;
+}
+
+extern "C" int psld_vp_reverse_drift(double* out, const void* x, int state_dtype, const float* eps,
+                                     const psld_vp_step* coeffs, double score_scale, int64_t n,
+                                     psld_stream_t stream) {
+  PSLD_CHECK_ARG(out && x && eps && coeffs && n > 0 && n % 4 == 0, "psld_vp_reverse_drift: bad arguments");
+  PSLD_CHECK_ARG(state_dtype == PSLD_F64 || state_dtype == PSLD_F32, "psld_vp_reverse_drift: state dtype");
+  const int grid = grid_for(n / 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (state_dtype == PSLD_F64)
+    launch_pdl(vp_reverse_drift_kernel<double>, dim3(grid), dim3(256), 0, s, 1, out, (const double*)x, eps,
+               *coeffs, score_scale, n);
+  else
+    launch_pdl(vp_reverse_drift_kernel<float>, dim3(grid), dim3(256), 0, s, 1, out, (const float*)x, eps,
+               *coeffs, score_scale, n);
   PSLD_CHECK_LAUNCH();
   return PSLD_OK;
 }

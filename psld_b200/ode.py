@@ -1,7 +1,8 @@
 """Black-box probability-flow ODE sampler on the fused sm_100a kernels.
 
 Drop-in for the reference's ``BBODESampler`` (``main/samplers/ode.py:8-76``; registry name
-``bb_ode``, used by ``scripts_psld/**/sample_uncond_psld_ode.sh`` with
+``bb_ode``, used by ``scripts_psld/**/sample_uncond_psld_ode.sh`` and, over the VP-SDE baseline, by
+``scripts_psld/ablations/uncond/cifar10/sample_uncond_vpsde_ode.sh`` with
 ``evaluation.sampler.{solver=RK45, rtol, atol}``):
 
   ``cls(config, sde, score_fn, corrector_fn=None)``
@@ -35,7 +36,7 @@ from . import _lib as L
 from .guidance import is_native
 from .registry import register_module
 from .samplers import Sampler
-from .schedule import PSLDSchedule, _fill_score, _score_rows
+from .schedule import PSLDSchedule, VPSchedule, _fill_score, _score_rows
 
 # Dormand-Prince 5(4) tableau (scipy.integrate._ivp.rk.RK45)
 _C = [0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0]
@@ -63,9 +64,12 @@ class BBODESampler(Sampler):
 
     def __init__(self, config, sde, score_fn, corrector_fn=None):
         super().__init__(config, sde, score_fn, corrector_fn=corrector_fn)
-        if str(getattr(sde, "type", "")) == "vpsde":
-            raise NotImplementedError("bb_ode_b200 is implemented for the PSLD SDE")
-        self.schedule = sde if isinstance(sde, PSLDSchedule) else PSLDSchedule.from_sde(sde)
+        # the VP-SDE baseline (state [B,C,H,W], vpsde.py:48-67) or PSLD (phase-space state [B,2C,H,W])
+        self.vp = isinstance(sde, VPSchedule) or str(getattr(sde, "type", "")) == "vpsde"
+        if self.vp:
+            self.schedule = sde if isinstance(sde, VPSchedule) else VPSchedule.from_sde(sde)
+        else:
+            self.schedule = sde if isinstance(sde, PSLDSchedule) else PSLDSchedule.from_sde(sde)
         self.nfe = 0
         s = config.evaluation.sampler
         get = (lambda k: s.get(k)) if hasattr(s, "get") else (lambda k: getattr(s, k))
@@ -103,9 +107,16 @@ class BBODESampler(Sampler):
         # torchdiffeq hands t over in the batch dtype (convert_func_to_numpy: torch.tensor(t).to(dtype))
         t_eff = float(np.float32(t)) if ctx["batch_f32"] else float(t)
         tau = torch.tensor([self.schedule.T - t_eff], dtype=torch.float64)
-        rows = _score_rows(self.schedule, tau, torch.ones(1, dtype=torch.float64))
-        co = L.ScoreStep()
-        _fill_score(co, self.schedule, rows, 0)
+        if self.vp:
+            beta = self.schedule.beta_t(tau)
+            co = L.VpStep()
+            co.half_beta = float(0.5 * beta[0])
+            co.g2 = float(torch.sqrt(beta)[0] ** 2)
+            co.neg_inv_std = float(-1.0 / self.schedule.std(tau)[0])
+        else:
+            rows = _score_rows(self.schedule, tau, torch.ones(1, dtype=torch.float64))
+            co = L.ScoreStep()
+            _fill_score(co, self.schedule, rows, 0)
         tau32 = tau.to(torch.float32)
         plan = ctx["plan"]
         if plan is not None:          # native network: net_in IS plan.x_in
@@ -114,8 +125,12 @@ class BBODESampler(Sampler):
             e = plan.eps
         else:
             e = self.score_fn(net_in, tau32.to(net_in.device).expand(B)).to(torch.float32).contiguous()
-        L.check(lib.psld_reverse_drift(L.ptr(out), L.ptr(u_state), sdt, L.ptr(e), C.byref(co), 0.5, B, chw,
-                                       stream), "psld_reverse_drift")
+        if self.vp:
+            L.check(lib.psld_vp_reverse_drift(L.ptr(out), L.ptr(u_state), sdt, L.ptr(e), C.byref(co), 0.5,
+                                              u_state.numel(), stream), "psld_vp_reverse_drift")
+        else:
+            L.check(lib.psld_reverse_drift(L.ptr(out), L.ptr(u_state), sdt, L.ptr(e), C.byref(co), 0.5, B, chw,
+                                           stream), "psld_reverse_drift")
         ctx["keep"] = (e, co)
 
     def sample(self, batch, ts, n_discrete_steps, denoise=True, eps=1e-3):
@@ -127,11 +142,11 @@ class BBODESampler(Sampler):
             dev = batch.device if batch.is_cuda else torch.device("cuda", torch.cuda.current_device())
         if dev.type != "cuda":
             raise RuntimeError("psld_b200 samplers run on CUDA only; there is no CPU path")
-        if batch.dim() != 4 or batch.shape[1] % 2:
+        if batch.dim() != 4 or (batch.shape[1] % 2 and not self.vp):
             raise ValueError(f"expected a [B,2C,H,W] phase-space batch, got {tuple(batch.shape)}")
-        B, C2, H, W = batch.shape
+        B, C2, H, W = batch.shape                       # C2 = the state's channel count (VP-SDE: C)
         chw = (C2 // 2) * H * W
-        if chw % 4:
+        if (batch.numel() if self.vp else chw) % 4:
             raise ValueError("C*H*W must be a multiple of 4")
         self._counter += 1
         n = batch.numel()

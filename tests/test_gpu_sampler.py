@@ -352,6 +352,44 @@ def test_bb_ode_sampler_vs_reference_golden(golden_dir, tag, tol, den):
     assert out.dtype == (torch.float64 if den else torch.float32)
 
 
+@pytest.mark.parametrize("tag,tol,den,dt", [("tol1e-5", 1e-5, True, torch.float32),
+                                            ("tol1e-4_f64_nodenoise", 1e-4, False, torch.float64)])
+def test_bb_ode_vp_sampler_vs_reference_golden(golden_dir, tag, tol, den, dt):
+    """bb_ode over the VP-SDE baseline (scripts_psld/ablations/uncond/cifar10/sample_uncond_vpsde_ode.sh): the
+    device RK45 driver + psld_vp_reverse_drift vs the reference's BBODESampler + VPSDE (same NFE count)."""
+    from _net import vp_config
+    from oracle.weights import vp_gaussian_score_fn
+    from psld_b200 import BBODESampler, VPSDE
+    g = np.load(f"{golden_dir}/sampler_bb_ode_vp_gauss_{tag}.npz")
+    cfg = vp_config(sampler=dict(name="bb_ode", solver="RK45", rtol=tol, atol=tol), denoise=den)
+    B = int(g["B"])
+    x0 = prior((B, 3, 8, 8), 1.0, 1)[:, :3].contiguous().to(dt)
+    S = BBODESampler(cfg, VPSDE(cfg), vp_gaussian_score_fn(cfg))
+    out = S.sample(x0.cuda(), None, 0, denoise=den, eps=cfg.evaluation.eval_eps)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["final"])
+    e, m = rel_l2(out, ref), max_rel(out, ref)
+    print(f"bb_ode VP {tag}: rel-L2 {e:.3e} max {m:.3e} nfe {S.nfe} (reference {int(g['nfe'])})")
+    assert S.nfe == int(g["nfe"]) and tuple(out.shape) == (B, 3, 8, 8)
+    assert e <= 1e-5 and m <= 1e-5
+
+
+def test_bb_ode_vp_with_network_vs_oracle():
+    """bb_ode + VP-SDE over the native NCSN++ program (in_ch = out_ch = 3, fp32 tier) vs the oracle."""
+    from _net import vp_config
+    from psld_b200 import BBODESampler, VPSDE
+    cfg = vp_config(sampler=dict(name="bb_ode", solver="RK45", rtol=1e-3, atol=1e-3))
+    cfg.data.image_size = 32
+    net, sd = make_net(cfg, "fp32")
+    x0 = prior((2, 3, 32, 32), 1.0, 1)[:, :3].contiguous()
+    S = BBODESampler(cfg, VPSDE(cfg), net)
+    out = S.sample(x0.cuda(), None, 0, denoise=True, eps=1e-3)
+    ref, nfe = O.bb_ode_sample(cfg, O.OracleScoreFn(cfg, sd), x0, 1e-3, 1e-3, denoise=True, eps=1e-3)
+    e = rel_l2(out, ref)
+    print(f"bb_ode VP + NCSN++ fp32: rel-L2 {e:.3e}, nfe {S.nfe} vs oracle {nfe}")
+    assert S.nfe == nfe and e <= 1e-4
+
+
 def test_bb_ode_with_network_vs_oracle():
     """bb_ode over the native NCSN++ program (tiny net, fp32 tier) vs the oracle's solve_ivp run."""
     from _net import ode_config

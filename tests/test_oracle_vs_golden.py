@@ -233,6 +233,25 @@ def test_bb_ode_sampler(golden_dir, tag, tol, den):
     assert np.abs(out.double().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
 
 
+VP_ODE_CASES = [("tol1e-5", 1e-5, True, torch.float32), ("tol1e-4_f64_nodenoise", 1e-4, False, torch.float64)]
+
+
+@pytest.mark.parametrize("tag,tol,den,dt", VP_ODE_CASES)
+def test_bb_ode_sampler_vp(golden_dir, tag, tol, den, dt):
+    """bb_ode over the VP-SDE baseline (sample_uncond_vpsde_ode.sh): oracle vs the reference's BBODESampler +
+    VPSDE (float32 and float64 batches)."""
+    from _net import vp_config
+    from oracle.weights import vp_gaussian_score_fn
+    g = np.load(f"{golden_dir}/sampler_bb_ode_vp_gauss_{tag}.npz")
+    cfg = vp_config(sampler=dict(name="bb_ode", solver="RK45", rtol=tol, atol=tol), denoise=den)
+    B = int(g["B"])
+    x0 = prior((B, 3, 8, 8), 1.0, 1)[:, :3].contiguous().to(dt)
+    out, nfe = O.bb_ode_sample(cfg, vp_gaussian_score_fn(cfg), x0, tol, tol, denoise=den, eps=cfg.evaluation.eval_eps)
+    ref = g["final"]
+    assert nfe == int(g["nfe"])
+    assert np.abs(out.double().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
 # ---------------------------------------------------------------- classifier-free guidance (configs[4])
 def _guided_oracle(cfg, w):
     from psld_b200 import NCSNpp
