@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-CTA phase timeline of conv_tc_kernel (library built with PSLD_NVCC_EXTRA=-DPSLD_TC_TRACE).
-    PSLD_NVCC_EXTRA=-DPSLD_TC_TRACE python -m psld_b200.build --force; python scripts/tc_trace.py c8 c16"""
+    PSLD_NVCC_EXTRA=-DPSLD_TC_TRACE python -m psld_b200.build --force; python scripts/tc_trace.py c8 c16
+    (ONE_OP_X3=1: split-bf16 operands)"""
 import ctypes as C
 import os
 import sys
@@ -25,10 +26,11 @@ def main():
     for name in sys.argv[1:]:
         hw, c1, c2, cout, ks, res, temb, stats, gn = one_op.SHAPES[name]
         B = one_op.B
-        x1 = torch.randn(B, hw, hw, c1, generator=g).to(dev, torch.bfloat16)
-        x2 = torch.randn(B, hw, hw, c2, generator=g).to(dev, torch.bfloat16) if c2 else None
+        act = (lambda t: _ops.to_split(t.to(dev))) if one_op.X3 else (lambda t: t.to(dev, torch.bfloat16))
+        x1 = act(torch.randn(B, hw, hw, c1, generator=g))
+        x2 = act(torch.randn(B, hw, hw, c2, generator=g)) if c2 else None
         w = torch.randn(cout, c1 + c2, ks, ks, generator=g) * 0.05
-        r = torch.randn(B, hw, hw, cout, generator=g).to(dev, torch.bfloat16) if res else None
+        r = act(torch.randn(B, hw, hw, cout, generator=g)) if res else None
         t = torch.randn(B, cout, generator=g).to(dev) if temb else None
         op, out, keep = _ops.conv_op(x1, x2, w, torch.randn(cout, generator=g), residual=r, temb=t,
                                      temb_bstride=cout if temb else 0, engine=L.ENGINE_TC, mg_stats=stats)
