@@ -222,6 +222,21 @@ def golden_full_size(R):
     golden_sampler(R, c, "sampler_celeba64_sscs20.npz", B=2, keep=1)
 
 
+def golden_full_length(R):
+    """BASELINE.json configs[1] at FULL length: the benchmarked CIFAR-10 NCSN++ through all 1000 SSCS steps of
+    the unmodified reference (B=2, init_scale=1, pre-drawn noise; ~6 min of CPU): per-step energies, probe
+    states and the final samples, i.e. the trajectory the bench times."""
+    c = cifar10_config(n_discrete_steps=1000, batch_size=2, n_samples=2)
+    c.model.score_fn.init_scale = 1.0
+    if "--celeba" not in sys.argv:
+        golden_sampler(R, c, "sampler_cifar10_sscs1000.npz", B=2, keep=2)
+        return
+    # configs[3] at full length (CelebA-64 NCSN++, B=1; ~25 min of CPU): `--only-full-length --celeba`
+    c = celeba64_config(n_discrete_steps=1000, batch_size=1, n_samples=1)
+    c.model.score_fn.init_scale = 1.0
+    golden_sampler(R, c, "sampler_celeba64_sscs1000.npz", B=1, keep=1)
+
+
 def golden_state_dict_contract(R):
     """Names and shapes of the REFERENCE module's state dict for the shipped architectures: the
     checkpoint contract (``ema_score_fn.all_modules.<i>...``, wrapper.py:30-31) the drop-in must keep."""
@@ -240,6 +255,8 @@ def main():
     R = load_reference()
     if "--only-full-size" in sys.argv:
         return golden_full_size(R)
+    if "--only-full-length" in sys.argv:
+        return golden_full_length(R)
     if "--only-contract" in sys.argv:
         return golden_state_dict_contract(R)
     if "--only-cc" in sys.argv:

@@ -384,6 +384,25 @@ def test_configs1_trajectory_vs_reference_golden(golden_dir, precision):
     assert e_l2 <= tol and e_mx <= 2 * tol and worst <= 2 * tol, (e_l2, e_mx, worst)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_configs1_full_length_vs_reference_golden(golden_dir, precision):
+    """BASELINE.json configs[1] at FULL length: all 1000 SSCS steps of the benchmarked CIFAR-10 NCSN++ against the
+    trajectory of the unmodified reference (oracle/make_golden.py::golden_full_length, B = 2, init_scale = 1,
+    pre-drawn noise): per-step energy of all 1000 states, probe states and the final samples."""
+    g = np.load(f"{golden_dir}/sampler_cifar10_sscs1000.npz")
+    cfg = _full(cifar10_config(n_discrete_steps=1000, batch_size=2, n_samples=2))
+    net, _ = make_net(cfg, precision)
+    assert int(g["n"]) == 999
+    u0, nb = sampler_inputs(cfg, int(g["B"]), int(g["n"]), "sscs_sde")
+    out, rec = _run(cfg, "sscs_sde", net, u0, nb)
+    e_l2, e_mx, worst = _traj_errors(g, out, rec)
+    print(f"configs[1] SSCS 1000 NFE {precision}: final rel-L2 {e_l2:.3e} max-abs/max|ref| {e_mx:.3e} "
+          f"worst per-step {worst:.3e}")
+    # measured on B200: fp32 2.5e-7 / 3.4e-7, bf16x3 1.2e-5 / 1.7e-5, bf16 3.6e-3 / 4.0e-3
+    tol = {"fp32": 2e-6, "bf16x3": 5e-5, "bf16": 8e-3}[precision]
+    assert e_l2 <= tol and e_mx <= 2 * tol and worst <= 2 * tol, (e_l2, e_mx, worst)
+
+
 def test_configs3_trajectory_vs_reference_golden(golden_dir):
     """BASELINE.json configs[3] (CelebA-64 NCSN++, SSCS): 20-NFE reference trajectory, bf16x3 tier."""
     g = np.load(f"{golden_dir}/sampler_celeba64_sscs20.npz")
