@@ -440,6 +440,14 @@ def golden_guidance(R):
         yc = fc(x, t)
     _save("forward_cfg_mid.npz", x=x.numpy(), t=t.numpy(), y=y.numpy(), y_cond=yc.numpy(),
           seeds=np.asarray([0, 1]), weight=np.asarray(CFG_WEIGHT))
+    if "--full-size" in sys.argv:
+        # configs[4] at full architecture size: two CIFAR-10 NCSN++ (init_scale = 1, weight seeds 0 / 1), SSCS,
+        # 100 NFE, B = 1 through the reference's own sampler (~3 min of CPU): `--only-guidance --full-size`
+        c = cifar10_config(n_discrete_steps=100, batch_size=1, n_samples=1)
+        c.model.score_fn.init_scale = 1.0
+        fc, fu = ref_net(R, c, 0)[0], ref_net(R, c, 1)[0]
+        golden_sampler(R, c, "sampler_cfg_cifar10_sscs100.npz", B=1, keep=1, score=guided(fc, fu, CFG_WEIGHT))
+        return
     # trajectory: the reference's own SSCS / EM samplers driven by the guided score_fn
     for name in ("sscs_sde", "em_sde"):
         cfg = tiny_config(sampler=name, n_discrete_steps=40)

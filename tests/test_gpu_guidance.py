@@ -92,6 +92,30 @@ def test_guided_sampler_vs_reference_golden(golden_dir, kind, precision, tol):
     assert n2 == n and S.nfe == n and e <= tol
 
 
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 5e-5), ("bf16", 1.5e-2)])      # measured 1.6e-5 / 5.9e-3
+def test_guided_full_size_trajectory_vs_reference_golden(golden_dir, precision, tol):
+    """BASELINE configs[4] at full architecture size: two CIFAR-10 NCSN++ (97.6 M parameters each, init_scale = 1),
+    guidance weight 1.5, 100 SSCS steps of the reference's own sampler driven by the composition of the two
+    unmodified reference networks (oracle/make_golden.py --only-guidance --full-size)."""
+    from psld_b200 import cifar10_config
+    g = np.load(f"{golden_dir}/sampler_cfg_cifar10_sscs100.npz")
+    cfg = cifar10_config(n_discrete_steps=100, batch_size=1, n_samples=1)
+    cfg.model.score_fn.init_scale = 1.0
+    net, _, _ = _guided(cfg, precision)
+    n = int(g["n"])
+    u0, nb = sampler_inputs(cfg, int(g["B"]), n, "sscs_sde")
+    S = SSCSSampler(cfg, PSLD(cfg), net)
+    S.use_graph, S.fuse_halves = False, False
+    S.noise = torch.stack(nb).cuda()
+    ts, n2 = time_grid(cfg)
+    out = S.sample(u0.cuda(), ts.cuda(), n2, denoise=True, eps=1e-3)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["final"])
+    e, m = rel_l2(out, ref), max_rel(out, ref)
+    print(f"guided CIFAR-10 SSCS 100 NFE ({precision}): final rel-L2 {e:.3e} max-abs/max|ref| {m:.3e}")
+    assert n2 == n and e <= tol and m <= 2 * tol
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_guidance_weight_zero_is_the_unguided_sampler(precision):
     """with w = 0 the two-pass sampler reproduces the one-network sampler bit for bit

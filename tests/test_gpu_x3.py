@@ -403,6 +403,22 @@ def test_configs1_full_length_vs_reference_golden(golden_dir, precision):
     assert e_l2 <= tol and e_mx <= 2 * tol and worst <= 2 * tol, (e_l2, e_mx, worst)
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_configs3_full_length_vs_reference_golden(golden_dir, precision):
+    """BASELINE.json configs[3] at FULL length: all 1000 SSCS steps of the CelebA-64 NCSN++ (B = 1) against the
+    unmodified reference (oracle/make_golden.py --only-full-length --celeba)."""
+    g = np.load(f"{golden_dir}/sampler_celeba64_sscs1000.npz")
+    cfg = _full(celeba64_config(n_discrete_steps=1000, batch_size=1, n_samples=1))
+    net, _ = make_net(cfg, precision)
+    u0, nb = sampler_inputs(cfg, int(g["B"]), int(g["n"]), "sscs_sde")
+    out, rec = _run(cfg, "sscs_sde", net, u0, nb)
+    e_l2, e_mx, worst = _traj_errors(g, out, rec)
+    print(f"configs[3] SSCS 1000 NFE {precision}: final rel-L2 {e_l2:.3e} max-abs/max|ref| {e_mx:.3e} "
+          f"worst per-step {worst:.3e}")
+    tol = {"bf16x3": 5e-5, "bf16": 8e-3}[precision]      # measured 8.3e-6 / 3.8e-3
+    assert e_l2 <= tol and e_mx <= 2 * tol and worst <= 2 * tol, (e_l2, e_mx, worst)
+
+
 def test_configs3_trajectory_vs_reference_golden(golden_dir):
     """BASELINE.json configs[3] (CelebA-64 NCSN++, SSCS): 20-NFE reference trajectory, bf16x3 tier."""
     g = np.load(f"{golden_dir}/sampler_celeba64_sscs20.npz")
