@@ -28,7 +28,6 @@ namespace psld {
 
 constexpr int AT_TILE = 128 * 64 * 2;           // one operand tile: 128 rows x 64 bf16 (128 B rows, SW128)
 constexpr int AT_RING = 3;                      // ring slots
-constexpr int AT_THREADS = 192;
 
 // Shared-memory plan (v2).  Everything is a [<=128 rows x 64 columns] bf16 tile of 16 KB:
 //   QP region  4 tiles : the Q channel chunks during S = Q K^T, then P (4 key chunks, written by the
@@ -49,10 +48,24 @@ struct AtCfg {
   static constexpr int kMul = kX3 ? 2 : 1;
   static constexpr int kQP = 4 * AT_TILE * kMul;             // hi tiles, then lo tiles
   static constexpr int kSlot = AT_TILE * kMul;               // hi | lo
-  static constexpr int kSmem = kQP + AT_RING * kSlot + 256;  // + barriers; the window must start on
+  // kX3 (one CTA per SM, nothing else overlaps its serial phases): TWO warps per TMEM lane quarter share the
+  // softmax, the O normalisation and the projection epilogue of a query row (columns / channels / column
+  // groups split in two; row max and row sum are exchanged through 2 KB of shared memory)
+  static constexpr int kParts = kX3 ? 2 : 1;
+  static constexpr int kThreads = 64 + 128 * kParts;         // TMA warp, MMA warp, 4 * kParts softmax warps
+  static constexpr int kXchg = kX3 ? 2048 : 0;               // row max / row sum exchange [2][2][128] floats
+  static constexpr int kSmem = kQP + AT_RING * kSlot + 256 + kXchg;  // + barriers; the window must start on
                                                              // a 1024-byte boundary (it does; trap otherwise)
   static constexpr int kMinBlocks = kX3 ? 1 : 2;
 };
+
+// Optional per-CTA phase timeline (build with -DPSLD_TC_TRACE; scripts/attn_trace.py reads it)
+#ifdef PSLD_TC_TRACE
+__device__ long long g_at_trace[1024 * 8];
+#define AT_TRACE(slot) do { if ((threadIdx.x & 31) == 0) { const int b_ = blockIdx.y * gridDim.x + blockIdx.x; if (b_ < 1024) g_at_trace[b_ * 8 + (slot)] = clock64(); } } while (0)
+#else
+#define AT_TRACE(slot) do { } while (0)
+#endif
 
 struct AttnTcParams {
   __nv_bfloat16* out;
@@ -75,7 +88,7 @@ struct AttnTcState {
 //   h = (NIN_3(O / rowsum) + x) * scale; the conv epilogue (bias, residual, scale, store, GroupNorm
 //   statistics) finishes the tile: no O round trip through HBM, no separate 1x1 convolution launch.
 template <bool kProj, bool kX3>
-__global__ void __launch_bounds__(AT_THREADS, AtCfg<kX3>::kMinBlocks)
+__global__ void __launch_bounds__(AtCfg<kX3>::kThreads, AtCfg<kX3>::kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmW, const AttnTcParams p) {
   using Cfg = AtCfg<kX3>;
@@ -83,6 +96,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   constexpr uint32_t S_LO = AT_TILE;                 // lo half of a ring slot (kX3)
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger_early();
+  if (threadIdx.x == 0) AT_TRACE(0);
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();                        // SW128 atoms need 1024-byte alignment
   const uint32_t qp = base;
@@ -99,7 +113,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_slot = q_full + 48u;
   // kProj epilogue: staging tiles + additive vectors alias the (by then idle) ring
   const uint32_t stg_base = ring;
-  const uint32_t addv_base = ring + 4u * 4096u;
+  const uint32_t addv_base = ring + 8u * 4096u;
+  constexpr int kParts = Cfg::kParts;
+  float* xchg = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - base));   // kX3: [max | sum][part][row]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
@@ -120,9 +136,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 128 * kParts);
     mbar_init(o_full, 1);
-    mbar_init(o_ready, 128);
+    mbar_init(o_ready, 128 * kParts);
     mbar_init(y_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,6 +223,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                ((uint32_t)(128 >> 4) << 24);
       mbar_wait(q_full, 0);
       tc_fence_after();
+      AT_TRACE(1);
       for (int c = 0; c < nck; ++c)
         for (int h = 0; h < nkh; ++h) {
           mbar_wait(full_bar(slot), phase);
@@ -273,19 +290,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    // kParts == 2: warps 2..5 take the first half of the keys / channels / column groups, warps 6..9 the
+    // second; the two warps of a lane quarter meet on named barrier 2 + quarter (64 threads)
+    const int part = kParts == 2 ? (warp >= 6 ? 1 : 0) : 0;
+    const int k_lo = part * (p.HW / kParts), k_hi = k_lo + p.HW / kParts;
+    const int c_lo = part * (p.C / kParts), c_hi = c_lo + p.C / kParts;
+    auto pair_sync = [&]() {
+      if (kParts == 2) asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+    };
     mbar_wait(s_full, 0);
     tc_fence_after();
+    if (warp == 2) AT_TRACE(2);
     float mx = -INFINITY;
-    for (int ch = 0; ch < p.HW; ch += 32) {
+    for (int ch = k_lo; ch < k_hi; ch += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
+    if (kParts == 2) {
+      xchg[part * 128 + row] = mx;
+      pair_sync();
+      mx = fmaxf(mx, xchg[(part ^ 1) * 128 + row]);
+    }
     const float mxs = mx * p.scale_log2;
     float sum = 0.f;
-    for (int ch = 0; ch < p.HW; ch += 32) {
+    for (int ch = k_lo; ch < k_hi; ch += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
       tmem_ld_wait();
@@ -321,15 +352,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     mbar_arrive(p_ready);
+    if (warp == 2) AT_TRACE(3);
+    if (kParts == 2) {
+      xchg[256 + part * 128 + row] = sum;
+      pair_sync();
+      sum += xchg[256 + (part ^ 1) * 128 + row];
+    }
     const float inv = 1.0f / sum;
     mbar_wait(o_full, 0);
     tc_fence_after();
+    if (warp == 2) AT_TRACE(4);
     const int q = q0 + row;
     const bool valid = q < p.HW;
     if (kProj) {
       // normalised O -> (split) bf16 in the QP region, same swizzled K-major tiles (tile = ch / 64);
       // P was last read by MMAs that completed before o_full
-      for (int ch = 0; ch < p.C; ch += 32) {
+      for (int ch = c_lo; ch < c_hi; ch += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
         tmem_ld_wait();
@@ -353,18 +391,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(o_ready);
+      if (warp == 2) AT_TRACE(5);
       mbar_wait(y_full, 0);
       tc_fence_after();
+      if (warp == 2) AT_TRACE(6);
       const int m_tile = n * (p.HW >> 7) + (int)blockIdx.x;
-      const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5
+      const int ew = warp - 2;                     // softmax / epilogue warps are warps 2..5 (kX3: 2..9)
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half)
+      for (int half = (kParts == 2 ? part : 0); half < (kParts == 2 ? part + 1 : 2); ++half)
         tc_epilogue_tile<true, kX3 ? 32 : 64, !kX3, kX3>(p.ep, tmem_acc, 0, m_tile, 0, p.ep.block_n, quarter, half, lane,
                                                          stg_base + (uint32_t)ew * 4096u,
                                                          addv_base + (uint32_t)ew * 256u, []() {}, []() {});
     } else {
       __nv_bfloat16* orow = p.out + ((int64_t)n * p.HW + q) * (p.C * (kX3 ? 2 : 1));
-      for (int ch = 0; ch < p.C; ch += 32) {
+      for (int ch = c_lo; ch < c_hi; ch += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_acc + lane_addr + (uint32_t)ch, r);
         tmem_ld_wait();
@@ -390,12 +430,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) AT_TRACE(7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                  ::"r"(tmem_acc), "n"(256) : "memory");
   }
 }
+
+#ifdef PSLD_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int psld_debug_attn_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_at_trace, sizeof(g_at_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---------------------------------------------------------------- host side
 static int encode_qkv_map(CUtensorMap* tm, const void* ptr, int N, int HW, int C3, int rows) {
@@ -508,7 +555,7 @@ int run_attn_tc(const psld_op& op, cudaStream_t s) {
   const AttnTcState* st = (const AttnTcState*)op.aux;
   PSLD_CHECK_ARG(st != nullptr, "attn_tc: op not prepared (call psld_op_prepare)");
 #define ATTN_LAUNCH(PROJ, X3)                                                                  \
-  PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<PROJ, X3>, st->grid, dim3(AT_THREADS),                \
+  PSLD_CHECK_CUDA(launch_pdl(attn_tc_kernel<PROJ, X3>, st->grid, dim3(AtCfg<X3>::kThreads),       \
                              AtCfg<X3>::kSmem, s, 1, st->tq, st->tkv,                              \
                              st->tw, st->p))
   if (st->proj) { if (st->x3) ATTN_LAUNCH(true, true); else ATTN_LAUNCH(true, false); }
